@@ -1,0 +1,617 @@
+"""CPU restatement of the tf-kaldi-speaker x-vector hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is the *checker* for the CUDA path, never the thing shipped or measured
+(except as the labelled ``cpu_baseline`` / ``--impl reference`` arm of ``bench.py``).
+It restates, in plain PyTorch-CPU (fp64 by default, fp32 for the timed CPU baseline),
+the arithmetic of these reference files (paths relative to /root/reference):
+
+  model/tdnn.py:33-191               network topology, variable names, defaults
+  model/pooling.py:22-32             statistics_pooling
+  model/multitask_v1/pooling.py:22-38  length-masked statistics pooling (statistics_pooling_v2)
+  model/pooling.py:78-189            self_attention (multi-head attentive statistics + penalty)
+  model/common.py:27-58,113-265      prelu, l2_scaling, dense_* helpers, split_heads
+  model/loss.py:29-35,97-159,207-247,293-345   softmax / asoftmax / AM / AAM heads
+  model/trainer.py:168-188           entire_network (feature_norm -> l2_scaling)
+  model/trainer.py:261-303           validation-time margin neutralisation
+  model/trainer.py:328-358,403-436   optimizer, total loss, gradient clipping, BN update deps
+  egs/voxceleb/v1/nnet/lib/extract.py:65-94    chunk-and-average extraction rule
+
+Parity pinning status (see DESIGN.md "Oracle"):
+  * margin heads (asoftmax m=1,2,4 / AM / AAM, feature_norm on/off): PINNED against the reference's own
+    NumPy known-answer functions model/test_utils.py:157-318 on the reference's adversarial inputs
+    (model/tdnn.py:254-343) -- tests/test_oracle_vs_reference.py imports them from /root/reference and
+    tests/golden/heads_*.npz holds the committed vectors made by tests/golden/make_golden.py.
+  * length-masked statistics pooling: PINNED against model/multitask_v1/pooling.py:68-83 (restated inline
+    NumPy check, golden vectors committed).
+  * self-attention pooling: weakly pinned against model/test_utils.py:321-376 (py2 integer division fixed).
+  * TDNN conv/dense/BN forward, unmasked statistics_pooling, all backward passes, optimizer and BN
+    moving-stat updates, plain softmax head, extraction averaging: "parity unpinned" -- the reference
+    holds no known-answer test for them and TensorFlow 1.x (un-vendored, unpinned; README.md:31-34) cannot
+    run in this image.  They are restated here from the cited lines plus the TF-1.12 documented defaults
+    (BN eps 1e-3, valid padding, glorot-uniform init, mean-reduced sparse softmax xent, l2_normalize eps
+    1e-12, l2_regularizer = s*sum(w^2)/2, leaky_relu alpha 0.2).
+
+Gradients: the reference never writes a backward pass (trainer.py:403 uses TF autodiff and its tests only
+assert "not NaN"), so PyTorch autograd on this fp64 restatement is the gradient oracle.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+VAR2STD_EPSILON = 1e-12   # model/pooling.py:6
+BN_EPSILON = 1e-3         # tf.layers.batch_normalization default
+
+
+# --------------------------------------------------------------------------------------
+# Params: stand-in for misc/utils.py:13-61 (the original imports TensorFlow at module top)
+# --------------------------------------------------------------------------------------
+class ParamsPlain(object):
+    """Attribute bag with a ``.dict`` view, as misc/utils.py:44-61."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def dict(self):
+        return self.__dict__
+
+
+# --------------------------------------------------------------------------------------
+# Parameter schema / initialisation (TF variable names are the keys)
+# --------------------------------------------------------------------------------------
+def _glorot_uniform(shape, gen):
+    """TF glorot_uniform / xavier_initializer(uniform=True): limit = sqrt(6/(fan_in+fan_out))."""
+    if len(shape) == 2:
+        fan_in, fan_out = shape
+    else:  # conv kernel [1, k, Cin, Cout]
+        rf = shape[0] * shape[1]
+        fan_in, fan_out = rf * shape[2], rf * shape[3]
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * limit
+
+
+def frame_layer_specs(dim, params):
+    """[(name, kind, k, Cin, Cout)] for tdnn1..5 (model/tdnn.py:39-127)."""
+    p = params.dict.get("num_nodes_pooling_layer", 1500)
+    return [("tdnn1", "conv", 5, dim, 512), ("tdnn2", "conv", 5, 512, 512), ("tdnn3", "conv", 7, 512, 512),
+            ("tdnn4", "dense", 1, 512, 512), ("tdnn5", "dense", 1, 512, p)]
+
+
+def pooling_output_dim(params):
+    p = params.dict.get("num_nodes_pooling_layer", 1500)
+    if params.pooling_type == "statistics_pooling":
+        return 2 * p
+    if params.pooling_type == "self_attention":
+        nodes = list(params.att_value_num_nodes)
+        dv = nodes[-1] if len(nodes) > 0 else _endpoint_dim(params.att_value_input, params)
+        return 2 * dv
+    raise NotImplementedError("Not implement %s pooling" % params.pooling_type)
+
+
+def _endpoint_dim(name, params):
+    p = params.dict.get("num_nodes_pooling_layer", 1500)
+    return p if name.startswith("tdnn5") else 512
+
+
+def init_params(dim, params, num_speakers=None, loss_type=None, seed=0, dtype=torch.float64):
+    """Create every variable of the graph with TF's default initialisers (Appendix B)."""
+    gen = torch.Generator().manual_seed(seed)
+    P = OrderedDict()
+    relu_type = params.dict.get("network_relu_type", "relu")
+
+    def bn(prefix, c):
+        P[prefix + "/gamma"] = torch.ones(c, dtype=torch.float64)
+        P[prefix + "/beta"] = torch.zeros(c, dtype=torch.float64)
+        P[prefix + "/moving_mean"] = torch.zeros(c, dtype=torch.float64)
+        P[prefix + "/moving_variance"] = torch.ones(c, dtype=torch.float64)
+
+    def alpha(prefix, c):
+        if relu_type == "prelu":
+            P[prefix + "/alpha"] = torch.full((c,), 0.01, dtype=torch.float64)
+
+    for name, kind, k, cin, cout in frame_layer_specs(dim, params):
+        if kind == "conv":
+            P["tdnn/%s_conv/kernel" % name] = _glorot_uniform((1, k, cin, cout), gen)
+            P["tdnn/%s_conv/bias" % name] = torch.zeros(cout, dtype=torch.float64)
+        else:
+            P["tdnn/%s_dense/kernel" % name] = _glorot_uniform((cin, cout), gen)
+            P["tdnn/%s_dense/bias" % name] = torch.zeros(cout, dtype=torch.float64)
+        bn("tdnn/%s_bn" % name, cout)
+        alpha("tdnn/%s_relu" % name, cout)
+
+    if params.pooling_type == "self_attention":
+        def net(kind, in_dim, nodes, last_type):
+            d = in_dim
+            for i, n in enumerate(nodes):
+                scope = "tdnn/attention/att_%s%d" % (kind, i)
+                P["%s/att_%s%d_dense/kernel" % (scope, kind, i)] = _glorot_uniform((d, n), gen)
+                P["%s/att_%s%d_dense/bias" % (scope, kind, i)] = torch.zeros(n, dtype=torch.float64)
+                is_last = (i == len(nodes) - 1)
+                if (not is_last) or last_type == 2:
+                    bn("%s/att_%s%d_bn" % (scope, kind, i), n)
+                if ((not is_last) or last_type in (1, 2)):
+                    alpha("%s/att_%s%d_relu" % (scope, kind, i), n)
+                d = n
+            return d
+        dk = net("key", _endpoint_dim(params.att_key_input, params), list(params.att_key_num_nodes),
+                 params.att_key_network_type)
+        dv = _endpoint_dim(params.att_value_input, params)
+        if len(params.att_value_num_nodes) > 0:
+            dv = net("value", dv, list(params.att_value_num_nodes), params.att_value_network_type)
+        h = params.att_num_heads
+        qd = dk // h if params.att_split_key else dk
+        q = torch.empty(h, qd, dtype=torch.float64)
+        torch.nn.init.trunc_normal_(q, mean=0.0, std=0.1, a=-0.2, b=0.2, generator=gen)
+        P["tdnn/attention/query"] = q
+        if params.dict.get("att_apply_nonlinear", False):
+            bn("tdnn/attention/att_post_bn", 2 * dv)
+            alpha("tdnn/attention/att_post_relu", 2 * dv)
+
+    pool_dim = pooling_output_dim(params)
+    P["tdnn/tdnn6_dense/kernel"] = _glorot_uniform((pool_dim, 512), gen)
+    P["tdnn/tdnn6_dense/bias"] = torch.zeros(512, dtype=torch.float64)
+    bn("tdnn/tdnn6_bn", 512)
+    alpha("tdnn/tdnn6_relu", 512)
+    e = params.dict.get("num_nodes_last_layer", 512)
+    P["tdnn/tdnn7_dense/kernel"] = _glorot_uniform((512, e), gen)
+    P["tdnn/tdnn7_dense/bias"] = torch.zeros(e, dtype=torch.float64)
+    if not params.dict.get("last_layer_no_bn", False):
+        bn("tdnn/tdnn7_bn", e)
+    if not params.dict.get("last_layer_linear", False):
+        alpha("tdnn/tdnn7_relu", e)
+
+    if num_speakers is not None:
+        P["softmax/output/kernel"] = _glorot_uniform((e, num_speakers), gen)
+        if loss_type == "softmax":
+            P["softmax/output/bias"] = torch.zeros(num_speakers, dtype=torch.float64)
+    return OrderedDict((k, v.to(dtype)) for k, v in P.items())
+
+
+def trainable_names(P):
+    return [k for k in P if not (k.endswith("moving_mean") or k.endswith("moving_variance"))]
+
+
+def l2_regularised(name):
+    """L2 applies to kernels only (model/tdnn.py:43, model/common.py:136, model/loss.py:33,102)."""
+    return name.endswith("/kernel")
+
+
+# --------------------------------------------------------------------------------------
+# Building blocks
+# --------------------------------------------------------------------------------------
+def _activation(x, P, prefix, relu_type):
+    """relu / prelu (model/common.py:27-42) / leaky_relu alpha=0.2 (model/tdnn.py:25-30)."""
+    if relu_type == "prelu":
+        a = P[prefix + "/alpha"]
+        return F.relu(x) + a * (x - x.abs()) * 0.5
+    if relu_type == "lrelu":
+        return F.leaky_relu(x, 0.2)
+    return F.relu(x)
+
+
+def batch_norm(x, P, prefix, momentum, is_training, updates, unbiased_moving_var=False):
+    """tf.layers.batch_normalization, axis=-1, eps=1e-3.  Training: biased batch statistics over all
+    leading axes; moving <- moving*m + batch*(1-m).  The fused rank-4 TF path (tdnn1-3) updates
+    moving_variance with the unbiased batch variance; the unfused rank-2/3 path with the biased one."""
+    g, b = P[prefix + "/gamma"], P[prefix + "/beta"]
+    if is_training:
+        xr = x.reshape(-1, x.shape[-1])
+        n = xr.shape[0]
+        mean = xr.mean(0)
+        var = ((xr - mean) ** 2).mean(0)
+        if updates is not None:
+            with torch.no_grad():
+                mv = var * (n / max(n - 1, 1)) if unbiased_moving_var else var
+                updates[prefix + "/moving_mean"] = P[prefix + "/moving_mean"] * momentum + mean * (1 - momentum)
+                updates[prefix + "/moving_variance"] = P[prefix + "/moving_variance"] * momentum + mv * (1 - momentum)
+    else:
+        mean, var = P[prefix + "/moving_mean"], P[prefix + "/moving_variance"]
+    return (x - mean) * torch.rsqrt(var + BN_EPSILON) * g + b
+
+
+def temporal_conv(x, kernel, bias):
+    """tf.layers.conv2d(features[b,1,l,d], Cout, (1,k)) with 'valid' padding, stride 1 (tdnn.py:39-44)."""
+    k, cin, cout = kernel.shape[1], kernel.shape[2], kernel.shape[3]
+    w = kernel[0].permute(2, 1, 0)              # [Cout, Cin, k]
+    y = F.conv1d(x.transpose(1, 2), w, bias)    # [B, Cout, T-k+1]
+    return y.transpose(1, 2)
+
+
+def statistics_pooling(x, lengths=None):
+    """model/pooling.py:22-32; with ``lengths`` the masked form of multitask_v1/pooling.py:22-38."""
+    if lengths is None:
+        mean = x.mean(1, keepdim=True)
+        var = ((x - mean) ** 2).mean(1)
+        mean = mean.squeeze(1)
+    else:
+        t = torch.arange(x.shape[1]).unsqueeze(0)
+        mask = (t < lengths.unsqueeze(1)).to(x.dtype).unsqueeze(2)
+        flen = lengths.to(x.dtype).reshape(-1, 1, 1)
+        mean = (x * mask).sum(1, keepdim=True) / (flen + 1e-16)
+        var = (((x - mean) ** 2) * mask).sum(1) / (flen.squeeze(2) + 1e-16)
+        mean = mean.squeeze(1)
+    floor = (var <= VAR2STD_EPSILON).to(x.dtype)
+    var = (1.0 - floor) * var + floor * VAR2STD_EPSILON
+    return torch.cat([mean, torch.sqrt(var)], 1)
+
+
+def _dense_stack(x, P, kind, nodes, last_type, params, is_training, endpoints, updates):
+    """Key / value nets of self_attention (pooling.py:83-118; common.py:113-223)."""
+    relu_type = params.dict.get("network_relu_type", "relu")
+    for i, _ in enumerate(nodes):
+        name = "att_%s%d" % (kind, i)
+        scope = "tdnn/attention/" + name
+        x = x @ P["%s/%s_dense/kernel" % (scope, name)] + P["%s/%s_dense/bias" % (scope, name)]
+        endpoints["%s_dense" % name] = x
+        last = (i == len(nodes) - 1)
+        if (not last) or last_type == 2:
+            x = batch_norm(x, P, "%s/%s_bn" % (scope, name), params.batchnorm_momentum, is_training, updates)
+            endpoints["%s_bn" % name] = x
+            x = _activation(x, P, "%s/%s_relu" % (scope, name), relu_type)
+            endpoints["%s_relu" % name] = x
+        elif last_type == 1:
+            x = _activation(x, P, "%s/%s_relu" % (scope, name), relu_type)
+            endpoints["%s_relu" % name] = x
+        elif last_type == 3:
+            x = torch.tanh(x)
+            endpoints["%s_tanh" % name] = x
+    return x
+
+
+def self_attention(endpoints, P, params, is_training, updates, lengths=None):
+    """model/pooling.py:78-189.  Returns (att [B, 2*dv], penalty scalar)."""
+    relu_type = params.dict.get("network_relu_type", "relu")
+    value = endpoints[params.att_value_input]
+    key = endpoints[params.att_key_input]
+    key = _dense_stack(key, P, "key", list(params.att_key_num_nodes), params.att_key_network_type,
+                       params, is_training, endpoints, updates)
+    if len(params.att_value_num_nodes) > 0:
+        value = _dense_stack(value, P, "value", list(params.att_value_num_nodes),
+                             params.att_value_network_type, params, is_training, endpoints, updates)
+    h = params.att_num_heads
+    b, l, dv = value.shape
+    assert dv % h == 0, "The dim of the value must be divided by the num of heads."
+    v = value.reshape(b, l, h, dv // h).permute(0, 2, 1, 3)            # split_heads: [B,H,L,dv/H]
+    if params.att_split_key:
+        assert key.shape[2] % h == 0
+        k = key.reshape(b, l, h, key.shape[2] // h).permute(0, 2, 1, 3)
+        e = torch.einsum("bhld,hd->blh", k, P["tdnn/attention/query"])
+    else:
+        k = key.unsqueeze(1)
+        e = torch.einsum("bmld,hd->blh", k, P["tdnn/attention/query"])
+    if params.att_use_scale:
+        e = e * (float(k.shape[-1]) ** -0.5)
+    e = e.permute(0, 2, 1)                                             # [B,H,L]
+    if lengths is not None:   # no reference definition; extrapolated from the masked pooling rule
+        t = torch.arange(l).reshape(1, 1, l)
+        e = e.masked_fill(t >= lengths.reshape(-1, 1, 1), float("-inf"))
+    w = torch.softmax(e, dim=-1)
+    endpoints["attention_weights"] = w
+    mean = torch.einsum("bhld,bhl->bhd", v, w)
+    var = torch.einsum("bhld,bhl->bhd", (v - mean.unsqueeze(2)) ** 2, w)
+    mean = mean.reshape(b, dv)
+    var = var.reshape(b, dv)
+    floor = (var <= VAR2STD_EPSILON).to(var.dtype)
+    var = (1.0 - floor) * var + floor * VAR2STD_EPSILON
+    att = torch.cat([mean, torch.sqrt(var)], 1)
+    endpoints["att_output_before_nonlinear"] = att
+    if params.dict.get("att_apply_nonlinear", False):
+        att = batch_norm(att, P, "tdnn/attention/att_post_bn", params.batchnorm_momentum, is_training, updates)
+        endpoints["att_post_bn"] = att
+        att = _activation(att, P, "tdnn/attention/att_post_relu", relu_type)
+        endpoints["att_post_relu"] = att
+    pen = torch.einsum("ijk,ilk->ijl", w, w) - torch.eye(h, dtype=w.dtype).unsqueeze(0)
+    penalty = params.att_penalty_term * (pen ** 2).sum() / float(b)
+    return att, penalty
+
+
+# --------------------------------------------------------------------------------------
+# Network (model/tdnn.py:8-191) and entire_network (model/trainer.py:168-188)
+# --------------------------------------------------------------------------------------
+def tdnn(features, P, params, is_training=False, updates=None, lengths=None, mirror_tf_fused_bn=True):
+    """Returns (features, endpoints, penalty).  ``lengths`` (input-domain frames per row) enables the
+    masked pooling used for batched variable-length extraction; frame layers are unaffected because
+    BN in inference mode is element-wise and valid output frames never read padded input frames."""
+    relu_type = params.dict.get("network_relu_type", "relu")
+    mom = params.batchnorm_momentum
+    ep = OrderedDict()
+    x = features
+    for name, kind, k, cin, cout in frame_layer_specs(features.shape[-1], params):
+        if kind == "conv":
+            x = temporal_conv(x, P["tdnn/%s_conv/kernel" % name], P["tdnn/%s_conv/bias" % name])
+            ep["%s_conv" % name] = x
+        else:
+            x = x @ P["tdnn/%s_dense/kernel" % name] + P["tdnn/%s_dense/bias" % name]
+            ep["%s_dense" % name] = x
+        x = batch_norm(x, P, "tdnn/%s_bn" % name, mom, is_training, updates,
+                       unbiased_moving_var=(mirror_tf_fused_bn and kind == "conv"))
+        ep["%s_bn" % name] = x
+        x = _activation(x, P, "tdnn/%s_relu" % name, relu_type)
+        ep["%s_relu" % name] = x
+    plen = None if lengths is None else (lengths - 14)
+    penalty = None
+    if params.pooling_type == "statistics_pooling":
+        x = statistics_pooling(x, plen)
+    elif params.pooling_type == "self_attention":
+        x, penalty = self_attention(ep, P, params, is_training, updates, plen)
+    else:
+        raise NotImplementedError("Not implement %s pooling" % params.pooling_type)
+    ep["pooling"] = x
+    x = x @ P["tdnn/tdnn6_dense/kernel"] + P["tdnn/tdnn6_dense/bias"]
+    ep["tdnn6_dense"] = x
+    x = batch_norm(x, P, "tdnn/tdnn6_bn", mom, is_training, updates)
+    ep["tdnn6_bn"] = x
+    x = _activation(x, P, "tdnn/tdnn6_relu", relu_type)
+    ep["tdnn6_relu"] = x
+    x = x @ P["tdnn/tdnn7_dense/kernel"] + P["tdnn/tdnn7_dense/bias"]
+    ep["tdnn7_dense"] = x
+    if not params.dict.get("last_layer_no_bn", False):
+        x = batch_norm(x, P, "tdnn/tdnn7_bn", mom, is_training, updates)
+        ep["tdnn7_bn"] = x
+    if not params.dict.get("last_layer_linear", False):
+        x = _activation(x, P, "tdnn/tdnn7_relu", relu_type)
+        ep["tdnn7_relu"] = x
+    return x, ep, penalty
+
+
+def l2_scaling(x, scaling_factor, epsilon=1e-12):
+    """model/common.py:45-58."""
+    sq = (x ** 2).sum(-1, keepdim=True)
+    return x * (torch.rsqrt(torch.clamp(sq, min=epsilon)) * scaling_factor)
+
+
+def entire_network(features, P, params, is_training=False, updates=None, lengths=None):
+    """model/trainer.py:168-188."""
+    x, ep, penalty = tdnn(features, P, params, is_training, updates, lengths)
+    ep["output"] = x
+    if params.dict.get("feature_norm", False):
+        assert "feature_scaling_factor" in params.dict
+        x = l2_scaling(x, params.feature_scaling_factor)
+        ep["output"] = x
+    return x, ep, penalty
+
+
+# --------------------------------------------------------------------------------------
+# Heads (model/loss.py)
+# --------------------------------------------------------------------------------------
+def margin_lambda(lmin, base, gamma, power, global_step):
+    """loss.py:144-147 / 235-240 / 333-337."""
+    lam = max(float(lmin), float(base) * (1.0 + float(gamma) * float(global_step)) ** (-float(power)))
+    fa = 1.0 / (1.0 + lam)
+    return lam, fa, 1.0 - fa
+
+
+def _xent(logits, labels):
+    """tf.losses.sparse_softmax_cross_entropy: mean over the batch of -log softmax(logits)[label]."""
+    return F.cross_entropy(logits, labels.long(), reduction="mean")
+
+
+def softmax_head(x, labels, P, params=None):
+    """loss.py:29-35 (dense with bias + xent)."""
+    logits = x @ P["softmax/output/kernel"] + P["softmax/output/bias"]
+    return _xent(logits, labels), logits
+
+
+def _margin_head(x, labels, w, phi_fn, fa, fs):
+    eps = 1e-12
+    wn = w * torch.rsqrt(torch.clamp((w ** 2).sum(0, keepdim=True), min=eps))     # l2_normalize(w, dim=0)
+    logits = x @ wn
+    idx = torch.arange(x.shape[0])
+    sel = logits[idx, labels.long()]
+    xnorm = torch.clamp(torch.linalg.norm(x, dim=1), min=eps)
+    cos = torch.clamp(sel / xnorm, -1 + eps, 1 - eps)
+    phi = phi_fn(cos)
+    scaled = phi * xnorm
+    delta = torch.zeros_like(logits)
+    delta[idx, labels.long()] = scaled - sel
+    logits_m = logits + delta
+    updated = fs * logits + fa * logits_m
+    return _xent(updated, labels), logits
+
+
+def asoftmax_head(x, labels, P, params, global_step=None):
+    """loss.py:97-159.  m=1 returns plain xent on ||x||cos(theta) (loss.py:110-115)."""
+    w = P["softmax/output/kernel"]
+    m = int(params.asoftmax_m)
+    if m == 1:
+        wn = w * torch.rsqrt(torch.clamp((w ** 2).sum(0, keepdim=True), min=1e-12))
+        logits = x @ wn
+        return _xent(logits, labels), logits
+    if m == 2:
+        def phi(c):
+            return 2 * torch.sign(c) * c ** 2 - 1
+    elif m == 4:
+        def phi(c):
+            c2, c4 = c ** 2, c ** 4
+            s0 = torch.sign(c)
+            s3 = torch.sign(2 * c2 - 1) * s0
+            s4 = 2 * s0 + s3 - 3
+            return s3 * (8 * c4 - 8 * c2 + 1) + s4
+    else:
+        raise NotImplementedError("[ERROR] m=%d is not unsupported." % m)
+    gs = params.dict["global_step"] if global_step is None else global_step
+    _, fa, fs = margin_lambda(params.asoftmax_lambda_min, params.asoftmax_lambda_base,
+                              params.asoftmax_lambda_gamma, params.asoftmax_lambda_power, gs)
+    return _margin_head(x, labels, w, phi, fa, fs)
+
+
+def additive_margin_softmax_head(x, labels, P, params, global_step=None):
+    """loss.py:207-247."""
+    m = float(params.amsoftmax_m)
+    gs = params.dict["global_step"] if global_step is None else global_step
+    _, fa, fs = margin_lambda(params.amsoftmax_lambda_min, params.amsoftmax_lambda_base,
+                              params.amsoftmax_lambda_gamma, params.amsoftmax_lambda_power, gs)
+    return _margin_head(x, labels, P["softmax/output/kernel"], lambda c: c - m, fa, fs)
+
+
+def additive_angular_margin_softmax_head(x, labels, P, params, global_step=None):
+    """loss.py:293-345."""
+    m = float(params.arcsoftmax_m)
+    gs = params.dict["global_step"] if global_step is None else global_step
+    _, fa, fs = margin_lambda(params.arcsoftmax_lambda_min, params.arcsoftmax_lambda_base,
+                              params.arcsoftmax_lambda_gamma, params.arcsoftmax_lambda_power, gs)
+
+    def phi(c):
+        sin = torch.sqrt(torch.clamp(1 - c ** 2, min=1e-12))
+        u = c * math.cos(m) - sin * math.sin(m)
+        return torch.where(c > math.cos(math.pi - m), u, -u - 2)
+    return _margin_head(x, labels, P["softmax/output/kernel"], phi, fa, fs)
+
+
+HEADS = {
+    "softmax": softmax_head,
+    "asoftmax": asoftmax_head,
+    "additive_margin_softmax": additive_margin_softmax_head,
+    "additive_angular_margin_softmax": additive_angular_margin_softmax_head,
+}
+
+
+def loss_network(loss_type, x, labels, P, params, global_step=None):
+    if loss_type not in HEADS:
+        raise NotImplementedError("Not implement %s loss" % loss_type)
+    if loss_type == "softmax":
+        return softmax_head(x, labels, P, params)
+    return HEADS[loss_type](x, labels, P, params, global_step)
+
+
+# --------------------------------------------------------------------------------------
+# Training step (model/trainer.py:328-358, 403-436)
+# --------------------------------------------------------------------------------------
+def regularization_loss(P, params):
+    """tf.losses.get_regularization_loss(): sum over kernels of s*sum(w^2)/2."""
+    s = float(params.weight_l2_regularizer)
+    s_out = float(params.dict.get("output_weight_l2_regularizer", s))
+    total = 0.0
+    for k, v in P.items():
+        if l2_regularised(k):
+            total = total + (s_out if k.startswith("softmax/") else s) * (v ** 2).sum() / 2
+    return total
+
+
+def forward_loss(P, features, labels, params, loss_type, global_step, is_training=True, updates=None):
+    x, ep, penalty = entire_network(features, P, params, is_training=is_training, updates=updates)
+    loss, logits = loss_network(loss_type, x, labels, P, params, global_step)
+    total = loss + regularization_loss(P, params)
+    if penalty is not None:
+        total = total + penalty
+    ep["logits"] = logits
+    return loss, total, ep
+
+
+def train_step(P, opt_state, features, labels, params, loss_type, learning_rate, global_step):
+    """One sess.run(train_op).  Returns (raw_loss, total_loss, grads, new_P, new_opt_state, endpoints)."""
+    Pg = OrderedDict((k, v.detach().clone().requires_grad_(k in trainable_names(P))) for k, v in P.items())
+    updates = OrderedDict()
+    loss, total, ep = forward_loss(Pg, features, labels, params, loss_type, global_step, True, updates)
+    names = trainable_names(P)
+    gl = torch.autograd.grad(total, [Pg[n] for n in names], allow_unused=True)
+    grads = OrderedDict((n, (g if g is not None else torch.zeros_like(P[n]))) for n, g in zip(names, gl))
+    if params.dict.get("clip_gradient", False):
+        gn = torch.sqrt(sum((g ** 2).sum() for g in grads.values()))
+        c = float(params.clip_gradient_norm)
+        scale = c / torch.clamp(gn, min=c)
+        grads = OrderedDict((n, g * scale) for n, g in grads.items())
+    newP, new_state = apply_optimizer(P, grads, opt_state, params, learning_rate)
+    for k, v in updates.items():
+        newP[k] = v.detach()
+    return loss.detach(), total.detach(), grads, newP, new_state, ep
+
+
+def apply_optimizer(P, grads, state, params, lr):
+    """tf.train.GradientDescentOptimizer / MomentumOptimizer / AdamOptimizer (trainer.py:328-347)."""
+    opt = params.dict.get("optimizer", "sgd")
+    state = dict(state) if state else {}
+    newP = OrderedDict((k, v.detach().clone()) for k, v in P.items())
+    if opt == "sgd":
+        for n, g in grads.items():
+            newP[n] = P[n].detach() - lr * g
+    elif opt == "momentum":
+        mu = float(params.momentum)
+        nest = bool(params.dict.get("use_nesterov", False))
+        for n, g in grads.items():
+            acc = state.get(n, torch.zeros_like(g)) * mu + g
+            state[n] = acc
+            newP[n] = P[n].detach() - lr * ((g + mu * acc) if nest else acc)
+    elif opt == "adam":
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        t = state.get("__t", 0) + 1
+        state["__t"] = t
+        lr_t = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        for n, g in grads.items():
+            m = state.get(n + "/m", torch.zeros_like(g)) * b1 + (1 - b1) * g
+            v = state.get(n + "/v", torch.zeros_like(g)) * b2 + (1 - b2) * g * g
+            state[n + "/m"], state[n + "/v"] = m, v
+            newP[n] = P[n].detach() - lr_t * m / (torch.sqrt(v) + eps)
+    else:
+        raise SystemExit("Optimizer %s is not supported." % opt)
+    return newP, state
+
+
+def valid_params(params, loss_type):
+    """Margin neutralisation for the validation graph (trainer.py:261-303)."""
+    vp = ParamsPlain(**dict(params.dict))
+    if loss_type == "asoftmax":
+        vp.asoftmax_m = 1
+    elif loss_type == "additive_margin_softmax":
+        vp.amsoftmax_m = 0
+    elif loss_type == "additive_angular_margin_softmax":
+        vp.arcsoftmax_m = 0
+    return vp
+
+
+# --------------------------------------------------------------------------------------
+# Extraction (egs/voxceleb/v1/nnet/lib/extract.py:65-94, model/trainer.py:708-726)
+# --------------------------------------------------------------------------------------
+def predict(features, P, params):
+    """Trainer.predict: [T,D] -> [E] or [N,T,D] -> [N,E]; BN in inference mode."""
+    with torch.no_grad():
+        single = features.dim() == 2
+        x = features.unsqueeze(0) if single else features
+        _, ep, _ = entire_network(x, P, params, is_training=False)
+        e = ep[params.embedding_node]
+        return e[0] if single else e
+
+
+def extract_embedding(feature, P, params, chunk_size=10000, min_chunk_size=25, normalize=False):
+    """One utterance of extract.py's loop.  Returns None if skipped (too short)."""
+    t = feature.shape[0]
+    if t < min_chunk_size:
+        return None
+    if t > chunk_size:
+        half = chunk_size // 2        # py2 integer division at extract.py:73,75
+        n = int(np.ceil(float(t - chunk_size) / half)) + 1
+        chunks, lens = [], []
+        for i in range(n):
+            start = i * half
+            this = chunk_size if t - start > chunk_size else t - start
+            lens.append(this)
+            chunks.append(feature[start:start + this])
+        embs = predict(torch.stack(chunks[:-1]), P, params)
+        last = predict(chunks[-1], P, params)
+        embs = torch.cat([embs, last.unsqueeze(0)], 0)
+        if normalize:
+            embs = embs / torch.sqrt((embs ** 2).sum(1, keepdim=True))
+        ln = torch.tensor(lens, dtype=embs.dtype).unsqueeze(1)
+        emb = (embs * ln).sum(0) / ln.sum()
+    else:
+        emb = predict(feature, P, params)
+    if normalize:
+        emb = emb / torch.sqrt((emb ** 2).sum())
+    return emb
+
+
+# --------------------------------------------------------------------------------------
+# Algorithmic work
+# --------------------------------------------------------------------------------------
+def flops_fwd(T, D, C, pool_nodes=1500):
+    return 2 * 512 * (5 * D * (T - 4) + 2560 * (T - 8) + (3584 + 512 + pool_nodes) * (T - 14)) \
+        + 2 * (2 * pool_nodes * 512 + 512 * 512 + 512 * C)
+
+
+def flops_train(T, D, C, pool_nodes=1500):
+    return 3 * flops_fwd(T, D, C, pool_nodes) - 2 * 512 * 5 * D * (T - 4)

@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors under tests/golden/ from the REFERENCE's own NumPy
+known-answer functions (run in the build container, where /root/reference exists):
+
+  heads.npz      model/test_utils.py:157-318 (compute_asoftmax / compute_amsoftmax / compute_arcsoftmax)
+                 on the adversarial rows of model/tdnn.py:271-277 (theta~0, theta~pi, tiny norm, x10 norm),
+                 m grids and feature_norm on/off as in model/tdnn.py:254-343.
+  statpool.npz   the inline NumPy check of model/multitask_v1/pooling.py:68-83 (restated verbatim in
+                 spirit: E[x^2]-mean^2 with a 1e-12 floor; the original lives under ``__main__``).
+  attention.npz  model/test_utils.py:321-376 compute_self_attention, exec'd from the reference source with
+                 the two py2 integer divisions (``value_dim/n_heads``, ``key_dim/n_heads``) turned into ``//``.
+
+Usage: python tests/golden/make_golden.py   (writes next to this file; seeded, deterministic)
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+REF = os.environ.get("XV_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class ParamsPlain(object):      # misc/utils.py:44-61 stand-in (the original imports TensorFlow)
+    @property
+    def dict(self):
+        return self.__dict__
+
+
+def load_test_utils():
+    sys.path.insert(0, REF)
+    from model import test_utils          # numpy + six only
+    return test_utils
+
+
+def xavier(rng, fan_in, fan_out):
+    lim = np.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=(fan_in, fan_out)).astype(np.float32)
+
+
+def make_heads(tu):
+    rng = np.random.RandomState(20240)
+    n, d, c = 100, 512, 10
+    labels = rng.randint(0, c, size=(n,)).astype(np.int32)
+    w = xavier(rng, d, c)
+    emb = rng.rand(n, d).astype(np.float32)
+    emb[0] = w[:, labels[0]] + 1e-5          # theta ~ 0
+    emb[1] = -1 * w[:, labels[1]] + 1e-5     # theta ~ pi
+    emb[2] = 1e-4 * emb[2]                   # tiny norm
+    emb_x10 = emb.copy()
+    emb_x10[3] = 10 * emb_x10[3]             # large norm (asoftmax test only, tdnn.py:277)
+    out = {"labels": labels, "w": w, "emb": emb, "emb_x10": emb_x10}
+    cases = []
+    p = ParamsPlain()
+    for pre in ("asoftmax", "amsoftmax", "arcsoftmax"):
+        p.dict[pre + "_lambda_min"] = 10
+        p.dict[pre + "_lambda_base"] = 1000
+        p.dict[pre + "_lambda_gamma"] = 1
+        p.dict[pre + "_lambda_power"] = 4
+    # the reference tests use feature_scaling_factor 0.1; add 2.0 as an extra scaled case
+    for scaling, factor in ((True, 0.1), (False, 0.1), (True, 2.0)):
+        p.dict["feature_norm"] = scaling
+        p.dict["feature_scaling_factor"] = factor
+        for m in (1, 2, 4):
+            p.dict["global_step"] = 1
+            p.dict["asoftmax_m"] = m
+            v = tu.compute_asoftmax(emb_x10.astype(np.float64), labels, p, w.astype(np.float64))
+            cases.append(("asoftmax", scaling, factor, float(m), 1, float(v)))
+        for m in (0, 0.1, 0.5):
+            p.dict["global_step"] = 1000
+            p.dict["amsoftmax_m"] = m
+            v = tu.compute_amsoftmax(emb.astype(np.float64), labels, p, w.astype(np.float64))
+            cases.append(("additive_margin_softmax", scaling, factor, float(m), 1000, float(v)))
+            p.dict["arcsoftmax_m"] = m
+            v = tu.compute_arcsoftmax(emb.astype(np.float64), labels, p, w.astype(np.float64))
+            cases.append(("additive_angular_margin_softmax", scaling, factor, float(m), 1000, float(v)))
+    out["case_loss_type"] = np.array([c_[0] for c_ in cases])
+    out["case_feature_norm"] = np.array([c_[1] for c_ in cases])
+    out["case_scaling_factor"] = np.array([c_[2] for c_ in cases], dtype=np.float64)
+    out["case_m"] = np.array([c_[3] for c_ in cases], dtype=np.float64)
+    out["case_global_step"] = np.array([c_[4] for c_ in cases], dtype=np.int64)
+    out["case_loss"] = np.array([c_[5] for c_ in cases], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "heads.npz"), **out)
+    print("heads.npz: %d cases" % len(cases))
+
+
+def make_statpool():
+    # model/multitask_v1/pooling.py:68-83 (inline compute_stat_pooling), row 0 all zeros as at :63
+    rng = np.random.RandomState(20241)
+    n, l, d = 12, 96, 40
+    x = rng.rand(n, l, d).astype(np.float32)
+    x[0] = 0
+    length = rng.randint(10, l + 1, size=(n,)).astype(np.int32)
+    mean = np.zeros((n, d))
+    std = np.zeros((n, d))
+    for i in range(n):
+        for j in range(length[i]):
+            mean[i] += x[i, j]
+            std[i] += np.square(x[i, j].astype(np.float64))
+        mean[i] /= length[i]
+        std[i] /= length[i]
+        std[i] = np.sqrt(np.maximum(std[i] - np.square(mean[i]), 1e-12))
+    np.savez_compressed(os.path.join(HERE, "statpool.npz"), x=x, length=length,
+                        out=np.concatenate([mean, std], axis=1))
+    print("statpool.npz")
+
+
+def make_attention(tu):
+    src = open(os.path.join(REF, "model", "test_utils.py")).read()
+    m = re.search(r"def compute_self_attention\(.*?\n(?=def )", src, re.S)
+    body = m.group(0).replace("value_dim/n_heads", "value_dim//n_heads").replace("key_dim/n_heads", "key_dim//n_heads")
+    ns = {"np": np, "softmax": tu.softmax, "range": range}
+    exec(body, ns)
+    fn = ns["compute_self_attention"]
+    rng = np.random.RandomState(20242)
+    out = {}
+    # model/pooling.py:430-476 (commented-out self-test): rows *1e-8, =0, *100, =100
+    for tag, (heads, split, scale, dk, dv) in {"h4_split": (4, True, True, 24, 32),
+                                               "h1_shared": (1, False, True, 24, 32),
+                                               "h2_shared_noscale": (2, False, False, 24, 32)}.items():
+        b, l = 6, 20
+        value = rng.rand(b, l, dv).astype(np.float32)
+        key = rng.rand(b, l, dk).astype(np.float32)
+        value[0] *= 1e-8
+        value[1] = 0
+        value[2] *= 100
+        value[3] = 100
+        query = (rng.randn(heads, dk // heads if split else dk) * 0.1).astype(np.float32)
+        p = ParamsPlain()
+        p.dict.update(att_split_key=split, att_use_scale=scale, att_penalty_term=0.5)
+        att, pen = fn(value.astype(np.float64), key.astype(np.float64), query.astype(np.float64), p)
+        out[tag + "/value"], out[tag + "/key"], out[tag + "/query"] = value, key, query
+        out[tag + "/att"], out[tag + "/penalty"] = att, np.float64(pen)
+        out[tag + "/cfg"] = np.array([heads, int(split), int(scale)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "attention.npz"), **out)
+    print("attention.npz")
+
+
+if __name__ == "__main__":
+    tu = load_test_utils()
+    make_heads(tu)
+    make_statpool()
+    make_attention(tu)

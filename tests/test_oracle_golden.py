@@ -1,0 +1,78 @@
+"""Pin the oracle (oracle/xvector_oracle.py) against the committed golden vectors that
+tests/golden/make_golden.py produced from the REFERENCE's NumPy known-answer functions
+(model/test_utils.py:157-376, model/multitask_v1/pooling.py:68-83).  CPU only."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import xvector_oracle as O
+
+
+def _params(**kw):
+    p = O.ParamsPlain(weight_l2_regularizer=1e-5)
+    for pre in ("asoftmax", "amsoftmax", "arcsoftmax"):
+        p.dict[pre + "_lambda_min"] = 10
+        p.dict[pre + "_lambda_base"] = 1000
+        p.dict[pre + "_lambda_gamma"] = 1
+        p.dict[pre + "_lambda_power"] = 4
+    p.dict.update(kw)
+    return p
+
+
+def test_heads_match_reference_numpy(golden_dir):
+    g = np.load(os.path.join(golden_dir, "heads.npz"))
+    labels = torch.from_numpy(g["labels"].astype(np.int64))
+    P = {"softmax/output/kernel": torch.from_numpy(g["w"].astype(np.float64))}
+    n = len(g["case_loss"])
+    assert n == 27
+    for i in range(n):
+        lt = str(g["case_loss_type"][i])
+        m = float(g["case_m"][i])
+        p = _params(feature_norm=bool(g["case_feature_norm"][i]),
+                    feature_scaling_factor=float(g["case_scaling_factor"][i]),
+                    global_step=int(g["case_global_step"][i]))
+        emb = g["emb_x10"] if lt == "asoftmax" else g["emb"]
+        x = torch.from_numpy(emb.astype(np.float64)).requires_grad_(True)
+        if lt == "asoftmax":
+            p.asoftmax_m = int(m)
+        elif lt == "additive_margin_softmax":
+            p.amsoftmax_m = m
+        else:
+            p.arcsoftmax_m = m
+        xin = O.l2_scaling(x, p.feature_scaling_factor) if p.feature_norm else x
+        loss, _ = O.loss_network(lt, xin, labels, P, p)
+        (gx,) = torch.autograd.grad(loss, x)
+        assert not torch.isnan(gx).any(), "Gradient should not be nan"      # model/tdnn.py:282,313,342
+        # same tolerance the reference's own self-tests use (np.allclose defaults)
+        assert np.allclose(loss.item(), g["case_loss"][i], rtol=1e-5, atol=1e-8), (lt, m, loss.item(), g["case_loss"][i])
+
+
+def test_masked_statistics_pooling(golden_dir):
+    g = np.load(os.path.join(golden_dir, "statpool.npz"))
+    x = torch.from_numpy(g["x"].astype(np.float64))
+    ln = torch.from_numpy(g["length"].astype(np.int64))
+    out = O.statistics_pooling(x, ln).numpy()
+    assert np.allclose(out, g["out"], rtol=1e-5, atol=1e-7)
+    # unmasked == masked with full lengths
+    full = torch.full((x.shape[0],), x.shape[1], dtype=torch.int64)
+    assert np.allclose(O.statistics_pooling(x).numpy(), O.statistics_pooling(x, full).numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_self_attention(golden_dir):
+    g = np.load(os.path.join(golden_dir, "attention.npz"))
+    for tag in ("h4_split", "h1_shared", "h2_shared_noscale"):
+        heads, split, scale = [int(v) for v in g[tag + "/cfg"]]
+        value = torch.from_numpy(g[tag + "/value"].astype(np.float64))
+        key = torch.from_numpy(g[tag + "/key"].astype(np.float64))
+        p = O.ParamsPlain(att_value_input="v", att_key_input="k", att_key_num_nodes=[], att_value_num_nodes=[],
+                          att_key_network_type=0, att_value_network_type=0, att_num_heads=heads,
+                          att_split_key=bool(split), att_use_scale=bool(scale), att_penalty_term=0.5,
+                          batchnorm_momentum=0.99)
+        P = {"tdnn/attention/query": torch.from_numpy(g[tag + "/query"].astype(np.float64))}
+        att, pen = O.self_attention({"v": value, "k": key}, P, p, True, None)
+        dv = value.shape[2]
+        # the reference numpy adds 1e-12 inside the sqrt instead of flooring (test_utils.py:369): rtol 1e-3 as pooling.py:474
+        assert np.allclose(att.numpy()[:, :dv], g[tag + "/att"][:, :dv], rtol=1e-6, atol=1e-9)
+        assert np.allclose(att.numpy()[:, dv:], g[tag + "/att"][:, dv:], rtol=1e-3, atol=2e-6)
+        assert np.allclose(pen.item(), float(g[tag + "/penalty"]), rtol=1e-8)
