@@ -1,0 +1,94 @@
+// Host side of the tcgen05 implicit-GEMM: tensor-map encoding, argument checks, dispatch.
+#include "xv_gemm_kernel.cuh"
+
+namespace xv {
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+static int make_tmap(CUtensorMap* map, const xv_operand& op, int box_rows_kmajor) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(XV_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if (op.ptr == nullptr || (reinterpret_cast<uintptr_t>(op.ptr) & 15)) return set_error(XV_ERR_INVALID, "operand pointer null or not 16B aligned");
+  if (op.ld % 8 != 0 || op.ld < op.cols) return set_error(XV_ERR_INVALID, "operand ld must be a multiple of 8 elements and >= cols");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(op.cols), static_cast<cuuint64_t>(op.rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(op.ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(op.mn_major ? 64 : box_rows_kmajor)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(XV_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+  return XV_OK;
+}
+
+}  // namespace xv
+
+extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
+  using namespace xv;
+  if (!a) return set_error(XV_ERR_INVALID, "null args");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(XV_ERR_INVALID, "M, N, K must be positive");
+  if (a->splits < 1) return set_error(XV_ERR_INVALID, "splits must be >= 1");
+  if (a->splits > 1 && a->epilogue != XV_EPI_F32) return set_error(XV_ERR_INVALID, "split-K needs the f32 epilogue");
+  if (a->out == nullptr) return set_error(XV_ERR_INVALID, "null output");
+  if (a->epilogue == XV_EPI_BF16 || a->epilogue == XV_EPI_HEAD_BWD) {
+    if (a->ldc % 8) return set_error(XV_ERR_INVALID, "bf16 output ldc must be a multiple of 8");
+  } else if (a->epilogue == XV_EPI_F32) {
+    if (a->ldc % 4) return set_error(XV_ERR_INVALID, "f32 output ldc must be a multiple of 4");
+  }
+  for (const xv_operand* op : {&a->a, &a->b}) {
+    if (!op->mn_major && op->div && (op->div % BLOCK_K)) return set_error(XV_ERR_INVALID, "K-major tap div must be a multiple of 64");
+    if (op->mn_major && op->div && (op->div % 64)) return set_error(XV_ERR_INVALID, "MN-major tap div must be a multiple of 64");
+  }
+  if (a->a.mn_major && a->a.div && (a->a.div % BLOCK_M)) return set_error(XV_ERR_INVALID, "MN-major A tap div must be a multiple of 128");
+  if (a->b.mn_major && a->b.div && (a->b.div % BLOCK_N)) return set_error(XV_ERR_INVALID, "MN-major B tap div must be a multiple of 256");
+  if ((a->col_sum == nullptr) != (a->col_sumsq == nullptr) && a->epilogue == XV_EPI_BF16)
+    return set_error(XV_ERR_INVALID, "col_sum and col_sumsq must be given together");
+
+  GemmKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  int rc = make_tmap(&kp.tma_a, a->a, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&kp.tma_b, a->b, BLOCK_N);
+  if (rc) return rc;
+  kp.M = a->M; kp.N = a->N; kp.K = a->K;
+  kp.a_div = a->a.div; kp.a_tap = a->a.tap_rows; kp.b_div = a->b.div; kp.b_tap = a->b.tap_rows;
+  kp.num_m = (a->M + BLOCK_M - 1) / BLOCK_M;
+  kp.num_n = (a->N + BLOCK_N - 1) / BLOCK_N;
+  kp.num_kb = (a->K + BLOCK_K - 1) / BLOCK_K;
+  int splits = a->splits < kp.num_kb ? a->splits : kp.num_kb;
+  kp.kb_per_split = (kp.num_kb + splits - 1) / splits;
+  splits = (kp.num_kb + kp.kb_per_split - 1) / kp.kb_per_split;   // no empty split
+  kp.splits = splits;
+  kp.seg_len = a->seg_len; kp.seg_valid = a->seg_valid;
+  kp.out = a->out; kp.ldc = a->ldc; kp.bias = a->bias; kp.col_sum = a->col_sum; kp.col_sumsq = a->col_sumsq;
+  kp.head = a->head;
+
+  int sms = 0;
+  rc = device_sm_count(&sms);
+  if (rc) return rc;
+  const long long tiles = static_cast<long long>(kp.num_m) * kp.num_n * kp.splits;
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  kp.a_mn = a->a.mn_major != 0; kp.b_mn = a->b.mn_major != 0;
+  switch (a->epilogue) {
+    case XV_EPI_BF16: return launch_gemm<XV_EPI_BF16>(kp, grid, s);
+    case XV_EPI_F32: return launch_gemm<XV_EPI_F32>(kp, grid, s);
+    case XV_EPI_HEAD_FWD: return launch_gemm<XV_EPI_HEAD_FWD>(kp, grid, s);
+    case XV_EPI_HEAD_BWD: return launch_gemm<XV_EPI_HEAD_BWD>(kp, grid, s);
+    default: return set_error(XV_ERR_INVALID, "unknown epilogue %d", a->epilogue);
+  }
+}
