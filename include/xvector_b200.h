@@ -82,7 +82,10 @@ typedef struct {
   int32_t type;          /* xv_head_type                                                            */
   int32_t asoftmax_m;    /* 1, 2 or 4 (XV_HEAD_ASOFTMAX)                                             */
   float margin;          /* m of AM / AAM                                                           */
-  float fa, fs;          /* 1/(1+lambda), 1-fa (lambda schedule evaluated by the host, loss.py:144) */
+  int32_t _pad0;
+  const float* sched;    /* device [2] = {fa, fs} = {1/(1+lambda), 1-fa}; lambda schedule of loss.py:144-147 is
+                            evaluated by the host each step and lives in device memory so a captured CUDA graph
+                            of the step stays valid as global_step advances                                */
   const int32_t* labels; /* [M]                                                                     */
   const float* xnorm;    /* [M] max(||x_i||, 1e-12)                                                 */
   /* forward outputs */
@@ -113,6 +116,97 @@ typedef struct {
 } xv_gemm_args;
 
 XV_API int xv_gemm_bf16(const xv_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Frame-level elementwise / reduction kernels (bf16 activations [rows, ld], channels-last).
+ * Row validity everywhere: row m (b = m / seg_len, t = m % seg_len) is valid iff
+ * t < (lengths ? lengths[b] : seg_valid); seg_len = 0 means every row is valid.
+ * Activations: 0 none, 1 relu, 2 leaky_relu(0.2) (tdnn.py:29-30), 3 prelu (common.py:27-42), 4 tanh.
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { XV_ACT_NONE = 0, XV_ACT_RELU = 1, XV_ACT_LRELU = 2, XV_ACT_PRELU = 3, XV_ACT_TANH = 4 } xv_activation;
+
+/* features f32 [B,T,D] -> bf16 rows [B*T, ldo], out[m, j*dpad + c] = x[b, t+j, c] (zero padded): the K-major
+ * A operand of tdnn1_conv (tf.expand_dims + conv2d input side, model/tdnn.py:35-44). */
+XV_API int xv_pack_input(const float* x, void* out, int B, int T, int D, int k, int dpad, int64_t ldo, void* stream);
+
+/* tf.layers.batch_normalization (model/tdnn.py:46,64,82,102,121), training mode: per-channel sums produced
+ * by the GEMM epilogue -> scale/shift (+ saved mean/rstd for backward, + moving-stat update, eps 1e-3). */
+XV_API int xv_bn_finalize_train(const float* col_sum, const float* col_sumsq, const float* bias, float count,
+                                const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                                float momentum, float eps, int unbiased_moving_var, float* scale, float* shift,
+                                float* save_mean, float* save_rstd, int C, void* stream);
+/* ... inference mode (is_training=False, model/trainer.py:210-225): scale/shift from the moving statistics. */
+XV_API int xv_bn_finalize_infer(const float* gamma, const float* beta, const float* moving_mean,
+                                const float* moving_var, float eps, float* scale, float* shift, int C, void* stream);
+/* a = act(y*scale + shift) on valid rows, 0 on invalid rows  (BN apply + relu, tdnn.py:46-52 etc.). */
+XV_API int xv_bn_act_apply(const void* y, void* a, const float* scale, const float* shift, const float* alpha, int act,
+                           int64_t rows, int C, int64_t ld, int seg_len, int seg_valid, const int32_t* lengths,
+                           void* stream);
+/* Backward of act(BN(y)) (what tf.gradients emits for FusedBatchNormGrad/ReluGrad, trainer.py:403):
+ * reduce: dgamma += sum g*yhat, dbeta += sum g, dalpha += sum da*min(z,0);  apply: dy (bf16), 0 on invalid rows. */
+XV_API int xv_bn_act_bwd_reduce(const void* y, const void* da, const float* scale, const float* shift,
+                                const float* save_mean, const float* save_rstd, const float* alpha, int act,
+                                int64_t rows, int C, int64_t ld, int seg_len, int seg_valid, const int32_t* lengths,
+                                float* dgamma, float* dbeta, float* dalpha, void* stream);
+XV_API int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, const float* scale, const float* shift,
+                               const float* save_mean, const float* save_rstd, const float* dgamma, const float* dbeta,
+                               float count, const float* alpha, int act, int64_t rows, int C, int64_t ld, int seg_len,
+                               int seg_valid, const int32_t* lengths, void* stream);
+
+/* statistics_pooling (model/pooling.py:9-34) and its length-masked form statistics_pooling_v2
+ * (model/multitask_v1/pooling.py:9-40): out f32 [B, 2*cpad] = [mean | std]; channels >= c_real read as 0.
+ * out_split (optional) = bf16 [B, 6*cpad] = [hi | hi | lo] of out, the A operand of tdnn6_dense. */
+XV_API int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int B, int seg_len, int seg_valid,
+                             const int32_t* lengths, int c_real, int cpad, int64_t ld, void* stream);
+XV_API int xv_stats_pool_bwd(const void* x, const float* pooled, const float* dpooled, void* dx, int B, int seg_len,
+                             int seg_valid, const int32_t* lengths, int c_real, int cpad, int64_t ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Utterance-level layers (tdnn6/tdnn7 BN + activation on f32 [B, C], model/tdnn.py:147-189).
+ * mode: 0 = no BN (last_layer_no_bn), 1 = training (batch statistics), 2 = inference (moving statistics).
+ * a_split: optional bf16 copy of the activation, split_terms = 1 (plain) or 3 ([hi | hi | lo]).
+ * ------------------------------------------------------------------------------------------ */
+XV_API int xv_bn_rows_fwd(const float* y, int B, int C, int mode, const float* gamma, const float* beta,
+                          float* moving_mean, float* moving_var, float momentum, float eps, const float* alpha, int act,
+                          float* bn_out, float* a, void* a_split, int split_terms, float* save_mean, float* save_rstd,
+                          void* stream);
+XV_API int xv_bn_rows_bwd(const float* y, const float* da, int B, int C, int mode, const float* gamma, const float* beta,
+                          const float* save_mean, const float* save_rstd, const float* alpha, int act, float* dy,
+                          void* dy_bf16, float* dgamma, float* dbeta, float* dalpha, float* dbias, void* stream);
+XV_API int xv_cast_split(const float* x, void* out, int64_t rows, int cols, int terms, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Margin-softmax head helpers around the XV_EPI_HEAD_* GEMM epilogues (model/loss.py, model/common.py:45-58).
+ * ------------------------------------------------------------------------------------------ */
+/* w f32 [E,C] -> bf16 [3E, ldw] = [hi; lo; hi] of l2_normalize(w, dim=0) (loss.py:104,213,299); inv_norm[C]. */
+XV_API int xv_head_prep_weights(const float* w, void* wn3, float* inv_norm, int E, int C, int64_t ldw, int normalize,
+                                void* stream);
+/* u f32 [B,E] -> x = l2_scaling(u, scaling) if scaling > 0 (trainer.py:183-186) else u; x3 bf16 [B,3E] = [hi|hi|lo];
+ * xnorm[B] = max(||x||, 1e-12) (loss.py:121,220,306); u_rinv[B] = rsqrt(max(||u||^2, 1e-12)). */
+XV_API int xv_head_prep_features(const float* u, float scaling, float* x, void* x3, float* xnorm, float* u_rinv, int B,
+                                 int E, void* stream);
+/* tf.losses.sparse_softmax_cross_entropy (loss.py:35,112,156,244,342): lse from tile partials; loss += mean CE. */
+XV_API int xv_head_combine(const float* part_max, const float* part_sum, const float* target_logit, int nblk, int B,
+                           float inv_batch, float* lse, float* loss_rows, float* loss, void* stream);
+XV_API int xv_head_finish_dx(const float* dx_gemm, const float* gnorm, const float* x, const float* xnorm, const float* u,
+                             const float* u_rinv, float scaling, float* du, int B, int E, void* stream);
+XV_API int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, int E, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer over one flat f32 parameter buffer whose tensors start at multiples of 1024 elements
+ * (tf.train.GradientDescent/Momentum/AdamOptimizer + l2_regularizer + clip_by_global_norm,
+ * model/trainer.py:328-347, 357-358, 403-436).  opt: 0 sgd, 1 momentum, 2 nesterov, 3 adam.
+ * hyper (device f32[8]): lr, momentum, beta1, beta2, adam_eps, adam_t, clip_norm (<=0 off), unused.
+ * blk_* arrays have one entry per 1024-element block: L2 coefficient, offset of the block's bf16 shadow
+ * (-1: none) and, for the 3-term split shadows, the element stride between the hi / lo / hi copies (0: plain).
+ * ------------------------------------------------------------------------------------------ */
+XV_API int xv_grad_sumsq(const float* params, const float* grads, const float* blk_l2, int64_t n, float* out, void* stream);
+XV_API int xv_opt_step(float* params, const float* grads, float* state1, float* state2, const float* blk_l2,
+                       const int64_t* blk_shadow, const int64_t* blk_split_stride, void* shadow, int64_t n, int opt,
+                       const float* hyper, const float* gsumsq, void* stream);
+XV_API int xv_shadow_refresh(const float* params, const int64_t* blk_shadow, const int64_t* blk_split_stride,
+                             void* shadow, int64_t n, void* stream);
+XV_API int xv_l2_loss(const float* params, const float* blk_l2, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

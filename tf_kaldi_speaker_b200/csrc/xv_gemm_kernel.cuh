@@ -99,9 +99,10 @@ __device__ __forceinline__ MarginOut margin_target(const xv_head_args& h, float 
       dphi = s3 * (32.0f * c2 * c - 16.0f * c);
     }
   }
-  o.zprime = h.fs * z + h.fa * n * phi;
-  o.dz = h.fs + h.fa * dphi * k;
-  o.dn = h.fa * (phi - dphi * k * ratio);
+  const float fa = __ldg(h.sched), fs = __ldg(h.sched + 1);
+  o.zprime = fs * z + fa * n * phi;
+  o.dz = fs + fa * dphi * k;
+  o.dn = fa * (phi - dphi * k * ratio);
   return o;
 }
 

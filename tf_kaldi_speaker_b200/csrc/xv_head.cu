@@ -1,0 +1,196 @@
+// Small kernels around the fused margin-softmax GEMM epilogues (model/loss.py:97-159, 207-247, 293-345,
+// model/common.py:45-58): weight/feature normalisation into bf16 GEMM operands, the log-sum-exp combine of
+// the per-tile partials, and the chain rule back through the two normalisations.
+#include <cuda_bf16.h>
+
+#include "xv_internal.h"
+
+namespace xv {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += sh[i];
+  return t;
+}
+
+// w f32 [E, C] (TF layout, C contiguous) -> wn3 bf16 [3E, ldw] = [hi(wn); lo(wn); hi(wn)], wn = w * rsqrt(max(sum_e w^2, 1e-12))
+// (tf.nn.l2_normalize(w, dim=0), loss.py:104,213,299).  normalize = 0 keeps w (plain softmax head).
+__global__ void head_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wn3,
+                                         float* __restrict__ inv_norm, int E, int C, long long ldw, int normalize) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float inv = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int e = 0; e < E; ++e) { const float v = w[static_cast<long long>(e) * C + c]; ss += v * v; }
+    inv = rsqrtf(fmaxf(ss, 1e-12f));
+  }
+  if (inv_norm) inv_norm[c] = inv;
+  for (int e = 0; e < E; ++e) {
+    const float v = w[static_cast<long long>(e) * C + c] * inv;
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    wn3[static_cast<long long>(e) * ldw + c] = h;
+    wn3[static_cast<long long>(E + e) * ldw + c] = __float2bfloat16(v - __bfloat162float(h));
+    wn3[static_cast<long long>(2 * E + e) * ldw + c] = h;
+  }
+}
+
+// One block per row: optional l2_scaling (trainer.py:183-186 / common.py:45-58), ||x||, bf16 [hi|hi|lo] split.
+__global__ void head_prep_features_kernel(const float* __restrict__ u, float scaling, float* __restrict__ x,
+                                          __nv_bfloat16* __restrict__ x3, float* __restrict__ xnorm,
+                                          float* __restrict__ u_rinv, int E) {
+  __shared__ float sh[32];
+  const int i = blockIdx.x;
+  const float* ur = u + static_cast<long long>(i) * E;
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) ss += ur[e] * ur[e];
+  ss = block_sum(ss, sh);
+  float mul = 1.f;
+  if (scaling > 0.f) {
+    const float rinv = rsqrtf(fmaxf(ss, 1e-12f));
+    mul = rinv * scaling;
+    if (threadIdx.x == 0 && u_rinv) u_rinv[i] = rinv;
+  }
+  float s2 = 0.f;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float v = ur[e] * mul;
+    s2 += v * v;
+    if (x) x[static_cast<long long>(i) * E + e] = v;
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    __nv_bfloat16* row = x3 + static_cast<long long>(i) * 3 * E;
+    row[e] = h;
+    row[E + e] = h;
+    row[2 * E + e] = __float2bfloat16(v - __bfloat162float(h));
+  }
+  s2 = block_sum(s2, sh);
+  if (threadIdx.x == 0 && xnorm) xnorm[i] = fmaxf(sqrtf(s2), 1e-12f);
+}
+
+// lse_i = log sum_j exp(z'_ij) from the per-N-tile (max, sum) partials; loss += sum_i (lse_i - z'_{i,y_i}) * inv_batch
+__global__ void head_combine_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                                    const float* __restrict__ target_logit, int nblk, int B, float inv_batch,
+                                    float* __restrict__ lse, float* __restrict__ loss_rows, float* loss) {
+  __shared__ float sh[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float li = 0.f;
+  if (i < B) {
+    float gmax = -INFINITY;
+    for (int k = 0; k < nblk; ++k) gmax = fmaxf(gmax, part_max[static_cast<long long>(k) * B + i]);
+    float s = 0.f;
+    for (int k = 0; k < nblk; ++k)
+      s += part_sum[static_cast<long long>(k) * B + i] * expf(part_max[static_cast<long long>(k) * B + i] - gmax);
+    const float l = logf(s) + gmax;
+    lse[i] = l;
+    li = l - target_logit[i];
+    if (loss_rows) loss_rows[i] = li;
+  }
+  const float tot = block_sum(li, sh);
+  if (threadIdx.x == 0) atomicAdd(loss, tot * inv_batch);
+}
+
+// dx = dx_gemm + gnorm * x/||x||, then (optionally) back through x = s * u / ||u||.
+__global__ void head_finish_dx_kernel(const float* __restrict__ dxg, const float* __restrict__ gnorm,
+                                      const float* __restrict__ x, const float* __restrict__ xnorm,
+                                      const float* __restrict__ u, const float* __restrict__ u_rinv, float scaling,
+                                      float* __restrict__ du, int E) {
+  __shared__ float sh[32];
+  const int i = blockIdx.x;
+  const long long off = static_cast<long long>(i) * E;
+  const float gn = gnorm ? gnorm[i] : 0.f;
+  const float xn = xnorm ? xnorm[i] : 1.f;
+  const float gcoef = (gnorm && xn > 1e-12f) ? gn / xn : 0.f;   // maximum(norm, eps): no gradient to x when clamped
+  if (scaling <= 0.f) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) du[off + e] = dxg[off + e] + gcoef * x[off + e];
+    return;
+  }
+  const float rinv = u_rinv[i];
+  float dot = 0.f;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float dxe = dxg[off + e] + gcoef * x[off + e];
+    dot += dxe * u[off + e];
+  }
+  dot = block_sum(dot, sh);
+  // x = s*u*rinv, rinv = (max(|u|^2, eps))^-1/2 : dx/du = s*rinv*(I - u u^T rinv^2) when |u|^2 > eps
+  const bool clamped = (rinv >= 1e6f);   // rsqrt(1e-12)
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float dxe = dxg[off + e] + gcoef * x[off + e];
+    float g = scaling * rinv * dxe;
+    if (!clamped) g -= scaling * rinv * rinv * rinv * dot * u[off + e];
+    du[off + e] = g;
+  }
+}
+
+// dW_j = (dWn_j - wn_j <wn_j, dWn_j>) * inv_norm_j   (in place on the gradient buffer), one thread per column.
+__global__ void head_finish_dw_kernel(float* __restrict__ dw, const float* __restrict__ w,
+                                      const float* __restrict__ inv_norm, int E, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv = inv_norm[c];
+  const bool clamped = (inv >= 1e6f);
+  float dot = 0.f;
+  for (int e = 0; e < E; ++e) {
+    const long long idx = static_cast<long long>(e) * C + c;
+    dot += w[idx] * inv * dw[idx];
+  }
+  for (int e = 0; e < E; ++e) {
+    const long long idx = static_cast<long long>(e) * C + c;
+    float g = dw[idx] * inv;
+    if (!clamped) g -= w[idx] * inv * inv * dot;
+    dw[idx] = g;
+  }
+}
+
+}  // namespace xv
+
+using namespace xv;
+
+extern "C" int xv_head_prep_weights(const float* w, void* wn3, float* inv_norm, int E, int C, int64_t ldw, int normalize,
+                                    void* stream) {
+  if (!w || !wn3 || E <= 0 || C <= 0 || ldw < C || ldw % 8) return set_error(XV_ERR_INVALID, "xv_head_prep_weights: bad arguments");
+  head_prep_weights_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(wn3), inv_norm, E, C, ldw, normalize);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_head_prep_features(const float* u, float scaling, float* x, void* x3, float* xnorm, float* u_rinv,
+                                     int B, int E, void* stream) {
+  if (!u || !x3 || B <= 0 || E <= 0) return set_error(XV_ERR_INVALID, "xv_head_prep_features: bad arguments");
+  if (scaling > 0.f && !u_rinv) return set_error(XV_ERR_INVALID, "xv_head_prep_features: feature_norm needs u_rinv");
+  head_prep_features_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(u, scaling, x, static_cast<__nv_bfloat16*>(x3),
+                                                                              xnorm, u_rinv, E);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_head_combine(const float* part_max, const float* part_sum, const float* target_logit, int nblk, int B,
+                               float inv_batch, float* lse, float* loss_rows, float* loss, void* stream) {
+  if (!part_max || !part_sum || !target_logit || !lse || !loss || nblk <= 0 || B <= 0)
+    return set_error(XV_ERR_INVALID, "xv_head_combine: bad arguments");
+  head_combine_kernel<<<ceil_div(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(part_max, part_sum, target_logit,
+                                                                                      nblk, B, inv_batch, lse, loss_rows, loss);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_head_finish_dx(const float* dx_gemm, const float* gnorm, const float* x, const float* xnorm,
+                                 const float* u, const float* u_rinv, float scaling, float* du, int B, int E, void* stream) {
+  if (!dx_gemm || !du || B <= 0 || E <= 0) return set_error(XV_ERR_INVALID, "xv_head_finish_dx: bad arguments");
+  if (gnorm && (!x || !xnorm)) return set_error(XV_ERR_INVALID, "xv_head_finish_dx: margin term needs x and xnorm");
+  if (scaling > 0.f && (!u || !u_rinv || !x)) return set_error(XV_ERR_INVALID, "xv_head_finish_dx: feature_norm needs u, u_rinv, x");
+  head_finish_dx_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(dx_gemm, gnorm, x, xnorm, u, u_rinv, scaling, du, E);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, int E, int C, void* stream) {
+  if (!dw || !w || !inv_norm || E <= 0 || C <= 0) return set_error(XV_ERR_INVALID, "xv_head_finish_dw: bad arguments");
+  head_finish_dw_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(dw, w, inv_norm, E, C);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}

@@ -1,0 +1,106 @@
+"""Classification heads with the reference's operator surface (model/loss.py:9-355).
+
+softmax / asoftmax / additive_margin_softmax / additive_angular_margin_softmax keep the reference signatures
+``f(features, labels, num_outputs, params, is_training=None, reuse_variables=None, name="softmax")
+-> (loss, endpoints)`` and parameter keys.  All four run ONE fused kernel sequence (Engine.margin_head): column
+normalisation of the speaker matrix, row normalisation/scaling of the embeddings, the cosine-logit GEMM on
+tcgen05 with the margin transform and an online log-sum-exp in its epilogue -- the [batch, speakers] logits
+matrix is never written to HBM unless ``params.dict["debug_logits"]`` asks for ``endpoints["logits"]``.
+"""
+from collections import OrderedDict
+
+import torch
+
+from .. import _lib as L
+from ..runtime import VarSpec, get_engine, _pad_to
+
+
+def declare_head_variables(engine, embedding_dim, num_outputs, params, loss_type, name="softmax"):
+    """softmax/output/kernel [E, C] (+ bias for the plain softmax), xavier-uniform, L2-regularised
+    (loss.py:30-34, 100-102, 208-210, 294-296)."""
+    l2 = float(params.weight_l2_regularizer)
+    if "output_weight_l2_regularizer" in params.dict:
+        l2 = float(params.output_weight_l2_regularizer)
+    cpad = _pad_to(num_outputs, 8)
+    st = engine.store
+    st.declare(VarSpec(name + "/output/kernel", (embedding_dim, num_outputs), (embedding_dim, cpad), l2=l2,
+                       init="glorot", fans=(embedding_dim, num_outputs)))
+    if loss_type == "softmax":
+        st.declare(VarSpec(name + "/output/bias", (num_outputs,), (cpad,)))
+
+
+def margin_lambda(lambda_min, lambda_base, lambda_gamma, lambda_power, global_step):
+    """lambda = max(lambda_min, lambda_base * (1 + gamma*step)^(-power)); fa = 1/(1+lambda); fs = 1-fa
+    (loss.py:144-147, 235-240, 333-337)."""
+    lam = max(float(lambda_min), float(lambda_base) * (1.0 + float(lambda_gamma) * float(global_step)) ** (-float(lambda_power)))
+    fa = 1.0 / (1.0 + lam)
+    return lam, fa, 1.0 - fa
+
+
+def _run_head(features, labels, num_outputs, params, is_training, name, head_type, margin=0.0, asoftmax_m=1,
+              fa=1.0, fs=0.0):
+    eng = get_engine()
+    assert features.data.dim() == labels.dim() + 1
+    eng.sched.copy_(torch.tensor([fa, fs], dtype=torch.float32), non_blocking=True)
+    scaling = float(getattr(features, "scaling", 0.0) or 0.0)
+    bias = (name + "/output/bias") if head_type == L.HEAD_SOFTMAX and (name + "/output/bias") in eng.store else None
+    want_logits = bool(params.dict.get("debug_logits", False))
+    loss, logits, x = eng.margin_head(features, labels, name + "/output/kernel", bias, head_type, num_outputs,
+                                      bool(is_training), margin=margin, asoftmax_m=asoftmax_m, scaling=scaling,
+                                      want_logits=want_logits)
+    params.dict["softmax_w"] = eng.store.view(name + "/output/kernel")      # loss.py:103,211,297
+    endpoints = OrderedDict()
+    endpoints["logits"] = None if logits is None else logits[:, :num_outputs]
+    endpoints["labels"] = labels
+    if 'aux_loss_func' in params.dict and len(params.dict['aux_loss_func']) > 0:
+        raise NotImplementedError("aux_loss_func (ring / MHE, loss.py:985-1037) is outside the accelerated path")
+    return loss, endpoints
+
+
+def softmax(features, labels, num_outputs, params, is_training=None, reuse_variables=None, name="softmax"):
+    """Vanilla softmax loss: dense(num_outputs) with bias + mean cross entropy (loss.py:9-48)."""
+    return _run_head(features, labels, num_outputs, params, is_training, name, L.HEAD_SOFTMAX)
+
+
+def asoftmax(features, labels, num_outputs, params, is_training=None, reuse_variables=None, name="softmax"):
+    """Angular softmax, m in {1, 2, 4} with the lambda annealing (loss.py:51-169)."""
+    params.asoftmax_lambda_min = float(params.asoftmax_lambda_min)
+    params.asoftmax_lambda_base = float(params.asoftmax_lambda_base)
+    params.asoftmax_lambda_gamma = float(params.asoftmax_lambda_gamma)
+    params.asoftmax_lambda_power = float(params.asoftmax_lambda_power)
+    m = int(params.asoftmax_m)
+    if m == 1:
+        # plain xent on ||x|| cos(theta): no margin, no lambda (loss.py:110-115)
+        # = the additive-margin epilogue with m = 0, fa = 0, fs = 1 (normalised weights, untouched target logit)
+        return _run_head(features, labels, num_outputs, params, is_training, name, L.HEAD_AM, margin=0.0, fa=0.0, fs=1.0)
+    if m not in (2, 4):
+        raise NotImplementedError("[ERROR] m=%d is not unsupported." % m)
+    _, fa, fs = margin_lambda(params.asoftmax_lambda_min, params.asoftmax_lambda_base, params.asoftmax_lambda_gamma,
+                              params.asoftmax_lambda_power, params.dict["global_step"])
+    return _run_head(features, labels, num_outputs, params, is_training, name, L.HEAD_ASOFTMAX, asoftmax_m=m, fa=fa, fs=fs)
+
+
+def additive_margin_softmax(features, labels, num_outputs, params, is_training=None, reuse_variables=None, name="softmax"):
+    """Additive margin softmax, phi = cos(theta) - m (loss.py:172-257)."""
+    params.amsoftmax_lambda_min = float(params.amsoftmax_lambda_min)
+    params.amsoftmax_lambda_base = float(params.amsoftmax_lambda_base)
+    params.amsoftmax_lambda_gamma = float(params.amsoftmax_lambda_gamma)
+    params.amsoftmax_lambda_power = float(params.amsoftmax_lambda_power)
+    params.amsoftmax_m = float(params.amsoftmax_m)
+    _, fa, fs = margin_lambda(params.amsoftmax_lambda_min, params.amsoftmax_lambda_base, params.amsoftmax_lambda_gamma,
+                              params.amsoftmax_lambda_power, params.dict["global_step"])
+    return _run_head(features, labels, num_outputs, params, is_training, name, L.HEAD_AM, margin=params.amsoftmax_m,
+                     fa=fa, fs=fs)
+
+
+def additive_angular_margin_softmax(features, labels, num_outputs, params, is_training=None, reuse_variables=None, name="softmax"):
+    """Additive angular margin softmax (ArcFace), phi = cos(theta + m) with the monotone extension (loss.py:260-355)."""
+    params.arcsoftmax_lambda_min = float(params.arcsoftmax_lambda_min)
+    params.arcsoftmax_lambda_base = float(params.arcsoftmax_lambda_base)
+    params.arcsoftmax_lambda_gamma = float(params.arcsoftmax_lambda_gamma)
+    params.arcsoftmax_lambda_power = float(params.arcsoftmax_lambda_power)
+    params.arcsoftmax_m = float(params.arcsoftmax_m)
+    _, fa, fs = margin_lambda(params.arcsoftmax_lambda_min, params.arcsoftmax_lambda_base,
+                              params.arcsoftmax_lambda_gamma, params.arcsoftmax_lambda_power, params.dict["global_step"])
+    return _run_head(features, labels, num_outputs, params, is_training, name, L.HEAD_AAM, margin=params.arcsoftmax_m,
+                     fa=fa, fs=fs)

@@ -1,0 +1,310 @@
+"""Trainer with the reference's surface (model/trainer.py:17-726): build / train / valid / predict / save / load.
+
+What changes: ``sess.run(train_op)`` (trainer.py:505-508) becomes ``train_step`` -- forward, backward, (data-parallel
+gradient all-reduce,) fused optimizer and BN moving-statistics update, all hand-written sm_100a kernels enqueued
+on one CUDA stream.  Host control flow (epochs, logging, checkpoints, LR bookkeeping) stays Python.  The Kaldi
+feature pipeline (dataset/data_loader.py) stays on the host: ``train``/``valid`` take any object with the
+``start()/fetch()/stop()`` queue protocol of KaldiDataRandomQueue (data_loader.py:310-414).
+"""
+import glob
+import os
+import re
+import sys
+import time
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..runtime import Engine, ScaledUtt, set_engine
+from . import tdnn as tdnn_mod
+from .tdnn import tdnn
+from .loss import softmax, asoftmax, additive_margin_softmax, additive_angular_margin_softmax, declare_head_variables
+
+
+class Trainer(object):
+    def __init__(self, params, model_dir, single_cpu=False, engine=None):
+        """Args mirror model/trainer.py:24.  ``single_cpu`` is accepted and ignored (the CUDA path has no CPU mode)."""
+        self.params = params
+        if params.network_type == "tdnn":
+            self.network = tdnn
+        else:
+            raise NotImplementedError("Not implement %s network" % params.network_type)
+        self.loss_type = None
+        self.loss_network = None
+        self.model = os.path.join(model_dir, "nnet")
+        self.model_log = os.path.join(model_dir, "log")
+        self.engine = set_engine(engine if engine is not None else Engine())
+        self.is_built = False
+        self.is_loaded = False
+        self.global_step = None
+        self.num_speakers = None
+        self.dim = None
+        self.modes = set()
+        self.opt = L.OPT_SGD
+        self.adam_t = 0
+        self.dp = None               # optional data-parallel wrapper (parallel.DataParallel)
+        self.endpoints = None
+        self.embeddings = None
+        self.train_ops = {}
+        self.valid_ops = {}
+
+    # ------------------------------------------------------------------ network (trainer.py:168-188)
+    def entire_network(self, features, params, is_training, reuse_variables, lengths=None):
+        features, endpoints = self.network(features, params, is_training, reuse_variables, lengths=lengths)
+        endpoints["output"] = features
+        if "feature_norm" in params.dict and params.feature_norm:
+            assert "feature_scaling_factor" in params.dict, "If feature normalization is applied, scaling factor is necessary."
+            features = ScaledUtt(features, params.feature_scaling_factor)
+            endpoints["output"] = features
+        return features, endpoints
+
+    # ------------------------------------------------------------------ build (trainer.py:190-449)
+    def build(self, mode, dim, loss_type=None, num_speakers=None, noupdate_var_list=None):
+        assert (mode == "train" or mode == "valid" or mode == "predict")
+        if noupdate_var_list is not None:
+            raise NotImplementedError("noupdate_var_list (fine-tuning) is outside the accelerated path")
+        eng = self.engine
+        self.dim = dim
+        if mode != "predict":
+            self.loss_type = loss_type
+            if loss_type == "softmax":
+                self.loss_network = softmax
+            elif loss_type == "asoftmax":
+                self.loss_network = asoftmax
+            elif loss_type == "additive_margin_softmax":
+                self.loss_network = additive_margin_softmax
+            elif loss_type == "additive_angular_margin_softmax":
+                self.loss_network = additive_angular_margin_softmax
+            else:
+                raise NotImplementedError("Not implement %s loss" % self.loss_type)
+            self.num_speakers = num_speakers
+            if self.global_step is None:
+                self.global_step = 0
+                self.params.dict["global_step"] = 0
+        if mode == "train":
+            if "optimizer" not in self.params.dict:
+                self.params.dict["optimizer"] = "sgd"
+            if self.params.optimizer == "sgd":
+                if "momentum" in self.params.dict:
+                    sys.exit("Using sgd as the optimizer and you should not specify the momentum.")
+                self.opt = L.OPT_SGD
+            elif self.params.optimizer == "momentum":
+                self.opt = L.OPT_NESTEROV if self.params.use_nesterov else L.OPT_MOMENTUM
+            elif self.params.optimizer == "adam":
+                self.opt = L.OPT_ADAM
+            else:
+                sys.exit("Optimizer %s is not supported." % self.params.optimizer)
+        if not eng.store.finalized:
+            tdnn_mod.declare_variables(eng, dim, self.params)
+            if mode != "predict":
+                e = int(self.params.dict.get("num_nodes_last_layer", 512))
+                declare_head_variables(eng, e, num_speakers, self.params, loss_type)
+            eng.store.finalize()
+            eng.store.init(int(self.params.dict.get("seed", 0)))
+        elif mode != "predict" and "softmax/output/kernel" not in eng.store:
+            raise L.XvError("build('predict') was called first: the head variables cannot be added afterwards; "
+                            "build train/valid before predict")
+        self.modes.add(mode)
+        self.is_built = True
+
+    # ------------------------------------------------------------------ one step = sess.run(train_op)
+    def _to_device(self, features, labels=None):
+        dev = self.engine.device
+        if not torch.is_tensor(features):
+            features = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+        features = features.to(dev, dtype=torch.float32, non_blocking=True)
+        if labels is not None:
+            if not torch.is_tensor(labels):
+                labels = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
+            labels = labels.to(dev, dtype=torch.int32, non_blocking=True)
+        return features, labels
+
+    def forward_backward(self, features, labels, global_step):
+        """Forward + backward of one batch; gradients are left in the flat gradient buffer."""
+        eng = self.engine
+        features, labels = self._to_device(features, labels)
+        self.params.dict["global_step"] = int(global_step)
+        eng.begin_step(True)
+        out, endpoints = self.entire_network(features, self.params, True, True)
+        loss, endpoints_loss = self.loss_network(out, labels, self.num_speakers, self.params, True, True)
+        endpoints.update(endpoints_loss)
+        self.endpoints = endpoints
+        reg = eng.l2_loss()
+        eng.backward()
+        return loss, reg
+
+    def train_step(self, features, labels, learning_rate, global_step=None, fetch_loss=False):
+        """The hot-loop body (trainer.py:491-508).  Returns {"loss": total, "raw_loss": loss} when fetch_loss."""
+        eng = self.engine
+        if global_step is None:
+            global_step = self.global_step
+        loss, reg = self.forward_backward(features, labels, global_step)
+        if self.dp is not None:
+            self.dp.allreduce_gradients()
+        if self.opt == L.OPT_ADAM:
+            self.adam_t += 1
+        clip = bool(self.params.dict.get("clip_gradient", False))
+        eng.set_hyper(float(learning_rate), float(self.params.dict.get("momentum", 0.0)), float(max(self.adam_t, 1)),
+                      float(self.params.dict.get("clip_gradient_norm", 0.0)) if clip else 0.0)
+        eng.optimizer_step(self.opt, clip=clip)
+        self.global_step = int(global_step) + 1
+        if fetch_loss:
+            vals = eng.scalars[:4].tolist()          # one D2H read
+            raw = vals[0]
+            if self.dp is not None:
+                raw = self.dp.mean_scalar(raw)
+            self.train_ops = {"raw_loss": raw, "loss": raw + vals[1] + vals[3]}
+            return dict(self.train_ops)
+        return None
+
+    def train(self, data, spklist, learning_rate, aux_data=None):
+        """One epoch (trainer.py:451-520).  ``data``: object with start()/fetch()/stop() yielding (features, labels)."""
+        assert "train" in self.modes
+        if not hasattr(data, "fetch"):
+            raise NotImplementedError("The Kaldi feature pipeline stays on the host: pass a loader object with "
+                                      "start()/fetch()/stop() (e.g. dataset.data_loader.KaldiDataRandomQueue).")
+        curr_step = self.global_step or 0
+        if hasattr(data, "start"):
+            data.start()
+        steps = int(self.params.num_steps_per_epoch)
+        t0 = time.time()
+        for step in range(curr_step % steps, steps):
+            show = (step % int(self.params.show_training_progress) == 0)
+            features, labels = data.fetch()
+            res = self.train_step(features, labels, learning_rate, curr_step, fetch_loss=show)
+            if show:
+                dt = time.time() - t0
+                t0 = time.time()
+                print("Epoch: [%2d] step: [%2d/%2d] time: %.4f s/step, raw loss: %f, total loss: %f"
+                      % (curr_step // steps, step, steps, dt / int(self.params.show_training_progress),
+                         res["raw_loss"], res["loss"]))
+            if curr_step % int(self.params.save_checkpoints_steps) == 0 and curr_step != 0:
+                self.save(curr_step)
+            curr_step += 1
+        self.save(curr_step)
+        if hasattr(data, "stop"):
+            data.stop()
+        return
+
+    # ------------------------------------------------------------------ validation (trainer.py:261-303, 592-706)
+    def _valid_params(self):
+        vp = type(self.params).__new__(type(self.params))
+        vp.__dict__.update(self.params.dict)
+        if self.loss_type == "asoftmax":
+            vp.asoftmax_m = 1
+        elif self.loss_type == "additive_margin_softmax":
+            vp.amsoftmax_m = 0
+        elif self.loss_type == "additive_angular_margin_softmax":
+            vp.arcsoftmax_m = 0
+        if "aux_loss_func" in vp.dict:
+            vp.aux_loss_func = []
+        return vp
+
+    def valid_step(self, features, labels):
+        """Loss of the validation graph (is_training=False, margins neutralised) and the output embeddings."""
+        eng = self.engine
+        features, labels = self._to_device(features, labels)
+        vp = self._valid_params()
+        vp.dict["global_step"] = self.global_step or 0
+        eng.begin_step(False)
+        out, endpoints = self.entire_network(features, vp, False, True)
+        loss, _ = self.loss_network(out, labels, self.num_speakers, vp, False, True)
+        self.endpoints = endpoints
+        return float(loss.item()), endpoints["output"].dense()
+
+    def valid(self, data, spklist, batch_type="softmax", output_embeddings=False, aux_data=None):
+        assert "valid" in self.modes or "train" in self.modes
+        if not hasattr(data, "fetch"):
+            raise NotImplementedError("pass a loader object with start()/fetch()/stop()")
+        if hasattr(data, "start"):
+            data.start()
+        losses, embs, labs = [], [], []
+        for _ in range(int(self.params.valid_max_iterations)):
+            try:
+                features, labels = data.fetch()
+            except Exception:
+                break
+            l, e = self.valid_step(features, labels)
+            losses.append(l)
+            if output_embeddings:
+                embs.append(e.cpu().numpy())
+                labs.append(np.asarray(labels))
+        if hasattr(data, "stop"):
+            data.stop()
+        loss = float(np.mean(losses)) if losses else 0.0
+        if output_embeddings:
+            return loss, np.concatenate(embs, 0), np.concatenate(labs, 0)
+        return loss, None, None
+
+    # ------------------------------------------------------------------ prediction (trainer.py:708-726)
+    def predict(self, features):
+        """features: np [T, D] or [N, T, D] -> embeddings np [E] or [N, E] from endpoints[embedding_node]."""
+        features = np.asarray(features, dtype=np.float32)
+        rank = features.ndim
+        if rank == 2:
+            features = features[None]
+        emb = self.predict_batch_padded(features, None)
+        return emb[0] if rank == 2 else emb
+
+    def predict_batch_padded(self, features, lengths):
+        """[N, Tmax, D] (+ optional lengths [N]) -> np [N, E]; rows are independent (BN in inference mode, masked
+        pooling), so a ragged batch gives the same result as one call per utterance (extract.py:90)."""
+        eng = self.engine
+        feats, _ = self._to_device(features)
+        ln = None if lengths is None else torch.as_tensor(np.asarray(lengths), dtype=torch.int32, device=eng.device)
+        eng.begin_step(False)
+        _, endpoints = self.entire_network(feats, self.params, False, True, lengths=ln)
+        self.endpoints = endpoints
+        node = endpoints[self.params.embedding_node]
+        return node.dense().float().cpu().numpy()
+
+    # ------------------------------------------------------------------ checkpoints (trainer.py:142-166)
+    def save(self, step):
+        os.makedirs(self.model, exist_ok=True)
+        st = self.engine.store
+        vals = st.export_tf()
+        path = os.path.join(self.model, "model-%d.npz" % step)
+        extra = {}
+        if st.state1 is not None:
+            extra["__opt_state1"] = st.state1.cpu().numpy()
+        if st.state2 is not None:
+            extra["__opt_state2"] = st.state2.cpu().numpy()
+        np.savez(path, __step=np.int64(step), __adam_t=np.int64(self.adam_t), **vals, **extra)
+        with open(os.path.join(self.model, "checkpoint"), "w") as f:
+            f.write('model_checkpoint_path: "model-%d"\n' % step)
+        keep = int(self.params.dict.get("keep_checkpoint_max", 5))
+        ckpts = sorted(glob.glob(os.path.join(self.model, "model-*.npz")),
+                       key=lambda p: int(re.search(r"model-(\d+)\.npz", p).group(1)))
+        for old in ckpts[:-keep] if keep > 0 else []:
+            os.remove(old)
+
+    def load(self):
+        ck = os.path.join(self.model, "checkpoint")
+        if not os.path.isfile(ck):
+            sys.exit("Cannot find model in %s" % self.model)
+        name = re.search(r'"(.*)"', open(ck).readline()).group(1)
+        step = int(next(re.finditer(r"(\d+)(?!.*\d)", name)).group(0))      # trainer.py:149-153
+        z = np.load(os.path.join(self.model, name + ".npz"))
+        st = self.engine.store
+        st.load_tf({k: z[k] for k in z.files if not k.startswith("__")})
+        if "__opt_state1" in z.files:
+            st.ensure_opt_state(L.OPT_MOMENTUM)
+            st.state1.copy_(torch.from_numpy(z["__opt_state1"]))
+        if "__opt_state2" in z.files:
+            st.ensure_opt_state(L.OPT_ADAM)
+            st.state2.copy_(torch.from_numpy(z["__opt_state2"]))
+        self.adam_t = int(z["__adam_t"]) if "__adam_t" in z.files else 0
+        self.global_step = step
+        self.is_loaded = True
+        return step
+
+    def reset(self):
+        self.engine = set_engine(Engine())
+        self.is_built = False
+        self.is_loaded = False
+        self.global_step = None
+        self.modes = set()
+
+    def close(self):
+        torch.cuda.synchronize()

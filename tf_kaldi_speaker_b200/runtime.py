@@ -1,0 +1,602 @@
+"""Device-side runtime of the x-vector path: parameter store, workspaces and the kernel sequencer ("Engine").
+
+The reference builds a TF1 graph and lets ``sess.run`` execute it (model/trainer.py:351-436, 491-508).  Here
+the operator functions in ``model/`` call Engine methods that enqueue hand-written sm_100a kernels (through the
+C ABI in libxvector_b200.so) on the current CUDA stream and push their backward closures on a tape; PyTorch
+only owns device memory and streams.  There is no CPU fallback.
+
+Data layout in HBM:
+  * parameters: ONE flat fp32 buffer (tensors start at multiples of 1024 elements) + one flat fp32 gradient
+    buffer of the same layout (a single NCCL all-reduce covers every gradient) + optimizer state + a flat bf16
+    "shadow" buffer holding the tensor-core copies of the kernels (plain, or the [hi; lo; hi] 3-term split).
+  * frame-level activations: bf16, channels-last, flat-time [B*T, C_pad]; the row stride T is constant through
+    tdnn1..5 and rows with t >= valid length are kept at zero ("invalid rows").
+  * utterance-level activations: fp32 [B, C] plus a bf16 [hi | hi | lo] split copy feeding the GEMMs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+ALIGN = 1024
+BN_EPS = 1e-3
+
+
+def _pad_to(n, m):
+    return (n + m - 1) // m * m
+
+
+class VarSpec(object):
+    def __init__(self, name, tf_shape, ishape, row_map=None, l2=0.0, shadow="none", init="zeros", trainable=True,
+                 fans=None, pad_value=0.0):
+        self.name, self.tf_shape, self.ishape = name, tuple(tf_shape), tuple(ishape)
+        self.row_map, self.l2, self.shadow, self.init = row_map, float(l2), shadow, init
+        self.trainable, self.fans, self.pad_value = trainable, fans, pad_value
+        self.numel = int(np.prod(self.ishape))
+        self.offset = None
+        self.shadow_offset = None
+
+    # TF-shaped numpy <-> internal (padded) numpy
+    def to_internal(self, arr):
+        arr = np.asarray(arr, dtype=np.float32)
+        assert tuple(arr.shape) == self.tf_shape, "%s: expected %s, got %s" % (self.name, self.tf_shape, arr.shape)
+        out = np.full(self.ishape, self.pad_value, dtype=np.float32)
+        if len(self.ishape) == 1:
+            out[:arr.size] = arr.reshape(-1)
+            return out
+        a2 = arr.reshape(-1, arr.shape[-1])
+        rows = np.arange(a2.shape[0]) if self.row_map is None else self.row_map
+        out[rows, :a2.shape[1]] = a2
+        if self.pad_value != 0.0:       # padded rows of a matrix are always zero
+            mask = np.ones(self.ishape[0], dtype=bool)
+            mask[rows] = False
+            out[mask] = 0.0
+            out[:, a2.shape[1]:] = 0.0
+        return out
+
+    def to_tf(self, arr):
+        arr = np.asarray(arr, dtype=np.float32).reshape(self.ishape)
+        if len(self.ishape) == 1:
+            return arr[:int(np.prod(self.tf_shape))].reshape(self.tf_shape).copy()
+        ncol = self.tf_shape[-1]
+        nrow = int(np.prod(self.tf_shape[:-1]))
+        rows = np.arange(nrow) if self.row_map is None else self.row_map
+        return arr[rows, :ncol].reshape(self.tf_shape).copy()
+
+
+class ParamStore(object):
+    """Name-keyed variables (TF variable names = checkpoint keys) in flat device buffers."""
+
+    def __init__(self, device):
+        self.device = device
+        self.specs = OrderedDict()
+        self.finalized = False
+
+    def declare(self, spec):
+        assert not self.finalized
+        if spec.name in self.specs:
+            return self.specs[spec.name]
+        self.specs[spec.name] = spec
+        return spec
+
+    def __contains__(self, name):
+        return name in self.specs
+
+    def finalize(self):
+        off = soff = boff = 0
+        for s in self.specs.values():
+            if s.trainable:
+                s.offset = off
+                off += _pad_to(s.numel, ALIGN)
+                if s.shadow == "plain":
+                    s.shadow_offset = soff
+                    soff += _pad_to(s.numel, ALIGN)
+                elif s.shadow == "split":
+                    assert s.numel % ALIGN == 0, "%s: split shadows need numel %% 1024 == 0" % s.name
+                    s.shadow_offset = soff
+                    soff += 3 * s.numel
+            else:
+                s.offset = boff
+                boff += _pad_to(s.numel, 32)
+        self.n = max(off, ALIGN)
+        dev = self.device
+        self.params = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.state1 = None
+        self.state2 = None
+        self.shadow = torch.zeros(max(soff, ALIGN), dtype=torch.bfloat16, device=dev)
+        self.buffers = torch.zeros(max(boff, 32), dtype=torch.float32, device=dev)
+        nblk = self.n // ALIGN
+        l2 = np.zeros(nblk, dtype=np.float32)
+        sh = np.full(nblk, -1, dtype=np.int64)
+        st = np.zeros(nblk, dtype=np.int64)
+        for s in self.specs.values():
+            if not s.trainable:
+                continue
+            b0, nb = s.offset // ALIGN, _pad_to(s.numel, ALIGN) // ALIGN
+            l2[b0:b0 + nb] = s.l2
+            if s.shadow != "none":
+                sh[b0:b0 + nb] = s.shadow_offset + np.arange(nb) * ALIGN
+                if s.shadow == "split":
+                    st[b0:b0 + nb] = s.numel
+        self.blk_l2 = torch.from_numpy(l2).to(dev)
+        self.blk_shadow = torch.from_numpy(sh).to(dev)
+        self.blk_stride = torch.from_numpy(st).to(dev)
+        self.finalized = True
+
+    # ---- views
+    def _buf(self, s):
+        return self.params if s.trainable else self.buffers
+
+    def view(self, name):
+        s = self.specs[name]
+        return self._buf(s)[s.offset:s.offset + s.numel].view(*s.ishape)
+
+    def grad(self, name):
+        s = self.specs[name]
+        return self.grads[s.offset:s.offset + s.numel].view(*s.ishape)
+
+    def shadow_view(self, name):
+        """bf16 [rows (x3 for split), cols] tensor-core copy of a kernel."""
+        s = self.specs[name]
+        assert s.shadow != "none"
+        rows, cols = s.ishape
+        if s.shadow == "split":
+            return self.shadow[s.shadow_offset:s.shadow_offset + 3 * s.numel].view(3 * rows, cols)
+        return self.shadow[s.shadow_offset:s.shadow_offset + s.numel].view(rows, cols)
+
+    # ---- values
+    def load_tf(self, values):
+        """values: name -> array in TF shape (missing names keep their current value)."""
+        for name, arr in values.items():
+            if name not in self.specs:
+                continue
+            if isinstance(arr, torch.Tensor):
+                arr = arr.detach().cpu().double().numpy()
+            s = self.specs[name]
+            self.view(name).copy_(torch.from_numpy(s.to_internal(arr)).to(self.device))
+        self.refresh_shadows()
+
+    def export_tf(self, grads=False):
+        out = OrderedDict()
+        for name, s in self.specs.items():
+            if grads and not s.trainable:
+                continue
+            t = self.grad(name) if grads else self.view(name)
+            out[name] = s.to_tf(t.detach().cpu().numpy())
+        return out
+
+    def init(self, seed=0):
+        gen = torch.Generator().manual_seed(seed)
+        vals = {}
+        for name, s in self.specs.items():
+            shp = s.tf_shape
+            if s.init == "glorot":
+                fan_in, fan_out = s.fans
+                lim = math.sqrt(6.0 / (fan_in + fan_out))
+                v = (torch.rand(shp, generator=gen, dtype=torch.float64) * 2 - 1) * lim
+            elif s.init == "ones":
+                v = torch.ones(shp, dtype=torch.float64)
+            elif s.init == "trunc_normal":
+                v = torch.empty(shp, dtype=torch.float64)
+                torch.nn.init.trunc_normal_(v, 0.0, 0.1, -0.2, 0.2, generator=gen)
+            elif isinstance(s.init, float):
+                v = torch.full(shp, s.init, dtype=torch.float64)
+            else:
+                v = torch.zeros(shp, dtype=torch.float64)
+            vals[name] = v.numpy()
+        self.load_tf(vals)
+
+    def refresh_shadows(self):
+        L.check(L.load().xv_shadow_refresh(L.ptr(self.params), L.ptr(self.blk_shadow), L.ptr(self.blk_stride),
+                                           L.ptr(self.shadow), C.c_int64(self.n), L.stream_ptr()))
+
+    def ensure_opt_state(self, opt):
+        if opt != L.OPT_SGD and self.state1 is None:
+            self.state1 = torch.zeros_like(self.params)
+        if opt == L.OPT_ADAM and self.state2 is None:
+            self.state2 = torch.zeros_like(self.params)
+
+
+class FrameAct(object):
+    """Handle of a frame-level tensor: bf16 [B*T, ld] flat-time, valid length per segment."""
+
+    def __init__(self, data, B, T, valid, C_real, lengths=None, name=""):
+        self.data, self.B, self.T, self.valid, self.C, self.lengths, self.name = data, B, T, valid, C_real, lengths, name
+        self.grad = None
+        self.needs_grad = False
+
+    @property
+    def ld(self):
+        return self.data.shape[1]
+
+    def dense(self):
+        """fp32 [B, valid, C] copy (inspection / endpoints only; uniform valid length)."""
+        return self.data.view(self.B, self.T, self.ld)[:, :self.valid, :self.C].float()
+
+    def lengths_ptr(self):
+        return L.ptr(self.lengths)
+
+
+class UttAct(object):
+    """Handle of an utterance-level tensor: fp32 [B, C] (+ optional bf16 split copy [B, 3C])."""
+
+    def __init__(self, data, split=None, name="", col_map=None):
+        self.data, self.split, self.name, self.col_map = data, split, name, col_map
+        self.grad = None
+        self.needs_grad = False
+
+    def dense(self):
+        return self.data if self.col_map is None else self.data[:, self.col_map]
+
+
+class ScaledUtt(UttAct):
+    """View of an utterance tensor with a pending l2_scaling (model/trainer.py:183-186, model/common.py:45-58):
+    the scaling itself is fused into the head's feature-preparation kernel; gradients land on the base."""
+
+    def __init__(self, base, scaling):
+        self.base, self.scaling = base, float(scaling)
+        self.data, self.split, self.name, self.col_map = base.data, None, base.name, base.col_map
+        self.needs_grad = base.needs_grad
+
+    @property
+    def grad(self):
+        return self.base.grad
+
+    @grad.setter
+    def grad(self, g):
+        self.base.grad = g
+
+    def dense(self):
+        x = self.base.dense()
+        sq = (x * x).sum(-1, keepdim=True)
+        return x * (torch.rsqrt(torch.clamp(sq, min=1e-12)) * self.scaling)
+
+
+class Engine(object):
+    """Sequences the sm_100a kernels of one replica on the current stream."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise L.XvError("xvector_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lib = L.load()
+        info = (C.c_int32 * 3)()
+        L.check(self.lib.xv_device_info(info))
+        self.num_sms = int(info[0])
+        if int(info[1]) != 10:
+            raise L.XvError("xvector_b200 kernels are sm_100a only (found cc %d.%d)" % (info[1], info[2]))
+        self.store = ParamStore(self.device)
+        self.ws = {}
+        self.tape = []
+        self.penalties = []
+        self.launches = 0
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.sched = torch.tensor([1.0, 0.0], dtype=torch.float32, device=self.device)
+        self.scalars = torch.zeros(8, dtype=torch.float32, device=self.device)   # [0] loss, [1] l2 loss, [2] grad sumsq, [3] penalty
+        self.inv_global_batch = None     # set by the data-parallel wrapper (1 / (N * B))
+
+    # ---- memory
+    def buf(self, name, shape, dtype, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self.ws.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self.ws[key] = t
+        elif zero:
+            t.zero_()
+        return t
+
+    def call(self, fn, *args):
+        self.launches += 1
+        L.check(fn(*args))
+
+    def gemm(self, *a, **kw):
+        self.launches += 1
+        L.gemm(*a, **kw)
+
+    def splits_for(self, M, N, K, max_splits=32):
+        tiles = ((M + 127) // 128) * ((N + 255) // 256)
+        kb = (K + 63) // 64
+        s = max(1, min(max_splits, self.num_sms // max(tiles, 1), kb))
+        return s
+
+    # ---- step bookkeeping
+    def begin_step(self, training):
+        self.tape = []
+        self.penalties = []
+        self.training = training
+        self.scalars.zero_()
+        if training:
+            self.store.grads.zero_()
+
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
+    # ---- frame-level ops ------------------------------------------------------------------------
+    def pack_input(self, features, lengths=None, k=5, dpad=32):
+        """features f32 [B, T, D] on device -> im2col FrameAct [B*T, 192] for tdnn1 (K = 5*32 padded to 192)."""
+        assert features.is_cuda and features.dtype == torch.float32 and features.dim() == 3
+        features = features.contiguous()
+        B, T, D = features.shape
+        assert D <= dpad
+        ldo = _pad_to(k * dpad, 64)
+        out = self.buf("input/col", (B * T, ldo), torch.bfloat16)
+        self.call(self.lib.xv_pack_input, L.ptr(features), L.ptr(out), B, T, D, k, dpad, C.c_int64(ldo), L.stream_ptr())
+        ln = None
+        if lengths is not None:
+            ln = lengths.to(device=self.device, dtype=torch.int32) - (k - 1)
+        return FrameAct(out, B, T, T - (k - 1), k * dpad, ln, "input")
+
+    def frame_affine(self, x, kernel, bias, k, cout, name, training, bn=None, act=L.ACT_RELU, alpha=None,
+                     unbiased_moving_var=False, momentum=0.99):
+        """affine (temporal conv of width k as implicit GEMM, or dense) -> [BN] -> activation.
+        Returns (pre-BN FrameAct y, post-activation FrameAct a).  bn = (gamma, beta, moving_mean, moving_var) names."""
+        st = self.store
+        W = st.shadow_view(kernel)                     # [k*cin_pad, cout_pad] bf16
+        K, cout_pad = W.shape
+        R = x.B * x.T
+        shrink = k - 1
+        valid = x.valid - shrink
+        lengths = None if x.lengths is None else (x.lengths - shrink)
+        assert K == k * x.ld, "%s: kernel rows %d != k*ld %d" % (name, K, k * x.ld)
+        y = self.buf(name + "/y", (R, cout_pad), torch.bfloat16)
+        use_stats = training and bn is not None
+        if use_stats:
+            stats = self.buf(name + "/stats", (2, cout_pad), torch.float32, zero=True)
+        a_op = L.operand(x.data, False, div=(x.ld if k > 1 else 0), tap_rows=(1 if k > 1 else 0))
+        self.gemm(a_op, L.operand(W, True), R, cout_pad, K, y, epilogue=L.EPI_BF16, bias=st.view(bias),
+                  col_sum=stats[0] if use_stats else None, col_sumsq=stats[1] if use_stats else None,
+                  seg_len=x.T, seg_valid=valid)
+        if use_stats and lengths is not None:
+            raise NotImplementedError("training-mode BN needs one valid length per batch (data_loader.py:273)")
+        scale = self.buf(name + "/scale", (cout_pad,), torch.float32)
+        shift = self.buf(name + "/shift", (cout_pad,), torch.float32)
+        smean = self.buf(name + "/save_mean", (cout_pad,), torch.float32)
+        srstd = self.buf(name + "/save_rstd", (cout_pad,), torch.float32)
+        count = float(x.B * valid)
+        if bn is None:
+            scale.fill_(1.0)
+            shift.zero_()
+            smean.zero_()
+            srstd.fill_(1.0)
+        elif training:
+            self.call(self.lib.xv_bn_finalize_train, L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(st.view(bias)),
+                      C.c_float(count), L.ptr(st.view(bn[0])), L.ptr(st.view(bn[1])), L.ptr(st.view(bn[2])),
+                      L.ptr(st.view(bn[3])), C.c_float(momentum), C.c_float(BN_EPS), int(unbiased_moving_var),
+                      L.ptr(scale), L.ptr(shift), L.ptr(smean), L.ptr(srstd), cout_pad, L.stream_ptr())
+        else:
+            self.call(self.lib.xv_bn_finalize_infer, L.ptr(st.view(bn[0])), L.ptr(st.view(bn[1])), L.ptr(st.view(bn[2])),
+                      L.ptr(st.view(bn[3])), C.c_float(BN_EPS), L.ptr(scale), L.ptr(shift), cout_pad, L.stream_ptr())
+        a = self.buf(name + "/a", (R, cout_pad), torch.bfloat16)
+        alpha_t = None if alpha is None else st.view(alpha)
+        lp = L.ptr(lengths)
+        self.call(self.lib.xv_bn_act_apply, L.ptr(y), L.ptr(a), L.ptr(scale), L.ptr(shift), L.ptr(alpha_t), act,
+                  C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, L.stream_ptr())
+        ya = FrameAct(y, x.B, x.T, valid, cout, lengths, name + "/y")
+        ya.affine = (scale, shift)
+        aa = FrameAct(a, x.B, x.T, valid, cout, lengths, name + "/a")
+
+        if training:
+            def bwd():
+                if aa.grad is None:
+                    return
+                if bn is not None:
+                    dgamma, dbeta = st.grad(bn[0]), st.grad(bn[1])
+                else:
+                    dgamma = self.buf(name + "/dgamma0", (cout_pad,), torch.float32, zero=True)
+                    dbeta = st.grad(bias)
+                dalpha = None if alpha is None else st.grad(alpha)
+                self.call(self.lib.xv_bn_act_bwd_reduce, L.ptr(y), L.ptr(aa.grad), L.ptr(scale), L.ptr(shift),
+                          L.ptr(smean), L.ptr(srstd), L.ptr(alpha_t), act, C.c_int64(R), cout_pad, C.c_int64(cout_pad),
+                          x.T, valid, lp, L.ptr(dgamma), L.ptr(dbeta), L.ptr(dalpha), L.stream_ptr())
+                dy = self.buf(name + "/dy", (R, cout_pad), torch.bfloat16)
+                if bn is not None:
+                    dg_used, db_used = dgamma, dbeta
+                else:       # no BN: dy = g; the reductions above were the bias gradient
+                    dg_used = db_used = self.buf(name + "/zeros", (cout_pad,), torch.float32, zero=True)
+                self.call(self.lib.xv_bn_act_bwd_apply, L.ptr(y), L.ptr(aa.grad), L.ptr(dy), L.ptr(scale), L.ptr(shift),
+                          L.ptr(smean), L.ptr(srstd), L.ptr(dg_used), L.ptr(db_used), C.c_float(count), L.ptr(alpha_t),
+                          act, C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, L.stream_ptr())
+                # wgrad: dW[(j,c), n] = sum_r X[r+j, c] dY[r, n]
+                gw = st.grad(kernel)
+                self.gemm(L.operand(x.data, True, div=(x.ld if k > 1 else 0), tap_rows=(1 if k > 1 else 0)),
+                          L.operand(dy, True), K, cout_pad, R, gw, epilogue=L.EPI_F32,
+                          splits=self.splits_for(K, cout_pad, R))
+                if x.needs_grad:
+                    # dgrad: dX[q, c] = sum_j dY[q-j, :] W_j[c, :]^T
+                    dx = self.buf(x.name + "/grad", (R, x.ld), torch.bfloat16)
+                    self.gemm(L.operand(dy, False, div=(cout_pad if k > 1 else 0), tap_rows=(-1 if k > 1 else 0)),
+                              L.operand(W, False, div=(cout_pad if k > 1 else 0), tap_rows=(x.ld if k > 1 else 0)),
+                              R, x.ld, k * cout_pad, dx, epilogue=L.EPI_BF16)
+                    x.grad = dx
+            self.tape.append(bwd)
+            aa.needs_grad = True
+        return ya, aa
+
+    def stats_pool(self, x, training):
+        cpad = x.ld
+        out = self.buf("pool/out", (x.B, 2 * cpad), torch.float32)
+        out3 = self.buf("pool/out3", (x.B, 6 * cpad), torch.bfloat16)
+        self.call(self.lib.xv_stats_pool_fwd, L.ptr(x.data), L.ptr(out), L.ptr(out3), x.B, x.T, x.valid, x.lengths_ptr(),
+                  x.C, cpad, C.c_int64(cpad), L.stream_ptr())
+        col_map = torch.cat([torch.arange(x.C), cpad + torch.arange(x.C)]).to(self.device)
+        u = UttAct(out, out3, "pool", col_map)
+        if training:
+            def bwd():
+                if u.grad is None:
+                    return
+                dx = self.buf(x.name + "/grad", (x.B * x.T, cpad), torch.bfloat16)
+                self.call(self.lib.xv_stats_pool_bwd, L.ptr(x.data), L.ptr(out), L.ptr(u.grad), L.ptr(dx), x.B, x.T,
+                          x.valid, x.lengths_ptr(), x.C, cpad, C.c_int64(cpad), L.stream_ptr())
+                x.grad = dx
+            self.tape.append(bwd)
+            u.needs_grad = True
+        return u
+
+    # ---- utterance-level ops ----------------------------------------------------------------------
+    def utt_affine(self, u, kernel, bias, name, training, bn=None, act=L.ACT_RELU, alpha=None, momentum=0.99):
+        """dense -> [BN over the batch] -> activation on fp32 [B, C] (tdnn6 / tdnn7, model/tdnn.py:147-189).
+        Returns (pre-BN UttAct, BN-output tensor or None, post-activation UttAct)."""
+        st = self.store
+        W3 = st.shadow_view(kernel)                    # [3K, cout] = [hi; lo; hi]
+        K = W3.shape[0] // 3
+        cout = W3.shape[1]
+        B = u.data.shape[0]
+        assert u.split is not None and u.split.shape[1] == 3 * K, "%s: input split %s vs K %d" % (name, tuple(u.split.shape), K)
+        splits = self.splits_for(B, cout, 3 * K)
+        y = self.buf(name + "/y", (B, cout), torch.float32, zero=(splits > 1))
+        self.gemm(L.operand(u.split, False), L.operand(W3, True), B, cout, 3 * K, y, epilogue=L.EPI_F32, splits=splits,
+                  bias=st.view(bias))
+        mode = 0 if bn is None else (1 if training else 2)
+        a = self.buf(name + "/a", (B, cout), torch.float32)
+        a3 = self.buf(name + "/a3", (B, 3 * cout), torch.bfloat16)
+        bn_out = self.buf(name + "/bn", (B, cout), torch.float32) if bn is not None else None
+        smean = self.buf(name + "/save_mean", (cout,), torch.float32)
+        srstd = self.buf(name + "/save_rstd", (cout,), torch.float32)
+        g = lambda i: (L.ptr(st.view(bn[i])) if bn is not None else L.ptr(None))
+        alpha_t = None if alpha is None else st.view(alpha)
+        self.call(self.lib.xv_bn_rows_fwd, L.ptr(y), B, cout, mode, g(0), g(1), g(2), g(3), C.c_float(momentum),
+                  C.c_float(BN_EPS), L.ptr(alpha_t), act, L.ptr(bn_out), L.ptr(a), L.ptr(a3), 3, L.ptr(smean),
+                  L.ptr(srstd), L.stream_ptr())
+        yu = UttAct(y, None, name + "/y")
+        au = UttAct(a, a3, name + "/a")
+        if bn_out is not None:
+            bn_out = UttAct(bn_out, None, name + "/bn")
+        if training:
+            def bwd():
+                if au.grad is None and yu.grad is None:
+                    return
+                da = au.grad if au.grad is not None else torch.zeros_like(a)
+                dy = self.buf(name + "/dy", (B, cout), torch.float32)
+                dyb = self.buf(name + "/dyb", (B, cout), torch.bfloat16)
+                gg = lambda i: (L.ptr(st.grad(bn[i])) if bn is not None else L.ptr(None))
+                self.call(self.lib.xv_bn_rows_bwd, L.ptr(y), L.ptr(da), B, cout, mode, g(0), g(1), L.ptr(smean),
+                          L.ptr(srstd), L.ptr(alpha_t), act, L.ptr(dy), L.ptr(dyb), gg(0), gg(1),
+                          L.ptr(None if alpha is None else st.grad(alpha)), L.ptr(st.grad(bias)), L.stream_ptr())
+                # wgrad: dW[kk, n] = sum_i u[i, kk] dy[i, n]   (A = bf16(u) MN-major window of the split copy)
+                self.gemm(L.operand(u.split, True, cols=K), L.operand(dyb, True), K, cout, B, st.grad(kernel),
+                          epilogue=L.EPI_F32)
+                if u.needs_grad:
+                    du = self.buf(u.name + "/grad", (B, K), torch.float32)
+                    self.gemm(L.operand(dyb, False), L.operand(W3, False, rows=K), B, K, cout, du, epilogue=L.EPI_F32)
+                    u.grad = du
+            self.tape.append(bwd)
+            au.needs_grad = True
+            yu.needs_grad = True
+        return yu, bn_out, au
+
+    # ---- head -------------------------------------------------------------------------------------
+    def margin_head(self, u, labels, kernel, bias, head_type, num_outputs, training, margin=0.0, asoftmax_m=1,
+                    scaling=0.0, want_logits=False):
+        """Fused normalise -> cosine GEMM -> margin -> online log-sum-exp (model/loss.py heads + l2_scaling).
+        ``u`` is the network output before feature_norm; returns (loss scalar tensor view, logits or None, x)."""
+        st = self.store
+        Wm = st.view(kernel)                           # fp32 [E, Cpad]
+        E, cpad = Wm.shape
+        Cn = num_outputs
+        B = u.data.shape[0]
+        normalize = 0 if head_type == L.HEAD_SOFTMAX else 1
+        wn3 = self.buf("head/wn3", (3 * E, cpad), torch.bfloat16)
+        inv_norm = self.buf("head/inv_norm", (cpad,), torch.float32)
+        self.call(self.lib.xv_head_prep_weights, L.ptr(Wm), L.ptr(wn3), L.ptr(inv_norm), E, cpad, C.c_int64(cpad),
+                  normalize, L.stream_ptr())
+        x = self.buf("head/x", (B, E), torch.float32)
+        x3 = self.buf("head/x3", (B, 3 * E), torch.bfloat16)
+        xnorm = self.buf("head/xnorm", (B,), torch.float32)
+        urinv = self.buf("head/urinv", (B,), torch.float32)
+        self.call(self.lib.xv_head_prep_features, L.ptr(u.data), C.c_float(scaling), L.ptr(x), L.ptr(x3), L.ptr(xnorm),
+                  L.ptr(urinv), B, E, L.stream_ptr())
+        labels = labels.to(device=self.device, dtype=torch.int32).contiguous()
+        nblk = (Cn + 255) // 256
+        pmax = self.buf("head/pmax", (nblk, B), torch.float32)
+        psum = self.buf("head/psum", (nblk, B), torch.float32)
+        tgt = self.buf("head/target", (B,), torch.float32)
+        lse = self.buf("head/lse", (B,), torch.float32)
+        gnorm = self.buf("head/gnorm", (B,), torch.float32, zero=True)
+        logits = self.buf("head/logits", (B, cpad), torch.float32) if want_logits else None
+        inv_batch = self.inv_global_batch if self.inv_global_batch is not None else 1.0 / B
+        h = L.HeadArgs()
+        h.type, h.asoftmax_m, h.margin = head_type, asoftmax_m, margin
+        h.sched = self.sched.data_ptr()
+        h.labels, h.xnorm = labels.data_ptr(), xnorm.data_ptr()
+        h.part_max, h.part_sum, h.target_logit = pmax.data_ptr(), psum.data_ptr(), tgt.data_ptr()
+        h.logits_out = 0 if logits is None else logits.data_ptr()
+        h.lse, h.inv_batch, h.gnorm = lse.data_ptr(), inv_batch, gnorm.data_ptr()
+        bias_t = None if bias is None else st.view(bias)
+        dummy = self.buf("head/dummy", (8,), torch.float32)
+        self.gemm(L.operand(x3, False), L.operand(wn3, True, cols=Cn), B, Cn, 3 * E, dummy, epilogue=L.EPI_HEAD_FWD,
+                  bias=bias_t, head=h, ldc=cpad)
+        self.call(self.lib.xv_head_combine, L.ptr(pmax), L.ptr(psum), L.ptr(tgt), nblk, B, C.c_float(inv_batch),
+                  L.ptr(lse), L.ptr(None), L.ptr(self.scalars[0:1]), L.stream_ptr())
+        if training:
+            def bwd():
+                d = self.buf("head/d", (B, cpad), torch.bfloat16)
+                self.gemm(L.operand(x3, False), L.operand(wn3, True, cols=Cn), B, Cn, 3 * E, d, epilogue=L.EPI_HEAD_BWD,
+                          bias=bias_t, head=h, col_sum=(st.grad(bias) if bias is not None else None))
+                # dWn[e, c] = sum_i x[i, e] d[i, c]
+                gw = st.grad(kernel)
+                self.gemm(L.operand(x3, True, cols=E), L.operand(d, True, cols=Cn), E, Cn, B, gw, epilogue=L.EPI_F32)
+                if normalize:
+                    self.call(self.lib.xv_head_finish_dw, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), E, cpad, L.stream_ptr())
+                # dx[i, e] = sum_c d[i, c] wn[e, c]
+                dxg = self.buf("head/dxg", (B, E), torch.float32)
+                self.gemm(L.operand(d, False, cols=Cn), L.operand(wn3, False, rows=E, cols=Cn), B, E, Cn, dxg,
+                          epilogue=L.EPI_F32)
+                du = self.buf(u.name + "/grad", (B, E), torch.float32)
+                use_margin = head_type != L.HEAD_SOFTMAX
+                self.call(self.lib.xv_head_finish_dx, L.ptr(dxg), L.ptr(gnorm if use_margin else None), L.ptr(x),
+                          L.ptr(xnorm), L.ptr(u.data), L.ptr(urinv), C.c_float(scaling), L.ptr(du), B, E, L.stream_ptr())
+                u.grad = du
+            self.tape.append(bwd)
+        return self.scalars[0], logits, x
+
+    # ---- regulariser + optimizer ---------------------------------------------------------------------
+    def l2_loss(self):
+        st = self.store
+        self.call(self.lib.xv_l2_loss, L.ptr(st.params), L.ptr(st.blk_l2), C.c_int64(st.n), L.ptr(self.scalars[1:2]),
+                  L.stream_ptr())
+        return self.scalars[1]
+
+    def set_hyper(self, lr, momentum=0.0, adam_t=1.0, clip_norm=0.0, fa=None, fs=None):
+        """Host -> device scalars (learning rate and the margin schedule are fed every step, trainer.py:493-494)."""
+        hv = torch.tensor([lr, momentum, 0.9, 0.999, 1e-8, adam_t, clip_norm, 0.0], dtype=torch.float32)
+        self.hyper.copy_(hv, non_blocking=True)
+        if fa is not None:
+            self.sched.copy_(torch.tensor([fa, fs], dtype=torch.float32), non_blocking=True)
+
+    def optimizer_step(self, opt, clip=False):
+        st = self.store
+        st.ensure_opt_state(opt)
+        gs = None
+        if clip:
+            gs = self.scalars[2:3]
+            self.call(self.lib.xv_grad_sumsq, L.ptr(st.params), L.ptr(st.grads), L.ptr(st.blk_l2), C.c_int64(st.n),
+                      L.ptr(gs), L.stream_ptr())
+        self.call(self.lib.xv_opt_step, L.ptr(st.params), L.ptr(st.grads), L.ptr(st.state1), L.ptr(st.state2),
+                  L.ptr(st.blk_l2), L.ptr(st.blk_shadow), L.ptr(st.blk_stride), L.ptr(st.shadow), C.c_int64(st.n), opt,
+                  L.ptr(self.hyper), L.ptr(gs), L.stream_ptr())
+
+
+_default_engine = None
+
+
+def get_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine
+
+
+def set_engine(e):
+    global _default_engine
+    _default_engine = e
+    return e
