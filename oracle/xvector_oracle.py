@@ -194,7 +194,14 @@ def _activation(x, P, prefix, relu_type):
     return F.relu(x)
 
 
-def batch_norm(x, P, prefix, momentum, is_training, updates, unbiased_moving_var=False):
+def bf16_ste(x):
+    """Round to bfloat16 storage with a straight-through gradient.  Used only by the ``emulate_bf16`` mode, which
+    mimics WHERE the CUDA path stores bf16 (inputs, trunk kernels, pre-BN outputs, activations) so that tests can
+    separate kernel bugs from the intrinsic rounding noise of a bf16 pipeline (ReLU-mask flips etc.)."""
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+
+def batch_norm(x, P, prefix, momentum, is_training, updates, unbiased_moving_var=False, store=None):
     """tf.layers.batch_normalization, axis=-1, eps=1e-3.  Training: biased batch statistics over all
     leading axes; moving <- moving*m + batch*(1-m).  The fused rank-4 TF path (tdnn1-3) updates
     moving_variance with the unbiased batch variance; the unfused rank-2/3 path with the biased one."""
@@ -211,6 +218,8 @@ def batch_norm(x, P, prefix, momentum, is_training, updates, unbiased_moving_var
                 updates[prefix + "/moving_variance"] = P[prefix + "/moving_variance"] * momentum + mv * (1 - momentum)
     else:
         mean, var = P[prefix + "/moving_mean"], P[prefix + "/moving_variance"]
+    if store is not None:      # statistics come from the fp32 accumulators, the normalised tensor from bf16 storage
+        x = store(x)
     return (x - mean) * torch.rsqrt(var + BN_EPSILON) * g + b
 
 
@@ -313,25 +322,28 @@ def self_attention(endpoints, P, params, is_training, updates, lengths=None):
 # --------------------------------------------------------------------------------------
 # Network (model/tdnn.py:8-191) and entire_network (model/trainer.py:168-188)
 # --------------------------------------------------------------------------------------
-def tdnn(features, P, params, is_training=False, updates=None, lengths=None, mirror_tf_fused_bn=True):
+def tdnn(features, P, params, is_training=False, updates=None, lengths=None, mirror_tf_fused_bn=True,
+         emulate_bf16=False):
     """Returns (features, endpoints, penalty).  ``lengths`` (input-domain frames per row) enables the
     masked pooling used for batched variable-length extraction; frame layers are unaffected because
     BN in inference mode is element-wise and valid output frames never read padded input frames."""
     relu_type = params.dict.get("network_relu_type", "relu")
     mom = params.batchnorm_momentum
     ep = OrderedDict()
-    x = features
+    q = bf16_ste if emulate_bf16 else (lambda t: t)
+    x = q(features)
     for name, kind, k, cin, cout in frame_layer_specs(features.shape[-1], params):
         if kind == "conv":
-            x = temporal_conv(x, P["tdnn/%s_conv/kernel" % name], P["tdnn/%s_conv/bias" % name])
+            x = temporal_conv(x, q(P["tdnn/%s_conv/kernel" % name]), P["tdnn/%s_conv/bias" % name])
             ep["%s_conv" % name] = x
         else:
-            x = x @ P["tdnn/%s_dense/kernel" % name] + P["tdnn/%s_dense/bias" % name]
+            x = x @ q(P["tdnn/%s_dense/kernel" % name]) + P["tdnn/%s_dense/bias" % name]
             ep["%s_dense" % name] = x
         x = batch_norm(x, P, "tdnn/%s_bn" % name, mom, is_training, updates,
-                       unbiased_moving_var=(mirror_tf_fused_bn and kind == "conv"))
+                       unbiased_moving_var=(mirror_tf_fused_bn and kind == "conv"),
+                       store=bf16_ste if emulate_bf16 else None)
         ep["%s_bn" % name] = x
-        x = _activation(x, P, "tdnn/%s_relu" % name, relu_type)
+        x = q(_activation(x, P, "tdnn/%s_relu" % name, relu_type))
         ep["%s_relu" % name] = x
     plen = None if lengths is None else (lengths - 14)
     penalty = None
@@ -365,9 +377,9 @@ def l2_scaling(x, scaling_factor, epsilon=1e-12):
     return x * (torch.rsqrt(torch.clamp(sq, min=epsilon)) * scaling_factor)
 
 
-def entire_network(features, P, params, is_training=False, updates=None, lengths=None):
+def entire_network(features, P, params, is_training=False, updates=None, lengths=None, emulate_bf16=False):
     """model/trainer.py:168-188."""
-    x, ep, penalty = tdnn(features, P, params, is_training, updates, lengths)
+    x, ep, penalty = tdnn(features, P, params, is_training, updates, lengths, emulate_bf16=emulate_bf16)
     ep["output"] = x
     if params.dict.get("feature_norm", False):
         assert "feature_scaling_factor" in params.dict
@@ -493,8 +505,10 @@ def regularization_loss(P, params):
     return total
 
 
-def forward_loss(P, features, labels, params, loss_type, global_step, is_training=True, updates=None):
-    x, ep, penalty = entire_network(features, P, params, is_training=is_training, updates=updates)
+def forward_loss(P, features, labels, params, loss_type, global_step, is_training=True, updates=None,
+                 emulate_bf16=False):
+    x, ep, penalty = entire_network(features, P, params, is_training=is_training, updates=updates,
+                                    emulate_bf16=emulate_bf16)
     loss, logits = loss_network(loss_type, x, labels, P, params, global_step)
     total = loss + regularization_loss(P, params)
     if penalty is not None:
@@ -503,14 +517,16 @@ def forward_loss(P, features, labels, params, loss_type, global_step, is_trainin
     return loss, total, ep
 
 
-def train_step(P, opt_state, features, labels, params, loss_type, learning_rate, global_step):
-    """One sess.run(train_op).  Returns (raw_loss, total_loss, grads, new_P, new_opt_state, endpoints)."""
+def train_step(P, opt_state, features, labels, params, loss_type, learning_rate, global_step, emulate_bf16=False):
+    """One sess.run(train_op).  Returns (raw_loss, total_loss, grads, new_P, new_opt_state, endpoints);
+    endpoints["__raw_grads"] holds the gradients before clip_by_global_norm."""
     Pg = OrderedDict((k, v.detach().clone().requires_grad_(k in trainable_names(P))) for k, v in P.items())
     updates = OrderedDict()
-    loss, total, ep = forward_loss(Pg, features, labels, params, loss_type, global_step, True, updates)
+    loss, total, ep = forward_loss(Pg, features, labels, params, loss_type, global_step, True, updates, emulate_bf16)
     names = trainable_names(P)
     gl = torch.autograd.grad(total, [Pg[n] for n in names], allow_unused=True)
     grads = OrderedDict((n, (g if g is not None else torch.zeros_like(P[n]))) for n, g in zip(names, gl))
+    ep["__raw_grads"] = grads
     if params.dict.get("clip_gradient", False):
         gn = torch.sqrt(sum((g ** 2).sum() for g in grads.values()))
         c = float(params.clip_gradient_norm)

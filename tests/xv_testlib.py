@@ -34,8 +34,13 @@ def head_params(loss_type, m=None):
 
 
 def make_batch(B, T, D, C, seed=0):
+    """Synthetic segments with per-utterance offset/scale (speaker-like variability).  Plain iid noise makes every
+    utterance's pooled statistics nearly identical, so the utterance-level batch-norms divide by a vanishing
+    between-utterance variance and amplify bf16 rounding noise by orders of magnitude (ill-conditioned test)."""
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(B, T, D, generator=g, dtype=torch.float32)
+    m = torch.randn(B, 1, D, generator=g, dtype=torch.float32)
+    s = 0.5 + torch.rand(B, 1, D, generator=g, dtype=torch.float32)
+    x = m + s * torch.randn(B, T, D, generator=g, dtype=torch.float32)
     y = torch.randint(0, C, (B,), generator=g, dtype=torch.int32)
     return x, y
 
