@@ -82,7 +82,8 @@ typedef struct {
   int32_t type;          /* xv_head_type                                                            */
   int32_t asoftmax_m;    /* 1, 2 or 4 (XV_HEAD_ASOFTMAX)                                             */
   float margin;          /* m of AM / AAM                                                           */
-  int32_t _pad0;
+  float cos_m, sin_m;    /* cos(m), sin(m) of AAM, evaluated by the host                            */
+  float threshold;       /* cos(pi - m) of AAM (loss.py:321)                                        */
   const float* sched;    /* device [2] = {fa, fs} = {1/(1+lambda), 1-fa}; lambda schedule of loss.py:144-147 is
                             evaluated by the host each step and lives in device memory so a captured CUDA graph
                             of the step stays valid as global_step advances                                */
@@ -143,21 +144,28 @@ XV_API int xv_bn_act_apply(const void* y, void* a, const float* scale, const flo
                            int64_t rows, int C, int64_t ld, int seg_len, int seg_valid, const int32_t* lengths,
                            void* stream);
 /* Backward of act(BN(y)) (what tf.gradients emits for FusedBatchNormGrad/ReluGrad, trainer.py:403):
- * reduce: dgamma += sum g*yhat, dbeta += sum g, dalpha += sum da*min(z,0);  apply: dy (bf16), 0 on invalid rows. */
+ * reduce: dgamma += sum g*yhat, dbeta += sum g, dalpha += sum da*min(z,0);  apply: dy (bf16), 0 on invalid rows.
+ * Fused tdnn5 path: with pooled/dpooled ([B, 2*pool_cpad] = [mean | std] and its gradient) the upstream gradient
+ * da is not read but evaluated on the fly as the statistics-pooling backward of a = act(BN(y)) (da may be NULL). */
 XV_API int xv_bn_act_bwd_reduce(const void* y, const void* da, const float* scale, const float* shift,
                                 const float* save_mean, const float* save_rstd, const float* alpha, int act,
                                 int64_t rows, int C, int64_t ld, int seg_len, int seg_valid, const int32_t* lengths,
-                                float* dgamma, float* dbeta, float* dalpha, void* stream);
+                                float* dgamma, float* dbeta, float* dalpha, const float* pooled, const float* dpooled,
+                                int pool_cpad, int pool_c_real, void* stream);
 XV_API int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, const float* scale, const float* shift,
                                const float* save_mean, const float* save_rstd, const float* dgamma, const float* dbeta,
                                float count, const float* alpha, int act, int64_t rows, int C, int64_t ld, int seg_len,
-                               int seg_valid, const int32_t* lengths, void* stream);
+                               int seg_valid, const int32_t* lengths, const float* pooled, const float* dpooled,
+                               int pool_cpad, int pool_c_real, void* stream);
 
 /* statistics_pooling (model/pooling.py:9-34) and its length-masked form statistics_pooling_v2
  * (model/multitask_v1/pooling.py:9-40): out f32 [B, 2*cpad] = [mean | std]; channels >= c_real read as 0.
- * out_split (optional) = bf16 [B, 6*cpad] = [hi | hi | lo] of out, the A operand of tdnn6_dense. */
+ * out_split (optional) = bf16 [B, 6*cpad] = [hi | hi | lo] of out, the A operand of tdnn6_dense.
+ * scale != NULL fuses the preceding BN + activation: x is then the pre-BN tensor and a = act(x*scale + shift) is
+ * pooled without tdnn5_relu ever being written to HBM. */
 XV_API int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int B, int seg_len, int seg_valid,
-                             const int32_t* lengths, int c_real, int cpad, int64_t ld, void* stream);
+                             const int32_t* lengths, int c_real, int cpad, int64_t ld, const float* scale,
+                             const float* shift, const float* alpha, int act, void* stream);
 XV_API int xv_stats_pool_bwd(const void* x, const float* pooled, const float* dpooled, void* dx, int B, int seg_len,
                              int seg_valid, const int32_t* lengths, int c_real, int cpad, int64_t ld, void* stream);
 
@@ -207,6 +215,9 @@ XV_API int xv_opt_step(float* params, const float* grads, float* state1, float* 
 XV_API int xv_shadow_refresh(const float* params, const int64_t* blk_shadow, const int64_t* blk_split_stride,
                              void* shadow, int64_t n, void* stream);
 XV_API int xv_l2_loss(const float* params, const float* blk_l2, int64_t n, float* out, void* stream);
+/* dst[0..n) = host_vals[0..n) (n <= 16), passed as kernel arguments: the learning_rate / global_step placeholders of
+ * model/trainer.py:229-231,326 fed per step without a host-buffer race under CUDA-graph replay. */
+XV_API int xv_set_scalars(float* dst, const float* host_vals, int n, void* stream);
 
 #ifdef __cplusplus
 }

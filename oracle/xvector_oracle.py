@@ -343,7 +343,9 @@ def tdnn(features, P, params, is_training=False, updates=None, lengths=None, mir
                        unbiased_moving_var=(mirror_tf_fused_bn and kind == "conv"),
                        store=bf16_ste if emulate_bf16 else None)
         ep["%s_bn" % name] = x
-        x = q(_activation(x, P, "tdnn/%s_relu" % name, relu_type))
+        x = _activation(x, P, "tdnn/%s_relu" % name, relu_type)
+        if not (name == "tdnn5" and params.pooling_type == "statistics_pooling"):
+            x = q(x)      # the fused tdnn5 BN+ReLU+pooling kernel pools the fp32 activation, never storing it
         ep["%s_relu" % name] = x
     plen = None if lengths is None else (lengths - 14)
     penalty = None

@@ -28,7 +28,8 @@ class Operand(C.Structure):
 
 
 class HeadArgs(C.Structure):
-    _fields_ = [("type", C.c_int32), ("asoftmax_m", C.c_int32), ("margin", C.c_float), ("_pad0", C.c_int32),
+    _fields_ = [("type", C.c_int32), ("asoftmax_m", C.c_int32), ("margin", C.c_float), ("cos_m", C.c_float),
+                ("sin_m", C.c_float), ("threshold", C.c_float),
                 ("sched", C.c_void_p), ("labels", C.c_void_p), ("xnorm", C.c_void_p), ("part_max", C.c_void_p),
                 ("part_sum", C.c_void_p), ("target_logit", C.c_void_p), ("logits_out", C.c_void_p),
                 ("lse", C.c_void_p), ("inv_batch", C.c_float), ("gnorm", C.c_void_p)]

@@ -77,12 +77,12 @@ __device__ __forceinline__ MarginOut margin_target(const xv_head_args& h, float 
     phi = c - h.margin;
     dphi = 1.0f;
   } else if (h.type == XV_HEAD_AAM) {
-    const float cm = cosf(h.margin), sm = sinf(h.margin);
+    const float cm = h.cos_m, sm = h.sin_m;
     const float s2 = 1.0f - c * c;
     const float s = sqrtf(fmaxf(s2, 1e-12f));
     const float u = c * cm - s * sm;
     const float du = cm + ((s2 > 1e-12f) ? (c * sm / s) : 0.0f);
-    const bool easy = c > cosf(3.14159265358979323846f - h.margin);
+    const bool easy = c > h.threshold;
     phi = easy ? u : (-u - 2.0f);
     dphi = easy ? du : -du;
   } else {  // XV_HEAD_ASOFTMAX, m = 2 or 4
@@ -338,22 +338,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           }
         } else if (EPI == XV_EPI_HEAD_FWD) {
           if (row_ok) {
+            const int jl = label - nc0;                 // position of the target column inside this chunk (or outside)
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += (nc0 + j < p.N) ? __ldg(p.bias + nc0 + j) : 0.f;
+            }
+            if (p.head.logits_out) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nc0 + j < p.N) p.head.logits_out[static_cast<long long>(m) * p.ldc + nc0 + j] = v[j];
+            }
+            if (jl >= 0 && jl < 32) {                    // margin transform once per row, not per column
+              float zl = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) zl = (j == jl) ? v[j] : zl;
+              if (p.head.type != XV_HEAD_SOFTMAX) zl = margin_target(p.head, zl, xn).zprime;
+              p.head.target_logit[m] = zl;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (j == jl) ? zl : v[j];
+            }
             float cmax = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int n = nc0 + j;
-              if (n < p.N) {
-                float z = v[j] + (p.bias ? __ldg(p.bias + n) : 0.f);
-                if (p.head.logits_out) p.head.logits_out[static_cast<long long>(m) * p.ldc + n] = z;
-                if (n == label) {
-                  if (p.head.type != XV_HEAD_SOFTMAX) z = margin_target(p.head, z, xn).zprime;
-                  p.head.target_logit[m] = z;
-                }
-                v[j] = z;
-                cmax = fmaxf(cmax, z);
-              } else {
-                v[j] = -INFINITY;
-              }
+              v[j] = (nc0 + j < p.N) ? v[j] : -INFINITY;
+              cmax = fmaxf(cmax, v[j]);
             }
             const float nmax = fmaxf(run_max, cmax);
             float acc_s = run_sum * __expf(run_max - nmax);   // exp(-inf) = 0 on the first chunk
@@ -364,24 +372,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           }
         } else {  // XV_EPI_HEAD_BWD
           float d[32];
+          const int jl = label - nc0;
+          float dz = 1.f;
+          if (row_ok && p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (nc0 + j < p.N) ? __ldg(p.bias + nc0 + j) : 0.f;
+          }
+          if (row_ok && jl >= 0 && jl < 32) {
+            float zl = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) zl = (j == jl) ? v[j] : zl;
+            float dn = 0.f;
+            if (p.head.type != XV_HEAD_SOFTMAX) {
+              const MarginOut mo = margin_target(p.head, zl, xn);
+              zl = mo.zprime; dz = mo.dz; dn = mo.dn;
+            }
+            if (p.head.gnorm) p.head.gnorm[m] = (__expf(zl - lse) - 1.0f) * p.head.inv_batch * dn;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (j == jl) ? zl : v[j];
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int n = nc0 + j;
             float g = 0.f;
-            if (row_ok && n < p.N) {
-              float z = v[j] + (p.bias ? __ldg(p.bias + n) : 0.f);
-              if (n == label) {
-                float dz = 1.f, dn = 0.f;
-                if (p.head.type != XV_HEAD_SOFTMAX) {
-                  const MarginOut mo = margin_target(p.head, z, xn);
-                  z = mo.zprime; dz = mo.dz; dn = mo.dn;
-                }
-                const float dt = (__expf(z - lse) - 1.0f) * p.head.inv_batch;
-                g = dt * dz;
-                if (p.head.gnorm) p.head.gnorm[m] = dt * dn;
-              } else {
-                g = __expf(z - lse) * p.head.inv_batch;
-              }
+            if (row_ok && nc0 + j < p.N) {
+              const float pr = __expf(v[j] - lse);
+              g = (j == jl) ? (pr - 1.0f) * p.head.inv_batch * dz : pr * p.head.inv_batch;
             }
             d[j] = g;
           }

@@ -20,23 +20,44 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 
 // w f32 [E, C] (TF layout, C contiguous) -> wn3 bf16 [3E, ldw] = [hi(wn); lo(wn); hi(wn)], wn = w * rsqrt(max(sum_e w^2, 1e-12))
 // (tf.nn.l2_normalize(w, dim=0), loss.py:104,213,299).  normalize = 0 keeps w (plain softmax head).
-__global__ void head_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wn3,
-                                         float* __restrict__ inv_norm, int E, int C, long long ldw, int normalize) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float inv = 1.f;
-  if (normalize) {
-    float ss = 0.f;
-    for (int e = 0; e < E; ++e) { const float v = w[static_cast<long long>(e) * C + c]; ss += v * v; }
-    inv = rsqrtf(fmaxf(ss, 1e-12f));
+// Block = 32 x 8 threads: 64 columns (two per thread, 8-byte loads) x 8 row groups; column sums go through smem.
+__global__ void __launch_bounds__(256) head_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wn3,
+                                                                float* __restrict__ inv_norm, int E, int C, long long ldw,
+                                                                int normalize) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + tx * 2;
+  const bool ok = c < C;                      // C is even (padded to a multiple of 8)
+  float s0 = 0.f, s1 = 0.f;
+  if (normalize && ok) {
+    for (int e = ty; e < E; e += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(w + static_cast<long long>(e) * C + c);
+      s0 += v.x * v.x;
+      s1 += v.y * v.y;
+    }
   }
-  if (inv_norm) inv_norm[c] = inv;
-  for (int e = 0; e < E; ++e) {
-    const float v = w[static_cast<long long>(e) * C + c] * inv;
-    const __nv_bfloat16 h = __float2bfloat16(v);
-    wn3[static_cast<long long>(e) * ldw + c] = h;
-    wn3[static_cast<long long>(E + e) * ldw + c] = __float2bfloat16(v - __bfloat162float(h));
-    wn3[static_cast<long long>(2 * E + e) * ldw + c] = h;
+  red[ty][tx * 2] = s0;
+  red[ty][tx * 2 + 1] = s1;
+  __syncthreads();
+  float i0 = 1.f, i1 = 1.f;
+  if (normalize) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a0 += red[k][tx * 2]; a1 += red[k][tx * 2 + 1]; }
+    i0 = rsqrtf(fmaxf(a0, 1e-12f));
+    i1 = rsqrtf(fmaxf(a1, 1e-12f));
+  }
+  if (!ok) return;
+  if (inv_norm && ty == 0) { inv_norm[c] = i0; inv_norm[c + 1] = i1; }
+  for (int e = ty; e < E; e += 8) {
+    const float2 v = *reinterpret_cast<const float2*>(w + static_cast<long long>(e) * C + c);
+    const float v0 = v.x * i0, v1 = v.y * i1;
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+    *reinterpret_cast<__nv_bfloat162*>(wn3 + static_cast<long long>(e) * ldw + c) = h;
+    *reinterpret_cast<__nv_bfloat162*>(wn3 + static_cast<long long>(E + e) * ldw + c) = l;
+    *reinterpret_cast<__nv_bfloat162*>(wn3 + static_cast<long long>(2 * E + e) * ldw + c) = h;
   }
 }
 
@@ -125,23 +146,40 @@ __global__ void head_finish_dx_kernel(const float* __restrict__ dxg, const float
   }
 }
 
-// dW_j = (dWn_j - wn_j <wn_j, dWn_j>) * inv_norm_j   (in place on the gradient buffer), one thread per column.
-__global__ void head_finish_dw_kernel(float* __restrict__ dw, const float* __restrict__ w,
-                                      const float* __restrict__ inv_norm, int E, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float inv = inv_norm[c];
-  const bool clamped = (inv >= 1e6f);
-  float dot = 0.f;
-  for (int e = 0; e < E; ++e) {
-    const long long idx = static_cast<long long>(e) * C + c;
-    dot += w[idx] * inv * dw[idx];
+// dW_j = (dWn_j - wn_j <wn_j, dWn_j>) * inv_norm_j   (in place on the gradient buffer); same 64 x 8 blocking.
+__global__ void __launch_bounds__(256) head_finish_dw_kernel(float* __restrict__ dw, const float* __restrict__ w,
+                                                             const float* __restrict__ inv_norm, int E, int C) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + tx * 2;
+  const bool ok = c < C;
+  float i0 = 1.f, i1 = 1.f, d0 = 0.f, d1 = 0.f;
+  if (ok) {
+    i0 = inv_norm[c];
+    i1 = inv_norm[c + 1];
+    for (int e = ty; e < E; e += 8) {
+      const long long idx = static_cast<long long>(e) * C + c;
+      const float2 wv = *reinterpret_cast<const float2*>(w + idx);
+      const float2 gv = *reinterpret_cast<const float2*>(dw + idx);
+      d0 += wv.x * i0 * gv.x;
+      d1 += wv.y * i1 * gv.y;
+    }
   }
-  for (int e = 0; e < E; ++e) {
+  red[ty][tx * 2] = d0;
+  red[ty][tx * 2 + 1] = d1;
+  __syncthreads();
+  if (!ok) return;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a0 += red[k][tx * 2]; a1 += red[k][tx * 2 + 1]; }
+  const bool cl0 = (i0 >= 1e6f), cl1 = (i1 >= 1e6f);     // rsqrt(1e-12): the norm was clamped, no projection term
+  for (int e = ty; e < E; e += 8) {
     const long long idx = static_cast<long long>(e) * C + c;
-    float g = dw[idx] * inv;
-    if (!clamped) g -= w[idx] * inv * inv * dot;
-    dw[idx] = g;
+    const float2 wv = *reinterpret_cast<const float2*>(w + idx);
+    float2 gv = *reinterpret_cast<const float2*>(dw + idx);
+    gv.x = gv.x * i0 - (cl0 ? 0.f : wv.x * i0 * i0 * a0);
+    gv.y = gv.y * i1 - (cl1 ? 0.f : wv.y * i1 * i1 * a1);
+    *reinterpret_cast<float2*>(dw + idx) = gv;
   }
 }
 
@@ -151,8 +189,8 @@ using namespace xv;
 
 extern "C" int xv_head_prep_weights(const float* w, void* wn3, float* inv_norm, int E, int C, int64_t ldw, int normalize,
                                     void* stream) {
-  if (!w || !wn3 || E <= 0 || C <= 0 || ldw < C || ldw % 8) return set_error(XV_ERR_INVALID, "xv_head_prep_weights: bad arguments");
-  head_prep_weights_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (!w || !wn3 || E <= 0 || C <= 0 || (C & 1) || ldw < C || ldw % 8) return set_error(XV_ERR_INVALID, "xv_head_prep_weights: bad arguments (C must be even, ldw a multiple of 8)");
+  head_prep_weights_kernel<<<ceil_div(C, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<__nv_bfloat16*>(wn3), inv_norm, E, C, ldw, normalize);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -189,8 +227,8 @@ extern "C" int xv_head_finish_dx(const float* dx_gemm, const float* gnorm, const
 }
 
 extern "C" int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, int E, int C, void* stream) {
-  if (!dw || !w || !inv_norm || E <= 0 || C <= 0) return set_error(XV_ERR_INVALID, "xv_head_finish_dw: bad arguments");
-  head_finish_dw_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(dw, w, inv_norm, E, C);
+  if (!dw || !w || !inv_norm || E <= 0 || C <= 0 || (C & 1)) return set_error(XV_ERR_INVALID, "xv_head_finish_dw: bad arguments (C must be even)");
+  head_finish_dw_kernel<<<ceil_div(C, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw, w, inv_norm, E, C);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

@@ -53,12 +53,20 @@ __device__ __forceinline__ float act_grad(int act, float z, float alpha) {
   }
 }
 
-__device__ __forceinline__ bool row_is_valid(long long m, int seg_len, int seg_valid, const int* lengths) {
+__device__ __forceinline__ bool row_is_valid(int m, int seg_len, int seg_valid, const int* lengths) {
   if (seg_len <= 0) return true;
-  const int b = static_cast<int>(m / seg_len), t = static_cast<int>(m % seg_len);
+  const int b = m / seg_len, t = m - b * seg_len;
   return t < (lengths ? lengths[b] : seg_valid);
 }
 
+// Gradient of the statistics pooling evaluated on the fly (fused layer-5 backward): the upstream gradient of
+// act(BN(y)) at frame (b, t) is  gmean/L + 1[var > floor] * gstd * (a - mean) / (L * std)  with a recomputed from y,
+// so neither tdnn5_relu nor its gradient ever round-trips HBM.
+struct PoolGradSrc {
+  const float* pooled;    // [B, 2*cpad] = [mean | std]   (nullptr: read the upstream gradient from memory)
+  const float* dpooled;   // [B, 2*cpad]
+  int cpad, c_real;
+};
 // ------------------------------------------------------------------------------------------------
 // Input packing: features f32 [B, T, D] -> bf16 im2col rows [B*T, ldo], out[m, j*dpad + c] = x[b, t+j, c].
 __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int T, int D,
@@ -110,41 +118,83 @@ __global__ void bn_finalize_infer_kernel(const float* __restrict__ gamma, const 
   shift[c] = beta[c] - mm[c] * sc;
 }
 
-// a = act(y*scale + shift) on valid rows, 0 on invalid rows.
-__global__ void bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ alpha, int act, long long rows, int C, long long ld,
-                                    int seg_len, int seg_valid, const int* __restrict__ lengths) {
-  const int cv = C / 8;
-  const long long total = rows * cv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / cv;
-    const int c0 = static_cast<int>(i % cv) * 8;
-    float o[8];
-    if (row_is_valid(m, seg_len, seg_valid, lengths)) {
-      float v[8], sc[8], sh[8];
-      load8(y + m * ld + c0, v);
-      load8f(scale + c0, sc);
-      load8f(shift + c0, sh);
+// Row-streaming layout shared by the three BN kernels below: grid = (C/256, row chunks of STREAM_ROWS); a block is
+// 8 warps, a warp covers 256 channels (8 per lane, one 16-byte vector) and walks rows w, w+8, ... of its chunk two
+// at a time.  Every per-channel constant (scale, shift, mean, rstd, dgamma, dbeta, alpha) is loaded ONCE per thread.
+constexpr int STREAM_ROWS = 64;
+
+// Per-(segment, channel) coefficients of the on-the-fly pooling gradient: da = ca + cb * a.
+struct PoolCoef {
+  float ca[8], cb[8];
+  int b;
+};
+__device__ __forceinline__ void pool_coef_load(PoolCoef& pc, const PoolGradSrc& ps, int b, int c0, int seg_valid,
+                                               const int* lengths) {
+  if (pc.b == b) return;
+  pc.b = b;
+  const float invl = 1.0f / (static_cast<float>(lengths ? lengths[b] : seg_valid) + 1e-16f);
+  float mu[8], sd[8], gm[8], gs[8];
+  const float* pb = ps.pooled + static_cast<long long>(b) * 2 * ps.cpad;
+  const float* gb = ps.dpooled + static_cast<long long>(b) * 2 * ps.cpad;
+  load8f(pb + c0, mu); load8f(pb + ps.cpad + c0, sd); load8f(gb + c0, gm); load8f(gb + ps.cpad + c0, gs);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = act_fwd(act, fmaf(v[j], sc[j], sh[j]), act == ACT_PRELU ? alpha[c0 + j] : 0.f);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    float ca = 0.f, cb = 0.f;
+    if (c0 + j < ps.c_real) {
+      ca = gm[j] * invl;
+      if (sd[j] * sd[j] > 1.0000001e-12f) {       // variance above the 1e-12 floor: gradient flows through std
+        cb = gs[j] * invl / sd[j];
+        ca -= cb * mu[j];
+      }
     }
-    store8(a + m * ld + c0, o);
+    pc.ca[j] = ca;
+    pc.cb[j] = cb;
+  }
+}
+
+// a = act(y*scale + shift) on valid rows, 0 on invalid rows.
+__global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ alpha, int act, int rows, int C, long long ld,
+                                    int seg_len, int seg_valid, const int* __restrict__ lengths) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  if (c0 >= C) return;
+  float sc[8], sh[8], al[8];
+  load8f(scale + c0, sc);
+  load8f(shift + c0, sh);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) al[j] = (act == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+  const int r0 = blockIdx.y * STREAM_ROWS;
+  const int r1 = min(r0 + STREAM_ROWS, rows);
+  for (int m = r0 + w; m < r1; m += 16) {
+    float v[2][8];
+    bool in[2], valid[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int mm = m + 8 * u;
+      in[u] = mm < r1;
+      valid[u] = in[u] && row_is_valid(mm, seg_len, seg_valid, lengths);
+      if (valid[u]) load8(y + static_cast<long long>(mm) * ld + c0, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!in[u]) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = valid[u] ? act_fwd(act, fmaf(v[u][j], sc[j], sh[j]), al[j]) : 0.f;
+      store8(a + static_cast<long long>(m + 8 * u) * ld + c0, o);
+    }
   }
 }
 
 // Column reductions for the BN backward: dbeta += sum g, dgamma += sum g*yhat, dalpha += sum da*min(z,0).
-// grid = (C/256, row chunks); block = 256 threads = 8 warps; warp w takes rows w, w+8, ... of the chunk.
-constexpr int RED_ROWS_PER_BLOCK = 128;
+template <bool FUSED_POOL>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
-    const float* __restrict__ alpha, int act, long long rows, int C, long long ld, int seg_len, int seg_valid,
-    const int* __restrict__ lengths, float* dgamma, float* dbeta, float* dalpha) {
+    const float* __restrict__ alpha, int act, int rows, int C, long long ld, int seg_len, int seg_valid,
+    const int* __restrict__ lengths, float* dgamma, float* dbeta, float* dalpha, PoolGradSrc ps) {
   __shared__ float red[8][3][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + lane * 8;
@@ -157,20 +207,35 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     load8f(scale + c0, sc); load8f(shift + c0, sh); load8f(save_mean + c0, mu); load8f(save_rstd + c0, rs);
 #pragma unroll
     for (int j = 0; j < 8; ++j) al[j] = (act == ACT_PRELU) ? alpha[c0 + j] : 0.f;
-    const long long r0 = static_cast<long long>(blockIdx.y) * RED_ROWS_PER_BLOCK;
-    const long long r1 = min(r0 + RED_ROWS_PER_BLOCK, rows);
-    for (long long m = r0 + w; m < r1; m += 8) {
-      if (!row_is_valid(m, seg_len, seg_valid, lengths)) continue;
-      float v[8], d[8];
-      load8(y + m * ld + c0, v);
-      load8(da + m * ld + c0, d);
+    PoolCoef pc;
+    pc.b = -1;
+    const int r0 = blockIdx.y * STREAM_ROWS;
+    const int r1 = min(r0 + STREAM_ROWS, rows);
+    for (int m = r0 + w; m < r1; m += 16) {
+      float v[2][8], d[2][8];
+      bool ok[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(v[j], sc[j], sh[j]);
-        const float g = d[j] * act_grad(act, z, al[j]);
-        sg[j] += g;
-        sgy[j] += g * (v[j] - mu[j]) * rs[j];
-        if (act == ACT_PRELU) sal[j] += d[j] * fminf(z, 0.f);
+      for (int u = 0; u < 2; ++u) {
+        const int mm = m + 8 * u;
+        ok[u] = mm < r1 && row_is_valid(mm, seg_len, seg_valid, lengths);
+        if (ok[u]) {
+          load8(y + static_cast<long long>(mm) * ld + c0, v[u]);
+          if (!FUSED_POOL) load8(da + static_cast<long long>(mm) * ld + c0, d[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        if (FUSED_POOL) pool_coef_load(pc, ps, (m + 8 * u) / seg_len, c0, seg_valid, lengths);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(v[u][j], sc[j], sh[j]);
+          const float dd = FUSED_POOL ? fmaf(pc.cb[j], act_fwd(act, z, al[j]), pc.ca[j]) : d[u][j];
+          const float g = dd * act_grad(act, z, al[j]);
+          sg[j] += g;
+          sgy[j] += g * (v[u][j] - mu[j]) * rs[j];
+          if (act == ACT_PRELU) sal[j] += dd * fminf(z, 0.f);
+        }
       }
     }
   }
@@ -193,38 +258,62 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
 }
 
 // dy = scale * (g - dbeta/n - yhat*dgamma/n) on valid rows, 0 elsewhere (scale = gamma*rstd).
-__global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da,
-                                        __nv_bfloat16* __restrict__ dy, const float* __restrict__ scale,
-                                        const float* __restrict__ shift, const float* __restrict__ save_mean,
-                                        const float* __restrict__ save_rstd, const float* __restrict__ dgamma,
-                                        const float* __restrict__ dbeta, float inv_count,
-                                        const float* __restrict__ alpha, int act, long long rows, int C, long long ld,
-                                        int seg_len, int seg_valid, const int* __restrict__ lengths) {
-  const int cv = C / 8;
-  const long long total = rows * cv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / cv;
-    const int c0 = static_cast<int>(i % cv) * 8;
-    float o[8];
-    if (row_is_valid(m, seg_len, seg_valid, lengths)) {
-      float v[8], d[8], sc[8], sh[8], mu[8], rs[8], dg[8], db[8];
-      load8(y + m * ld + c0, v);
-      load8(da + m * ld + c0, d);
-      load8f(scale + c0, sc); load8f(shift + c0, sh); load8f(save_mean + c0, mu); load8f(save_rstd + c0, rs);
-      load8f(dgamma + c0, dg); load8f(dbeta + c0, db);
+template <bool FUSED_POOL>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dy,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ save_mean,
+    const float* __restrict__ save_rstd, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+    float inv_count, const float* __restrict__ alpha, int act, int rows, int C, long long ld, int seg_len,
+    int seg_valid, const int* __restrict__ lengths, PoolGradSrc ps) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  if (c0 >= C) return;
+  float sc[8], sh[8], mu[8], rs[8], dg[8], db[8], al[8];
+  load8f(scale + c0, sc); load8f(shift + c0, sh); load8f(save_mean + c0, mu); load8f(save_rstd + c0, rs);
+  load8f(dgamma + c0, dg); load8f(dbeta + c0, db);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(v[j], sc[j], sh[j]);
-        const float g = d[j] * act_grad(act, z, act == ACT_PRELU ? alpha[c0 + j] : 0.f);
-        const float yh = (v[j] - mu[j]) * rs[j];
-        o[j] = sc[j] * (g - db[j] * inv_count - yh * dg[j] * inv_count);
+  for (int j = 0; j < 8; ++j) {
+    al[j] = (act == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+    dg[j] *= inv_count;
+    db[j] *= inv_count;
+  }
+  PoolCoef pc;
+  pc.b = -1;
+  const int r0 = blockIdx.y * STREAM_ROWS;
+  const int r1 = min(r0 + STREAM_ROWS, rows);
+  for (int m = r0 + w; m < r1; m += 16) {
+    float v[2][8], d[2][8];
+    bool in[2], valid[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int mm = m + 8 * u;
+      in[u] = mm < r1;
+      valid[u] = in[u] && row_is_valid(mm, seg_len, seg_valid, lengths);
+      if (valid[u]) {
+        load8(y + static_cast<long long>(mm) * ld + c0, v[u]);
+        if (!FUSED_POOL) load8(da + static_cast<long long>(mm) * ld + c0, d[u]);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.f;
     }
-    store8(dy + m * ld + c0, o);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!in[u]) continue;
+      float o[8];
+      if (valid[u]) {
+        if (FUSED_POOL) pool_coef_load(pc, ps, (m + 8 * u) / seg_len, c0, seg_valid, lengths);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(v[u][j], sc[j], sh[j]);
+          const float dd = FUSED_POOL ? fmaf(pc.cb[j], act_fwd(act, z, al[j]), pc.ca[j]) : d[u][j];
+          const float g = dd * act_grad(act, z, al[j]);
+          const float yh = (v[u][j] - mu[j]) * rs[j];
+          o[j] = sc[j] * (g - db[j] - yh * dg[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      }
+      store8(dy + static_cast<long long>(m + 8 * u) * ld + c0, o);
+    }
   }
 }
 
@@ -235,7 +324,11 @@ __global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, con
 __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ out3, int seg_len,
                                                              int seg_valid, const int* __restrict__ lengths,
-                                                             int c_real, int cpad, long long ld) {
+                                                             int c_real, int cpad, long long ld,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ shift,
+                                                             const float* __restrict__ alpha, int act) {
+  // scale != nullptr: x is the PRE-BN tensor and the pooled quantity is act(x*scale + shift) (fused tdnn5 BN+ReLU)
   __shared__ float red[8][2][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -246,15 +339,34 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = x0[j] = 0.f;
   if (c0 < cpad && L > 0) {
-    load8(xb + c0, x0);
-    for (int t = w; t < L; t += 8) {
-      float v[8];
-      load8(xb + static_cast<long long>(t) * ld + c0, v);
+    float sc[8], sh[8], al[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[j] - x0[j];
-        s1[j] += d;
-        s2[j] += d * d;
+    for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; al[j] = 0.f; }
+    if (scale) {
+      load8f(scale + c0, sc);
+      load8f(shift + c0, sh);
+      if (act == ACT_PRELU) load8f(alpha + c0, al);
+    }
+    load8(xb + c0, x0);
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x0[j] = act_fwd(act, fmaf(x0[j], sc[j], sh[j]), al[j]);
+    }
+    for (int t = w; t < L; t += 16) {
+      float v[2][8];
+      const bool ok1 = (t + 8) < L;
+      load8(xb + static_cast<long long>(t) * ld + c0, v[0]);
+      if (ok1) load8(xb + static_cast<long long>(t + 8) * ld + c0, v[1]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !ok1) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = scale ? act_fwd(act, fmaf(v[u][j], sc[j], sh[j]), al[j]) : v[u][j];
+          const float d = a - x0[j];
+          s1[j] += d;
+          s2[j] += d * d;
+        }
       }
     }
   }
@@ -268,7 +380,8 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
     for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; q += red[k][1][threadIdx.x]; }
     float mean = 0.f, sd = 0.f;
     if (c < c_real && L > 0) {
-      const float first = __bfloat162float(xb[c]);
+      float first = __bfloat162float(xb[c]);
+      if (scale) first = act_fwd(act, fmaf(first, scale[c], shift[c]), act == ACT_PRELU ? alpha[c] : 0.f);
       const float invl = 1.0f / (static_cast<float>(L) + 1e-16f);
       const float md = a * invl;
       mean = first + md;
@@ -385,25 +498,43 @@ extern "C" int xv_bn_act_apply(const void* y, void* a, const float* scale, const
                                const int32_t* lengths, void* stream) {
   if (!y || !a || !scale || !shift || rows <= 0) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: bad arguments");
   int rc = check_act_layout("xv_bn_act_apply", C, ld, act, alpha); if (rc) return rc;
-  int sms; rc = device_sm_count(&sms); if (rc) return rc;
-  bn_act_apply_kernel<<<grid_for(rows * (C / 8), 256, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha, act, rows, C, ld,
-      seg_len, seg_valid, lengths);
+  if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: rows must fit in int32");
+  dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
+  bn_act_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha, act,
+      static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths);
   XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+static int check_pool_src(const char* who, const void* da, const float* pooled, const float* dpooled, int pool_cpad,
+                          int C, int seg_len) {
+  if (!da && !pooled) return set_error(XV_ERR_INVALID, "%s: need either the upstream gradient or the pooled statistics", who);
+  if (pooled && (!dpooled || pool_cpad != C || seg_len <= 0))
+    return set_error(XV_ERR_INVALID, "%s: fused pooling gradient needs dpooled, pool_cpad == C and seg_len > 0", who);
   return XV_OK;
 }
 
 extern "C" int xv_bn_act_bwd_reduce(const void* y, const void* da, const float* scale, const float* shift,
                                     const float* save_mean, const float* save_rstd, const float* alpha, int act,
                                     int64_t rows, int C, int64_t ld, int seg_len, int seg_valid, const int32_t* lengths,
-                                    float* dgamma, float* dbeta, float* dalpha, void* stream) {
-  if (!y || !da || !scale || !shift || !save_mean || !save_rstd || !dgamma || !dbeta || rows <= 0)
+                                    float* dgamma, float* dbeta, float* dalpha, const float* pooled,
+                                    const float* dpooled, int pool_cpad, int pool_c_real, void* stream) {
+  { int rcp = check_pool_src("xv_bn_act_bwd_reduce", da, pooled, dpooled, pool_cpad, C, seg_len); if (rcp) return rcp; }
+  if (!y || !scale || !shift || !save_mean || !save_rstd || !dgamma || !dbeta || rows <= 0)
     return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_reduce: bad arguments");
   int rc = check_act_layout("xv_bn_act_bwd_reduce", C, ld, act, alpha); if (rc) return rc;
-  dim3 grid(ceil_div(C, 256), ceil_div(rows, RED_ROWS_PER_BLOCK));
-  bn_act_bwd_reduce_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), scale, shift, save_mean, save_rstd,
-      alpha, act, rows, C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha);
+  if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_reduce: rows must fit in int32");
+  dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
+  PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
+  if (pooled)
+    bn_act_bwd_reduce_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), nullptr, scale, shift, save_mean, save_rstd, alpha, act, static_cast<int>(rows), C, ld,
+        seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps);
+  else
+    bn_act_bwd_reduce_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), scale, shift, save_mean, save_rstd,
+        alpha, act, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
@@ -411,26 +542,38 @@ extern "C" int xv_bn_act_bwd_reduce(const void* y, const void* da, const float* 
 extern "C" int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, const float* scale, const float* shift,
                                    const float* save_mean, const float* save_rstd, const float* dgamma,
                                    const float* dbeta, float count, const float* alpha, int act, int64_t rows, int C,
-                                   int64_t ld, int seg_len, int seg_valid, const int32_t* lengths, void* stream) {
-  if (!y || !da || !dy || !scale || !shift || !save_mean || !save_rstd || !dgamma || !dbeta || rows <= 0 || count <= 0)
+                                   int64_t ld, int seg_len, int seg_valid, const int32_t* lengths, const float* pooled,
+                                   const float* dpooled, int pool_cpad, int pool_c_real, void* stream) {
+  { int rcp = check_pool_src("xv_bn_act_bwd_apply", da, pooled, dpooled, pool_cpad, C, seg_len); if (rcp) return rcp; }
+  if (!y || !dy || !scale || !shift || !save_mean || !save_rstd || !dgamma || !dbeta || rows <= 0 || count <= 0)
     return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_apply: bad arguments");
   int rc = check_act_layout("xv_bn_act_bwd_apply", C, ld, act, alpha); if (rc) return rc;
-  int sms; rc = device_sm_count(&sms); if (rc) return rc;
-  bn_act_bwd_apply_kernel<<<grid_for(rows * (C / 8), 256, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dy),
-      scale, shift, save_mean, save_rstd, dgamma, dbeta, 1.0f / count, alpha, act, rows, C, ld, seg_len, seg_valid, lengths);
+  if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_apply: rows must fit in int32");
+  PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
+  dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
+  if (pooled)
+    bn_act_bwd_apply_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), nullptr, static_cast<__nv_bfloat16*>(dy), scale, shift, save_mean,
+        save_rstd, dgamma, dbeta, 1.0f / count, alpha, act, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, ps);
+  else
+    bn_act_bwd_apply_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dy),
+        scale, shift, save_mean, save_rstd, dgamma, dbeta, 1.0f / count, alpha, act, static_cast<int>(rows), C, ld,
+        seg_len, seg_valid, lengths, ps);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
 
 extern "C" int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int B, int seg_len, int seg_valid,
-                                 const int32_t* lengths, int c_real, int cpad, int64_t ld, void* stream) {
+                                 const int32_t* lengths, int c_real, int cpad, int64_t ld, const float* scale,
+                                 const float* shift, const float* alpha, int act, void* stream) {
+  if (scale && (!shift || (act == ACT_PRELU && !alpha))) return set_error(XV_ERR_INVALID, "xv_stats_pool_fwd: fused BN needs shift (and alpha for prelu)");
   if (!x || !out || B <= 0 || seg_len <= 0 || cpad % 8 || c_real > cpad || ld % 8 || ld < cpad)
     return set_error(XV_ERR_INVALID, "xv_stats_pool_fwd: bad arguments");
   dim3 grid(ceil_div(cpad, 256), B);
   stats_pool_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), out, static_cast<__nv_bfloat16*>(out_split), seg_len, seg_valid, lengths,
-      c_real, cpad, ld);
+      c_real, cpad, ld, scale, shift, alpha, act);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

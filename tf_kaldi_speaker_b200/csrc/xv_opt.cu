@@ -154,6 +154,13 @@ __global__ void __launch_bounds__(256) l2_loss_kernel(const float* __restrict__ 
   }
 }
 
+// Host scalars -> device memory through kernel ARGUMENTS (captured by value at launch time): lets the per-step
+// learning rate / margin schedule change between replays of a captured CUDA graph without any host-buffer race.
+struct Scalars16 { float v[16]; };
+__global__ void set_scalars_kernel(float* dst, Scalars16 s, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = s.v[threadIdx.x];
+}
+
 static int opt_grid(long long n, int sms) {
   long long blocks = (n + OPT_BLOCK - 1) / OPT_BLOCK;
   const long long cap = static_cast<long long>(sms) * 8;
@@ -204,6 +211,15 @@ extern "C" int xv_l2_loss(const float* params, const float* blk_l2, int64_t n, f
   if (!params || !blk_l2 || !out || n <= 0 || n % OPT_BLOCK) return set_error(XV_ERR_INVALID, "xv_l2_loss: bad arguments");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
   l2_loss_kernel<<<opt_grid(n, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, blk_l2, n, out);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_set_scalars(float* dst, const float* host_vals, int n, void* stream) {
+  if (!dst || !host_vals || n <= 0 || n > 16) return set_error(XV_ERR_INVALID, "xv_set_scalars: n must be in [1, 16]");
+  Scalars16 s;
+  for (int i = 0; i < 16; ++i) s.v[i] = i < n ? host_vals[i] : 0.f;
+  set_scalars_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(dst, s, n);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

@@ -37,11 +37,23 @@ def margin_lambda(lambda_min, lambda_base, lambda_gamma, lambda_power, global_st
     return lam, fa, 1.0 - fa
 
 
+def margin_schedule(loss_type, params, global_step):
+    """(fa, fs) that the head named ``loss_type`` will use at ``global_step`` (validation-neutralised margins excepted)."""
+    pre = {"asoftmax": "asoftmax", "additive_margin_softmax": "amsoftmax",
+           "additive_angular_margin_softmax": "arcsoftmax"}.get(loss_type)
+    if pre is None or (loss_type == "asoftmax" and int(params.asoftmax_m) == 1):
+        return (0.0, 1.0) if pre is not None else (1.0, 0.0)
+    d = params.dict
+    _, fa, fs = margin_lambda(d[pre + "_lambda_min"], d[pre + "_lambda_base"], d[pre + "_lambda_gamma"],
+                              d[pre + "_lambda_power"], global_step)
+    return fa, fs
+
+
 def _run_head(features, labels, num_outputs, params, is_training, name, head_type, margin=0.0, asoftmax_m=1,
               fa=1.0, fs=0.0):
     eng = get_engine()
     assert features.data.dim() == labels.dim() + 1
-    eng.sched.copy_(torch.tensor([fa, fs], dtype=torch.float32), non_blocking=True)
+    eng.set_sched(fa, fs)
     scaling = float(getattr(features, "scaling", 0.0) or 0.0)
     bias = (name + "/output/bias") if head_type == L.HEAD_SOFTMAX and (name + "/output/bias") in eng.store else None
     want_logits = bool(params.dict.get("debug_logits", False))

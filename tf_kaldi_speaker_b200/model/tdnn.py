@@ -124,7 +124,9 @@ def tdnn(features, params, is_training=None, reuse_variables=None, aux_features=
         y, a = eng.frame_affine(x, "tdnn/%s_%s/kernel" % (name, kind), "tdnn/%s_%s/bias" % (name, kind), k, cout,
                                 name, training, bn=_bn_names("tdnn/%s_bn" % name), act=act,
                                 alpha=("tdnn/%s_relu/alpha" % name) if prelu else None,
-                                unbiased_moving_var=(kind == "conv"), momentum=mom)
+                                unbiased_moving_var=(kind == "conv"), momentum=mom,
+                                # tdnn5's BN + ReLU is fused into the statistics pooling (tdnn5_relu stays lazy)
+                                defer_apply=(n == 5 and params.pooling_type == "statistics_pooling"))
         endpoints["%s_%s" % (name, kind)] = y
         endpoints["%s_bn" % name] = y            # y.affine = (scale, shift): BN output = y*scale + shift (lazy)
         endpoints["%s_relu" % name] = a

@@ -19,7 +19,8 @@ from .. import _lib as L
 from ..runtime import Engine, ScaledUtt, set_engine
 from . import tdnn as tdnn_mod
 from .tdnn import tdnn
-from .loss import softmax, asoftmax, additive_margin_softmax, additive_angular_margin_softmax, declare_head_variables
+from .loss import (softmax, asoftmax, additive_margin_softmax, additive_angular_margin_softmax,
+                   declare_head_variables, margin_schedule)
 
 
 class Trainer(object):
@@ -48,6 +49,8 @@ class Trainer(object):
         self.embeddings = None
         self.train_ops = {}
         self.valid_ops = {}
+        self._static = {}
+        self.use_cuda_graph = bool(params.dict.get("cuda_graph", True))
 
     # ------------------------------------------------------------------ network (trainer.py:168-188)
     def entire_network(self, features, params, is_training, reuse_variables, lengths=None):
@@ -120,34 +123,103 @@ class Trainer(object):
             labels = labels.to(dev, dtype=torch.int32, non_blocking=True)
         return features, labels
 
-    def forward_backward(self, features, labels, global_step):
-        """Forward + backward of one batch; gradients are left in the flat gradient buffer."""
+    def _fwd_bwd(self, features, labels):
+        """Forward + backward of one device-resident batch; gradients are left in the flat gradient buffer."""
         eng = self.engine
-        features, labels = self._to_device(features, labels)
-        self.params.dict["global_step"] = int(global_step)
         eng.begin_step(True)
         out, endpoints = self.entire_network(features, self.params, True, True)
         loss, endpoints_loss = self.loss_network(out, labels, self.num_speakers, self.params, True, True)
         endpoints.update(endpoints_loss)
         self.endpoints = endpoints
-        reg = eng.l2_loss()
+        eng.l2_loss()
         eng.backward()
-        return loss, reg
+
+    def forward_backward(self, features, labels, global_step):
+        """Eager forward + backward (no optimizer step); used by tests and gradient inspection."""
+        eng = self.engine
+        features, labels = self._to_device(features, labels)
+        self.params.dict["global_step"] = int(global_step)
+        eng.set_sched(*margin_schedule(self.loss_type, self.params, global_step))
+        self._fwd_bwd(features, labels)
+        return eng.scalars[0], eng.scalars[1]
+
+    def _static_batch(self, features, labels):
+        """Static device buffers per batch shape (a captured CUDA graph replays on fixed addresses)."""
+        key = tuple(features.shape)
+        st = self._static.get(key)
+        if st is None:
+            dev = self.engine.device
+            st = {"x": torch.empty(key, dtype=torch.float32, device=dev),
+                  "y": torch.empty((key[0],), dtype=torch.int32, device=dev), "calls": 0, "graphs": None, "launches": 0}
+            self._static[key] = st
+        if not torch.is_tensor(features):
+            features = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+        if not torch.is_tensor(labels):
+            labels = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
+        st["x"].copy_(features, non_blocking=True)           # H2D (or D2D) of this step's batch
+        st["y"].copy_(labels.to(torch.int32), non_blocking=True)
+        return st
 
     def train_step(self, features, labels, learning_rate, global_step=None, fetch_loss=False):
-        """The hot-loop body (trainer.py:491-508).  Returns {"loss": total, "raw_loss": loss} when fetch_loss."""
+        """The hot-loop body = sess.run(train_op) (trainer.py:491-508): forward, backward, [all-reduce], optimizer,
+        BN moving statistics.  After two eager warm-up calls per batch shape the whole step is captured into a CUDA
+        graph and replayed; learning rate / margin schedule live in device scalars set before each replay.
+        Returns {"loss": total, "raw_loss": loss} when fetch_loss (one 16-byte D2H read), else None."""
         eng = self.engine
         if global_step is None:
-            global_step = self.global_step
-        loss, reg = self.forward_backward(features, labels, global_step)
-        if self.dp is not None:
-            self.dp.allreduce_gradients()
+            global_step = self.global_step or 0
+        st = self._static_batch(features, labels)
+        self.params.dict["global_step"] = int(global_step)
         if self.opt == L.OPT_ADAM:
             self.adam_t += 1
         clip = bool(self.params.dict.get("clip_gradient", False))
         eng.set_hyper(float(learning_rate), float(self.params.dict.get("momentum", 0.0)), float(max(self.adam_t, 1)),
                       float(self.params.dict.get("clip_gradient_norm", 0.0)) if clip else 0.0)
-        eng.optimizer_step(self.opt, clip=clip)
+        eng.set_sched(*margin_schedule(self.loss_type, self.params, global_step))
+
+        def part_a():
+            self._fwd_bwd(st["x"], st["y"])
+
+        def part_b():
+            eng.optimizer_step(self.opt, clip=clip)
+
+        if st["graphs"] is not None:
+            ga, gb = st["graphs"]
+            ga.replay()
+            if self.dp is not None:
+                self.dp.allreduce_gradients()
+            if gb is not None:
+                gb.replay()
+            eng.launches += st["launches"]
+        else:
+            st["calls"] += 1
+            if self.use_cuda_graph and st["calls"] > 2:
+                l0 = eng.launches
+                eng.capturing = True
+                try:
+                    ga = torch.cuda.CUDAGraph()
+                    gb = None
+                    with torch.cuda.graph(ga):
+                        part_a()
+                        if self.dp is None:
+                            part_b()
+                    if self.dp is not None:
+                        gb = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gb):
+                            part_b()
+                finally:
+                    eng.capturing = False
+                st["launches"] = eng.launches - l0
+                st["graphs"] = (ga, gb)
+                ga.replay()
+                if self.dp is not None:
+                    self.dp.allreduce_gradients()
+                    gb.replay()
+            else:
+                part_a()
+                if self.dp is not None:
+                    self.dp.allreduce_gradients()
+                part_b()
         self.global_step = int(global_step) + 1
         if fetch_loss:
             vals = eng.scalars[:4].tolist()          # one D2H read

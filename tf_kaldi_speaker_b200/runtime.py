@@ -207,18 +207,23 @@ class ParamStore(object):
 class FrameAct(object):
     """Handle of a frame-level tensor: bf16 [B*T, ld] flat-time, valid length per segment."""
 
-    def __init__(self, data, B, T, valid, C_real, lengths=None, name=""):
+    def __init__(self, data, B, T, valid, C_real, lengths=None, name="", ld=None):
         self.data, self.B, self.T, self.valid, self.C, self.lengths, self.name = data, B, T, valid, C_real, lengths, name
         self.grad = None
         self.needs_grad = False
+        self.ld = data.shape[1] if data is not None else ld
+        self.lazy = None          # (y, scale, shift, alpha, act): BN+activation not applied yet (fused into pooling)
+        self.pool_grad = None     # (pooled, dpooled): upstream gradient given implicitly by the statistics pooling
+        self._materialize = None
 
-    @property
-    def ld(self):
-        return self.data.shape[1]
+    def materialize(self):
+        if self.data is None:
+            self._materialize()
+        return self.data
 
     def dense(self):
         """fp32 [B, valid, C] copy (inspection / endpoints only; uniform valid length)."""
-        return self.data.view(self.B, self.T, self.ld)[:, :self.valid, :self.C].float()
+        return self.materialize().view(self.B, self.T, self.ld)[:, :self.valid, :self.C].float()
 
     def lengths_ptr(self):
         return L.ptr(self.lengths)
@@ -233,7 +238,10 @@ class UttAct(object):
         self.needs_grad = False
 
     def dense(self):
-        return self.data if self.col_map is None else self.data[:, self.col_map]
+        if self.col_map is None:
+            return self.data
+        c, cpad = self.col_map            # [mean | std] halves of a channel-padded pooling output
+        return torch.cat([self.data[:, :c], self.data[:, cpad:cpad + c]], 1)
 
 
 class ScaledUtt(UttAct):
@@ -281,6 +289,7 @@ class Engine(object):
         self.sched = torch.tensor([1.0, 0.0], dtype=torch.float32, device=self.device)
         self.scalars = torch.zeros(8, dtype=torch.float32, device=self.device)   # [0] loss, [1] l2 loss, [2] grad sumsq, [3] penalty
         self.inv_global_batch = None     # set by the data-parallel wrapper (1 / (N * B))
+        self.capturing = False           # True while a CUDA graph of the step is being captured
 
     # ---- memory
     def buf(self, name, shape, dtype, zero=False):
@@ -337,7 +346,7 @@ class Engine(object):
         return FrameAct(out, B, T, T - (k - 1), k * dpad, ln, "input")
 
     def frame_affine(self, x, kernel, bias, k, cout, name, training, bn=None, act=L.ACT_RELU, alpha=None,
-                     unbiased_moving_var=False, momentum=0.99):
+                     unbiased_moving_var=False, momentum=0.99, defer_apply=False):
         """affine (temporal conv of width k as implicit GEMM, or dense) -> [BN] -> activation.
         Returns (pre-BN FrameAct y, post-activation FrameAct a).  bn = (gamma, beta, moving_mean, moving_var) names."""
         st = self.store
@@ -352,7 +361,8 @@ class Engine(object):
         use_stats = training and bn is not None
         if use_stats:
             stats = self.buf(name + "/stats", (2, cout_pad), torch.float32, zero=True)
-        a_op = L.operand(x.data, False, div=(x.ld if k > 1 else 0), tap_rows=(1 if k > 1 else 0))
+        xd = x.materialize()
+        a_op = L.operand(xd, False, div=(x.ld if k > 1 else 0), tap_rows=(1 if k > 1 else 0))
         self.gemm(a_op, L.operand(W, True), R, cout_pad, K, y, epilogue=L.EPI_BF16, bias=st.view(bias),
                   col_sum=stats[0] if use_stats else None, col_sumsq=stats[1] if use_stats else None,
                   seg_len=x.T, seg_valid=valid)
@@ -376,19 +386,30 @@ class Engine(object):
         else:
             self.call(self.lib.xv_bn_finalize_infer, L.ptr(st.view(bn[0])), L.ptr(st.view(bn[1])), L.ptr(st.view(bn[2])),
                       L.ptr(st.view(bn[3])), C.c_float(BN_EPS), L.ptr(scale), L.ptr(shift), cout_pad, L.stream_ptr())
-        a = self.buf(name + "/a", (R, cout_pad), torch.bfloat16)
         alpha_t = None if alpha is None else st.view(alpha)
         lp = L.ptr(lengths)
-        self.call(self.lib.xv_bn_act_apply, L.ptr(y), L.ptr(a), L.ptr(scale), L.ptr(shift), L.ptr(alpha_t), act,
-                  C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, L.stream_ptr())
         ya = FrameAct(y, x.B, x.T, valid, cout, lengths, name + "/y")
         ya.affine = (scale, shift)
-        aa = FrameAct(a, x.B, x.T, valid, cout, lengths, name + "/a")
+        aa = FrameAct(None, x.B, x.T, valid, cout, lengths, name + "/a", ld=cout_pad)
+
+        def apply_now():
+            a = self.buf(name + "/a", (R, cout_pad), torch.bfloat16)
+            self.call(self.lib.xv_bn_act_apply, L.ptr(y), L.ptr(a), L.ptr(scale), L.ptr(shift), L.ptr(alpha_t), act,
+                      C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, L.stream_ptr())
+            aa.data = a
+        aa._materialize = apply_now
+        if defer_apply:     # the consumer (statistics pooling) applies BN + activation on the fly
+            aa.lazy = (y, scale, shift, alpha_t, act)
+        else:
+            apply_now()
 
         if training:
             def bwd():
-                if aa.grad is None:
+                if aa.grad is None and aa.pool_grad is None:
                     return
+                fused = aa.grad is None
+                pooled, dpooled = aa.pool_grad if fused else (None, None)
+                pool_args = (L.ptr(pooled), L.ptr(dpooled), cout_pad, cout)
                 if bn is not None:
                     dgamma, dbeta = st.grad(bn[0]), st.grad(bn[1])
                 else:
@@ -397,7 +418,7 @@ class Engine(object):
                 dalpha = None if alpha is None else st.grad(alpha)
                 self.call(self.lib.xv_bn_act_bwd_reduce, L.ptr(y), L.ptr(aa.grad), L.ptr(scale), L.ptr(shift),
                           L.ptr(smean), L.ptr(srstd), L.ptr(alpha_t), act, C.c_int64(R), cout_pad, C.c_int64(cout_pad),
-                          x.T, valid, lp, L.ptr(dgamma), L.ptr(dbeta), L.ptr(dalpha), L.stream_ptr())
+                          x.T, valid, lp, L.ptr(dgamma), L.ptr(dbeta), L.ptr(dalpha), *pool_args, L.stream_ptr())
                 dy = self.buf(name + "/dy", (R, cout_pad), torch.bfloat16)
                 if bn is not None:
                     dg_used, db_used = dgamma, dbeta
@@ -405,10 +426,10 @@ class Engine(object):
                     dg_used = db_used = self.buf(name + "/zeros", (cout_pad,), torch.float32, zero=True)
                 self.call(self.lib.xv_bn_act_bwd_apply, L.ptr(y), L.ptr(aa.grad), L.ptr(dy), L.ptr(scale), L.ptr(shift),
                           L.ptr(smean), L.ptr(srstd), L.ptr(dg_used), L.ptr(db_used), C.c_float(count), L.ptr(alpha_t),
-                          act, C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, L.stream_ptr())
+                          act, C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, *pool_args, L.stream_ptr())
                 # wgrad: dW[(j,c), n] = sum_r X[r+j, c] dY[r, n]
                 gw = st.grad(kernel)
-                self.gemm(L.operand(x.data, True, div=(x.ld if k > 1 else 0), tap_rows=(1 if k > 1 else 0)),
+                self.gemm(L.operand(xd, True, div=(x.ld if k > 1 else 0), tap_rows=(1 if k > 1 else 0)),
                           L.operand(dy, True), K, cout_pad, R, gw, epilogue=L.EPI_F32,
                           splits=self.splits_for(K, cout_pad, R))
                 if x.needs_grad:
@@ -426,13 +447,21 @@ class Engine(object):
         cpad = x.ld
         out = self.buf("pool/out", (x.B, 2 * cpad), torch.float32)
         out3 = self.buf("pool/out3", (x.B, 6 * cpad), torch.bfloat16)
-        self.call(self.lib.xv_stats_pool_fwd, L.ptr(x.data), L.ptr(out), L.ptr(out3), x.B, x.T, x.valid, x.lengths_ptr(),
-                  x.C, cpad, C.c_int64(cpad), L.stream_ptr())
-        col_map = torch.cat([torch.arange(x.C), cpad + torch.arange(x.C)]).to(self.device)
-        u = UttAct(out, out3, "pool", col_map)
+        if x.lazy is not None:      # fused tdnn5 BN + activation: pool act(y*scale + shift) straight from y
+            y_, scale_, shift_, alpha_, act_ = x.lazy
+            self.call(self.lib.xv_stats_pool_fwd, L.ptr(y_), L.ptr(out), L.ptr(out3), x.B, x.T, x.valid, x.lengths_ptr(),
+                      x.C, cpad, C.c_int64(cpad), L.ptr(scale_), L.ptr(shift_), L.ptr(alpha_), act_, L.stream_ptr())
+        else:
+            self.call(self.lib.xv_stats_pool_fwd, L.ptr(x.data), L.ptr(out), L.ptr(out3), x.B, x.T, x.valid,
+                      x.lengths_ptr(), x.C, cpad, C.c_int64(cpad), L.ptr(None), L.ptr(None), L.ptr(None), 0,
+                      L.stream_ptr())
+        u = UttAct(out, out3, "pool", (x.C, cpad))
         if training:
             def bwd():
                 if u.grad is None:
+                    return
+                if x.lazy is not None:      # the tdnn5 BN backward evaluates the pooling gradient on the fly
+                    x.pool_grad = (out, u.grad)
                     return
                 dx = self.buf(x.name + "/grad", (x.B * x.T, cpad), torch.bfloat16)
                 self.call(self.lib.xv_stats_pool_bwd, L.ptr(x.data), L.ptr(out), L.ptr(u.grad), L.ptr(dx), x.B, x.T,
@@ -475,7 +504,7 @@ class Engine(object):
             def bwd():
                 if au.grad is None and yu.grad is None:
                     return
-                da = au.grad if au.grad is not None else torch.zeros_like(a)
+                da = au.grad if au.grad is not None else self.buf(name + "/da0", (B, cout), torch.float32, zero=True)
                 dy = self.buf(name + "/dy", (B, cout), torch.float32)
                 dyb = self.buf(name + "/dyb", (B, cout), torch.bfloat16)
                 gg = lambda i: (L.ptr(st.grad(bn[i])) if bn is not None else L.ptr(None))
@@ -526,6 +555,7 @@ class Engine(object):
         inv_batch = self.inv_global_batch if self.inv_global_batch is not None else 1.0 / B
         h = L.HeadArgs()
         h.type, h.asoftmax_m, h.margin = head_type, asoftmax_m, margin
+        h.cos_m, h.sin_m, h.threshold = math.cos(margin), math.sin(margin), math.cos(math.pi - margin)
         h.sched = self.sched.data_ptr()
         h.labels, h.xnorm = labels.data_ptr(), xnorm.data_ptr()
         h.part_max, h.part_sum, h.target_logit = pmax.data_ptr(), psum.data_ptr(), tgt.data_ptr()
@@ -549,8 +579,11 @@ class Engine(object):
                     self.call(self.lib.xv_head_finish_dw, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), E, cpad, L.stream_ptr())
                 # dx[i, e] = sum_c d[i, c] wn[e, c]
                 dxg = self.buf("head/dxg", (B, E), torch.float32)
+                sp = self.splits_for(B, E, Cn)
+                if sp > 1:
+                    dxg.zero_()
                 self.gemm(L.operand(d, False, cols=Cn), L.operand(wn3, False, rows=E, cols=Cn), B, E, Cn, dxg,
-                          epilogue=L.EPI_F32)
+                          epilogue=L.EPI_F32, splits=sp)
                 du = self.buf(u.name + "/grad", (B, E), torch.float32)
                 use_margin = head_type != L.HEAD_SOFTMAX
                 self.call(self.lib.xv_head_finish_dx, L.ptr(dxg), L.ptr(gnorm if use_margin else None), L.ptr(x),
@@ -566,12 +599,21 @@ class Engine(object):
                   L.stream_ptr())
         return self.scalars[1]
 
-    def set_hyper(self, lr, momentum=0.0, adam_t=1.0, clip_norm=0.0, fa=None, fs=None):
-        """Host -> device scalars (learning rate and the margin schedule are fed every step, trainer.py:493-494)."""
-        hv = torch.tensor([lr, momentum, 0.9, 0.999, 1e-8, adam_t, clip_norm, 0.0], dtype=torch.float32)
-        self.hyper.copy_(hv, non_blocking=True)
-        if fa is not None:
-            self.sched.copy_(torch.tensor([fa, fs], dtype=torch.float32), non_blocking=True)
+    def _set_scalars(self, dst, vals):
+        arr = (C.c_float * len(vals))(*[float(v) for v in vals])
+        L.check(self.lib.xv_set_scalars(L.ptr(dst), arr, len(vals), L.stream_ptr()))
+
+    def set_hyper(self, lr, momentum=0.0, adam_t=1.0, clip_norm=0.0):
+        """Host -> device scalars (the learning rate placeholder is fed every step, trainer.py:326,493-494)."""
+        if self.capturing:
+            return
+        self._set_scalars(self.hyper, [lr, momentum, 0.9, 0.999, 1e-8, adam_t, clip_norm, 0.0])
+
+    def set_sched(self, fa, fs):
+        """Margin annealing factors of loss.py:144-147 for the current global_step."""
+        if self.capturing:
+            return
+        self._set_scalars(self.sched, [fa, fs])
 
     def optimizer_step(self, opt, clip=False):
         st = self.store
