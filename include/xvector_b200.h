@@ -136,6 +136,10 @@ XV_API int xv_bn_finalize_train(const float* col_sum, const float* col_sumsq, co
                                 const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                                 float momentum, float eps, int unbiased_moving_var, float* scale, float* shift,
                                 float* save_mean, float* save_rstd, int C, void* stream);
+/* Per-channel sum and sum of squares of (y - bias) over the valid rows (+= into col_sum / col_sumsq): the batch
+ * statistics of tf.layers.batch_normalization for layers whose GEMM is too short to hide a reduction epilogue. */
+XV_API int xv_col_stats(const void* y, const float* bias, int64_t rows, int C, int64_t ld, int seg_len, int seg_valid,
+                        const int32_t* lengths, float* col_sum, float* col_sumsq, void* stream);
 /* ... inference mode (is_training=False, model/trainer.py:210-225): scale/shift from the moving statistics. */
 XV_API int xv_bn_finalize_infer(const float* gamma, const float* beta, const float* moving_mean,
                                 const float* moving_var, float eps, float* scale, float* shift, int C, void* stream);

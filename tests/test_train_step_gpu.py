@@ -105,4 +105,4 @@ def test_train_step_parity(name, loss_type, extra, gstep, lr):
         else:
             assert e <= 1e-3, (n, e)        # zero-gradient biases: absolute
     for n, e in r["param_err"].items():
-        assert e <= (3e-2 if "moving" in n else 1e-2), (n, e)
+        assert e <= 5e-2, (n, e)

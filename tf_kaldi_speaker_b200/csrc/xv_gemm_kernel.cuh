@@ -316,9 +316,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldc + nc0;
             const bool add_bias = p.bias != nullptr && split == 0;
             if (p.splits > 1) {
+              if (full_chunk) {      // 16-byte vector reductions: 8 RED instructions per 32 columns instead of 32
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nc0 + j < p.N) atomicAdd(dst + j, v[j] + (add_bias ? __ldg(p.bias + nc0 + j) : 0.f));
+                for (int j = 0; j < 8; ++j) {
+                  float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                  if (add_bias) {
+                    o.x += __ldg(p.bias + nc0 + 4 * j); o.y += __ldg(p.bias + nc0 + 4 * j + 1);
+                    o.z += __ldg(p.bias + nc0 + 4 * j + 2); o.w += __ldg(p.bias + nc0 + 4 * j + 3);
+                  }
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(o.x), "f"(o.y),
+                               "f"(o.z), "f"(o.w) : "memory");
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (nc0 + j < p.N) atomicAdd(dst + j, v[j] + (add_bias ? __ldg(p.bias + nc0 + j) : 0.f));
+              }
             } else if (full_chunk) {
               float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll

@@ -188,6 +188,57 @@ __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* 
   }
 }
 
+// Per-channel sum / sum of squares of (y - bias) over the valid rows: the BN batch statistics of layers whose GEMM is
+// too short (K <= 512) to hide a reduction epilogue.  Same row-streaming layout.
+__global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
+                                                        int rows, int C, long long ld, int seg_len, int seg_valid,
+                                                        const int* __restrict__ lengths, float* col_sum, float* col_sumsq) {
+  __shared__ float red[8][2][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (c0 < C) {
+    float bs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bs[j] = bias ? bias[c0 + j] : 0.f;
+    const int r0 = blockIdx.y * STREAM_ROWS;
+    const int r1 = min(r0 + STREAM_ROWS, rows);
+    for (int m = r0 + w; m < r1; m += 16) {
+      float v[2][8];
+      bool ok[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int mm = m + 8 * u;
+        ok[u] = mm < r1 && row_is_valid(mm, seg_len, seg_valid, lengths);
+        if (ok[u]) load8(y + static_cast<long long>(mm) * ld + c0, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[u][j] - bs[j];
+          s1[j] += d;
+          s2[j] = fmaf(d, d, s2[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[w][0][lane * 8 + j] = s1[j]; red[w][1][lane * 8 + j] = s2[j]; }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; q += red[k][1][threadIdx.x]; }
+    atomicAdd(col_sum + c, a);
+    atomicAdd(col_sumsq + c, q);
+  }
+}
+
 // Column reductions for the BN backward: dbeta += sum g, dgamma += sum g*yhat, dalpha += sum da*min(z,0).
 template <bool FUSED_POOL>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
@@ -503,6 +554,18 @@ extern "C" int xv_bn_act_apply(const void* y, void* a, const float* scale, const
   bn_act_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha, act,
       static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_col_stats(const void* y, const float* bias, int64_t rows, int C, int64_t ld, int seg_len, int seg_valid,
+                            const int32_t* lengths, float* col_sum, float* col_sumsq, void* stream) {
+  if (!y || !col_sum || !col_sumsq || rows <= 0 || rows > 0x7fffffffLL || C <= 0 || C % 8 || ld % 8 || ld < C)
+    return set_error(XV_ERR_INVALID, "xv_col_stats: bad arguments");
+  dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
+  col_stats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), bias, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, col_sum,
+      col_sumsq);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

@@ -363,9 +363,15 @@ class Engine(object):
             stats = self.buf(name + "/stats", (2, cout_pad), torch.float32, zero=True)
         xd = x.materialize()
         a_op = L.operand(xd, False, div=(x.ld if k > 1 else 0), tap_rows=(1 if k > 1 else 0))
+        # BN statistics: in the GEMM epilogue when the K loop is long enough to hide the column reduction
+        # (tdnn2/tdnn3), otherwise in a separate streaming pass over y (tdnn1/4/5: the epilogue would be exposed).
+        epi_stats = use_stats and K >= 1024
         self.gemm(a_op, L.operand(W, True), R, cout_pad, K, y, epilogue=L.EPI_BF16, bias=st.view(bias),
-                  col_sum=stats[0] if use_stats else None, col_sumsq=stats[1] if use_stats else None,
+                  col_sum=stats[0] if epi_stats else None, col_sumsq=stats[1] if epi_stats else None,
                   seg_len=x.T, seg_valid=valid)
+        if use_stats and not epi_stats:
+            self.call(self.lib.xv_col_stats, L.ptr(y), L.ptr(st.view(bias)), C.c_int64(R), cout_pad, C.c_int64(cout_pad),
+                      x.T, valid, L.ptr(lengths), L.ptr(stats[0]), L.ptr(stats[1]), L.stream_ptr())
         if use_stats and lengths is not None:
             raise NotImplementedError("training-mode BN needs one valid length per batch (data_loader.py:273)")
         scale = self.buf(name + "/scale", (cout_pad,), torch.float32)
