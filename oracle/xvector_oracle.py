@@ -201,11 +201,15 @@ def bf16_ste(x):
     return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
 
 
-def batch_norm(x, P, prefix, momentum, is_training, updates, unbiased_moving_var=False, store=None):
+def batch_norm(x, P, prefix, momentum, is_training, updates, unbiased_moving_var=False, store=None,
+               stats_from_stored=False):
     """tf.layers.batch_normalization, axis=-1, eps=1e-3.  Training: biased batch statistics over all
     leading axes; moving <- moving*m + batch*(1-m).  The fused rank-4 TF path (tdnn1-3) updates
     moving_variance with the unbiased batch variance; the unfused rank-2/3 path with the biased one."""
     g, b = P[prefix + "/gamma"], P[prefix + "/beta"]
+    if store is not None and stats_from_stored:   # short-K layers: statistics are taken from the stored bf16 tensor
+        x = store(x)
+        store = None
     if is_training:
         xr = x.reshape(-1, x.shape[-1])
         n = xr.shape[0]
@@ -341,7 +345,8 @@ def tdnn(features, P, params, is_training=False, updates=None, lengths=None, mir
             ep["%s_dense" % name] = x
         x = batch_norm(x, P, "tdnn/%s_bn" % name, mom, is_training, updates,
                        unbiased_moving_var=(mirror_tf_fused_bn and kind == "conv"),
-                       store=bf16_ste if emulate_bf16 else None)
+                       store=bf16_ste if emulate_bf16 else None,
+                       stats_from_stored=(name in ("tdnn1", "tdnn4", "tdnn5")))
         ep["%s_bn" % name] = x
         x = _activation(x, P, "tdnn/%s_relu" % name, relu_type)
         if not (name == "tdnn5" and params.pooling_type == "statistics_pooling"):

@@ -1,0 +1,62 @@
+"""World-size-2 gloo test of the data-parallel host logic (batch sharding, flat-buffer all-reduce, scalar mean).
+The N-GPU semantics to preserve: summing the per-rank gradients of sum_i CE_i / (N*B) equals the gradient of the
+mean loss over the concatenated global batch."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from oracle import xvector_oracle as O
+    from tf_kaldi_speaker_b200 import parallel
+    r, w = parallel.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    B, E, C = 8, 16, 5
+    x = torch.randn(B, E, dtype=torch.float64)
+    y = torch.randint(0, C, (B,))
+    W = torch.randn(E, C, dtype=torch.float64)
+    # global-batch reference
+    Wg = W.clone().requires_grad_(True)
+    p = O.ParamsPlain(amsoftmax_m=0.2, amsoftmax_lambda_min=0, amsoftmax_lambda_base=10, amsoftmax_lambda_gamma=1,
+                      amsoftmax_lambda_power=1, global_step=3)
+    loss, _ = O.additive_margin_softmax_head(x, y, {"softmax/output/kernel": Wg}, p)
+    (gref,) = torch.autograd.grad(loss, Wg)
+    # this rank's shard, loss scaled by 1/(N*B_local) = local mean / N
+    xs, ys = parallel.shard_batch(x, y, rank, world)
+    Wl = W.clone().requires_grad_(True)
+    ll, _ = O.additive_margin_softmax_head(xs, ys, {"softmax/output/kernel": Wl}, p)
+    (gl,) = torch.autograd.grad(ll / world, Wl)
+    comm = parallel.FlatAllReduce()
+    flat = gl.reshape(-1).clone()
+    comm.allreduce_(flat)
+    ok_grad = torch.allclose(flat.reshape(E, C), gref, rtol=1e-10, atol=1e-12)
+    tot = comm.mean_scalar(float(ll) / world)
+    ok_loss = abs(tot - float(loss)) < 1e-10
+    params = torch.full((4,), float(rank))
+    comm.broadcast_(params, src=0)
+    ok_bcast = bool((params == 0).all())
+    out.put((rank, ok_grad, ok_loss, ok_bcast))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_allreduce_equals_global_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29731
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    for r in res:
+        assert r[1] and r[2] and r[3], r

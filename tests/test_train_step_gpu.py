@@ -4,7 +4,7 @@ oracle, through the reference-shaped API (Trainer.build / train_step) and the C 
 Tolerances (north_star): per-step loss relative error <= 1e-3 and embedding cosine >= 0.999 against the fp64
 oracle.  Gradients are checked twice:
   * against the oracle run in ``emulate_bf16`` mode (same arithmetic, bf16 rounding at the same storage points as
-    the CUDA path): per-tensor relative Frobenius error <= 0.12 (residual ReLU-mask flips from accumulation-order
+    the CUDA path): per-tensor relative Frobenius error <= 0.15 (residual ReLU-mask flips from accumulation-order
     differences) -- this isolates kernel bugs;
   * against the plain fp64 oracle: <= 0.30 and cosine >= 0.95.  A bf16-activation pipeline cannot do better on
     this metric: a 0.3-1 % perturbation of a pre-activation flips the ReLU mask of the ~0.5 % of units nearest to
@@ -99,7 +99,7 @@ def test_train_step_parity(name, loss_type, extra, gstep, lr):
     print("  worst vs fp64:", sorted(r["grad_err64"].items(), key=lambda kv: -kv[1])[:3])
     for n, e in r["grad_err"].items():
         if n in r["grad_err64"]:
-            assert e <= 0.12, (n, e)
+            assert e <= 0.15, (n, e)
             assert r["grad_err64"][n] <= 0.30, (n, r["grad_err64"][n])
             assert r["grad_cos64"][n] >= 0.95, (n, r["grad_cos64"][n])
         else:

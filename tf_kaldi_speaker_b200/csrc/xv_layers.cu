@@ -118,14 +118,40 @@ __global__ void bn_finalize_infer_kernel(const float* __restrict__ gamma, const 
   shift[c] = beta[c] - mm[c] * sc;
 }
 
-// Row-streaming layout shared by the three BN kernels below: grid = (C/256, row chunks of STREAM_ROWS); a block is
-// 8 warps, a warp covers 256 channels (8 per lane, one 16-byte vector) and walks rows w, w+8, ... of its chunk two
-// at a time.  Every per-channel constant (scale, shift, mean, rstd, dgamma, dbeta, alpha) is loaded ONCE per thread.
+// Row-streaming layout shared by the BN kernels below: grid = (C/128, row chunks of STREAM_ROWS); a block is 8 warps,
+// a warp covers 128 channels (4 per lane, one 8-byte vector) and walks rows w, w+8, ... of its chunk two at a time.
+// Every per-channel constant (scale, shift, mean, rstd, dgamma, dbeta, alpha) is loaded ONCE per thread, and four
+// channels per thread keep the kernels under 64-80 registers so that 3-4 blocks (24-32 warps) stay resident per SM.
 constexpr int STREAM_ROWS = 64;
+constexpr int SV = 4;                 // channels per thread
+constexpr int SCH = 32 * SV;          // channels per warp / block column
+
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&f)[4]) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+__device__ __forceinline__ void load4f(const float* p, float (&f)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+}
+
+template <int ACT>
+__device__ __forceinline__ float actf(float z, float alpha) { return act_fwd(ACT, z, alpha); }
+template <int ACT>
+__device__ __forceinline__ float actg(float z, float alpha) { return act_grad(ACT, z, alpha); }
 
 // Per-(segment, channel) coefficients of the on-the-fly pooling gradient: da = ca + cb * a.
 struct PoolCoef {
-  float ca[8], cb[8];
+  float ca[SV], cb[SV];
   int b;
 };
 __device__ __forceinline__ void pool_coef_load(PoolCoef& pc, const PoolGradSrc& ps, int b, int c0, int seg_valid,
@@ -133,12 +159,12 @@ __device__ __forceinline__ void pool_coef_load(PoolCoef& pc, const PoolGradSrc& 
   if (pc.b == b) return;
   pc.b = b;
   const float invl = 1.0f / (static_cast<float>(lengths ? lengths[b] : seg_valid) + 1e-16f);
-  float mu[8], sd[8], gm[8], gs[8];
+  float mu[SV], sd[SV], gm[SV], gs[SV];
   const float* pb = ps.pooled + static_cast<long long>(b) * 2 * ps.cpad;
   const float* gb = ps.dpooled + static_cast<long long>(b) * 2 * ps.cpad;
-  load8f(pb + c0, mu); load8f(pb + ps.cpad + c0, sd); load8f(gb + c0, gm); load8f(gb + ps.cpad + c0, gs);
+  load4f(pb + c0, mu); load4f(pb + ps.cpad + c0, sd); load4f(gb + c0, gm); load4f(gb + ps.cpad + c0, gs);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < SV; ++j) {
     float ca = 0.f, cb = 0.f;
     if (c0 + j < ps.c_real) {
       ca = gm[j] * invl;
@@ -153,72 +179,73 @@ __device__ __forceinline__ void pool_coef_load(PoolCoef& pc, const PoolGradSrc& 
 }
 
 // a = act(y*scale + shift) on valid rows, 0 on invalid rows.
+template <int ACT>
 __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ alpha, int act, int rows, int C, long long ld,
+                                    const float* __restrict__ alpha, int rows, int C, long long ld,
                                     int seg_len, int seg_valid, const int* __restrict__ lengths) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int c0 = blockIdx.x * SCH + lane * SV;
   if (c0 >= C) return;
-  float sc[8], sh[8], al[8];
-  load8f(scale + c0, sc);
-  load8f(shift + c0, sh);
+  float sc[SV], sh[SV], al[SV];
+  load4f(scale + c0, sc);
+  load4f(shift + c0, sh);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) al[j] = (act == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+  for (int j = 0; j < SV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
   const int r0 = blockIdx.y * STREAM_ROWS;
   const int r1 = min(r0 + STREAM_ROWS, rows);
-  for (int m = r0 + w; m < r1; m += 16) {
-    float v[2][8];
-    bool in[2], valid[2];
+  for (int m = r0 + w; m < r1; m += 32) {
+    float v[4][SV];
+    bool in[4], valid[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int mm = m + 8 * u;
       in[u] = mm < r1;
       valid[u] = in[u] && row_is_valid(mm, seg_len, seg_valid, lengths);
-      if (valid[u]) load8(y + static_cast<long long>(mm) * ld + c0, v[u]);
+      if (valid[u]) load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
       if (!in[u]) continue;
-      float o[8];
+      float o[SV];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = valid[u] ? act_fwd(act, fmaf(v[u][j], sc[j], sh[j]), al[j]) : 0.f;
-      store8(a + static_cast<long long>(m + 8 * u) * ld + c0, o);
+      for (int j = 0; j < SV; ++j) o[j] = valid[u] ? actf<ACT>(fmaf(v[u][j], sc[j], sh[j]), al[j]) : 0.f;
+      store4(a + static_cast<long long>(m + 8 * u) * ld + c0, o);
     }
   }
 }
 
 // Per-channel sum / sum of squares of (y - bias) over the valid rows: the BN batch statistics of layers whose GEMM is
-// too short (K <= 512) to hide a reduction epilogue.  Same row-streaming layout.
+// too short (K <= 512) to hide a reduction epilogue.
 __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
                                                         int rows, int C, long long ld, int seg_len, int seg_valid,
                                                         const int* __restrict__ lengths, float* col_sum, float* col_sumsq) {
-  __shared__ float red[8][2][256];
+  __shared__ float red[8][2][SCH];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + lane * 8;
-  float s1[8], s2[8];
+  const int c0 = blockIdx.x * SCH + lane * SV;
+  float s1[SV], s2[SV];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (int j = 0; j < SV; ++j) s1[j] = s2[j] = 0.f;
   if (c0 < C) {
-    float bs[8];
+    float bs[SV];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) bs[j] = bias ? bias[c0 + j] : 0.f;
+    for (int j = 0; j < SV; ++j) bs[j] = bias ? bias[c0 + j] : 0.f;
     const int r0 = blockIdx.y * STREAM_ROWS;
     const int r1 = min(r0 + STREAM_ROWS, rows);
-    for (int m = r0 + w; m < r1; m += 16) {
-      float v[2][8];
-      bool ok[2];
+    for (int m = r0 + w; m < r1; m += 32) {
+      float v[4][SV];
+      bool ok[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const int mm = m + 8 * u;
         ok[u] = mm < r1 && row_is_valid(mm, seg_len, seg_valid, lengths);
-        if (ok[u]) load8(y + static_cast<long long>(mm) * ld + c0, v[u]);
+        if (ok[u]) load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         if (!ok[u]) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < SV; ++j) {
           const float d = v[u][j] - bs[j];
           s1[j] += d;
           s2[j] = fmaf(d, d, s2[j]);
@@ -227,10 +254,10 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { red[w][0][lane * 8 + j] = s1[j]; red[w][1][lane * 8 + j] = s2[j]; }
+  for (int j = 0; j < SV; ++j) { red[w][0][lane * SV + j] = s1[j]; red[w][1][lane * SV + j] = s2[j]; }
   __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < C) {
+  const int c = blockIdx.x * SCH + threadIdx.x;
+  if (threadIdx.x < SCH && c < C) {
     float a = 0.f, q = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; q += red[k][1][threadIdx.x]; }
@@ -240,38 +267,38 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
 }
 
 // Column reductions for the BN backward: dbeta += sum g, dgamma += sum g*yhat, dalpha += sum da*min(z,0).
-template <bool FUSED_POOL>
+template <bool FUSED_POOL, int ACT>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
-    const float* __restrict__ alpha, int act, int rows, int C, long long ld, int seg_len, int seg_valid,
+    const float* __restrict__ alpha, int rows, int C, long long ld, int seg_len, int seg_valid,
     const int* __restrict__ lengths, float* dgamma, float* dbeta, float* dalpha, PoolGradSrc ps) {
-  __shared__ float red[8][3][256];
+  __shared__ float red[8][3][SCH];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int c0 = blockIdx.x * SCH + lane * SV;
   const bool c_ok = c0 < C;
-  float sg[8], sgy[8], sal[8];
+  float sg[SV], sgy[SV], sal[SV];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sg[j] = sgy[j] = sal[j] = 0.f;
+  for (int j = 0; j < SV; ++j) sg[j] = sgy[j] = sal[j] = 0.f;
   if (c_ok) {
-    float sc[8], sh[8], mu[8], rs[8], al[8];
-    load8f(scale + c0, sc); load8f(shift + c0, sh); load8f(save_mean + c0, mu); load8f(save_rstd + c0, rs);
+    float sc[SV], sh[SV], mu[SV], rs[SV], al[SV];
+    load4f(scale + c0, sc); load4f(shift + c0, sh); load4f(save_mean + c0, mu); load4f(save_rstd + c0, rs);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) al[j] = (act == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+    for (int j = 0; j < SV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
     PoolCoef pc;
     pc.b = -1;
     const int r0 = blockIdx.y * STREAM_ROWS;
     const int r1 = min(r0 + STREAM_ROWS, rows);
     for (int m = r0 + w; m < r1; m += 16) {
-      float v[2][8], d[2][8];
+      float v[2][SV], d[2][SV];
       bool ok[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int mm = m + 8 * u;
         ok[u] = mm < r1 && row_is_valid(mm, seg_len, seg_valid, lengths);
         if (ok[u]) {
-          load8(y + static_cast<long long>(mm) * ld + c0, v[u]);
-          if (!FUSED_POOL) load8(da + static_cast<long long>(mm) * ld + c0, d[u]);
+          load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
+          if (!FUSED_POOL) load4(da + static_cast<long long>(mm) * ld + c0, d[u]);
         }
       }
 #pragma unroll
@@ -279,52 +306,52 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
         if (!ok[u]) continue;
         if (FUSED_POOL) pool_coef_load(pc, ps, (m + 8 * u) / seg_len, c0, seg_valid, lengths);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < SV; ++j) {
           const float z = fmaf(v[u][j], sc[j], sh[j]);
-          const float dd = FUSED_POOL ? fmaf(pc.cb[j], act_fwd(act, z, al[j]), pc.ca[j]) : d[u][j];
-          const float g = dd * act_grad(act, z, al[j]);
+          const float dd = FUSED_POOL ? fmaf(pc.cb[j], actf<ACT>(z, al[j]), pc.ca[j]) : d[u][j];
+          const float g = dd * actg<ACT>(z, al[j]);
           sg[j] += g;
           sgy[j] += g * (v[u][j] - mu[j]) * rs[j];
-          if (act == ACT_PRELU) sal[j] += dd * fminf(z, 0.f);
+          if (ACT == ACT_PRELU) sal[j] += dd * fminf(z, 0.f);
         }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    red[w][0][lane * 8 + j] = sg[j];
-    red[w][1][lane * 8 + j] = sgy[j];
-    red[w][2][lane * 8 + j] = sal[j];
+  for (int j = 0; j < SV; ++j) {
+    red[w][0][lane * SV + j] = sg[j];
+    red[w][1][lane * SV + j] = sgy[j];
+    red[w][2][lane * SV + j] = sal[j];
   }
   __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < C) {
+  const int c = blockIdx.x * SCH + threadIdx.x;
+  if (threadIdx.x < SCH && c < C) {
     float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; b += red[k][1][threadIdx.x]; d += red[k][2][threadIdx.x]; }
     atomicAdd(dbeta + c, a);
     atomicAdd(dgamma + c, b);
-    if (act == ACT_PRELU && dalpha) atomicAdd(dalpha + c, d);
+    if (ACT == ACT_PRELU && dalpha) atomicAdd(dalpha + c, d);
   }
 }
 
 // dy = scale * (g - dbeta/n - yhat*dgamma/n) on valid rows, 0 elsewhere (scale = gamma*rstd).
-template <bool FUSED_POOL>
+template <bool FUSED_POOL, int ACT>
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dy,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ save_mean,
     const float* __restrict__ save_rstd, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-    float inv_count, const float* __restrict__ alpha, int act, int rows, int C, long long ld, int seg_len,
+    float inv_count, const float* __restrict__ alpha, int rows, int C, long long ld, int seg_len,
     int seg_valid, const int* __restrict__ lengths, PoolGradSrc ps) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int c0 = blockIdx.x * SCH + lane * SV;
   if (c0 >= C) return;
-  float sc[8], sh[8], mu[8], rs[8], dg[8], db[8], al[8];
-  load8f(scale + c0, sc); load8f(shift + c0, sh); load8f(save_mean + c0, mu); load8f(save_rstd + c0, rs);
-  load8f(dgamma + c0, dg); load8f(dbeta + c0, db);
+  float sc[SV], sh[SV], mu[SV], rs[SV], dg[SV], db[SV], al[SV];
+  load4f(scale + c0, sc); load4f(shift + c0, sh); load4f(save_mean + c0, mu); load4f(save_rstd + c0, rs);
+  load4f(dgamma + c0, dg); load4f(dbeta + c0, db);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    al[j] = (act == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+  for (int j = 0; j < SV; ++j) {
+    al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
     dg[j] *= inv_count;
     db[j] *= inv_count;
   }
@@ -333,7 +360,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
   const int r0 = blockIdx.y * STREAM_ROWS;
   const int r1 = min(r0 + STREAM_ROWS, rows);
   for (int m = r0 + w; m < r1; m += 16) {
-    float v[2][8], d[2][8];
+    float v[2][SV], d[2][SV];
     bool in[2], valid[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -341,29 +368,29 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
       in[u] = mm < r1;
       valid[u] = in[u] && row_is_valid(mm, seg_len, seg_valid, lengths);
       if (valid[u]) {
-        load8(y + static_cast<long long>(mm) * ld + c0, v[u]);
-        if (!FUSED_POOL) load8(da + static_cast<long long>(mm) * ld + c0, d[u]);
+        load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
+        if (!FUSED_POOL) load4(da + static_cast<long long>(mm) * ld + c0, d[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (!in[u]) continue;
-      float o[8];
+      float o[SV];
       if (valid[u]) {
         if (FUSED_POOL) pool_coef_load(pc, ps, (m + 8 * u) / seg_len, c0, seg_valid, lengths);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < SV; ++j) {
           const float z = fmaf(v[u][j], sc[j], sh[j]);
-          const float dd = FUSED_POOL ? fmaf(pc.cb[j], act_fwd(act, z, al[j]), pc.ca[j]) : d[u][j];
-          const float g = dd * act_grad(act, z, al[j]);
+          const float dd = FUSED_POOL ? fmaf(pc.cb[j], actf<ACT>(z, al[j]), pc.ca[j]) : d[u][j];
+          const float g = dd * actg<ACT>(z, al[j]);
           const float yh = (v[u][j] - mu[j]) * rs[j];
           o[j] = sc[j] * (g - db[j] - yh * dg[j]);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        for (int j = 0; j < SV; ++j) o[j] = 0.f;
       }
-      store8(dy + static_cast<long long>(m + 8 * u) * ld + c0, o);
+      store4(dy + static_cast<long long>(m + 8 * u) * ld + c0, o);
     }
   }
 }
@@ -492,6 +519,15 @@ __global__ void stats_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const
   }
 }
 
+#define XV_ACT_DISPATCH(ACTV, EXPR)                               \
+  switch (ACTV) {                                                  \
+    case ACT_NONE: { constexpr int A_ = ACT_NONE; EXPR; } break;   \
+    case ACT_RELU: { constexpr int A_ = ACT_RELU; EXPR; } break;   \
+    case ACT_LRELU: { constexpr int A_ = ACT_LRELU; EXPR; } break; \
+    case ACT_PRELU: { constexpr int A_ = ACT_PRELU; EXPR; } break; \
+    default: { constexpr int A_ = ACT_TANH; EXPR; } break;         \
+  }
+
 static inline int grid_for(long long work_items, int block, int sms) {
   long long g = (work_items + block - 1) / block;
   const long long cap = static_cast<long long>(sms) * 16;   // grid-stride beyond 16 resident-ish blocks per SM
@@ -550,10 +586,10 @@ extern "C" int xv_bn_act_apply(const void* y, void* a, const float* scale, const
   if (!y || !a || !scale || !shift || rows <= 0) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: bad arguments");
   int rc = check_act_layout("xv_bn_act_apply", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: rows must fit in int32");
-  dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
-  bn_act_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha, act,
-      static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths);
+  dim3 grid(ceil_div(C, SCH), ceil_div(rows, STREAM_ROWS));
+  XV_ACT_DISPATCH(act, (bn_act_apply_kernel<A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha,
+      static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths)));
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
@@ -562,7 +598,7 @@ extern "C" int xv_col_stats(const void* y, const float* bias, int64_t rows, int 
                             const int32_t* lengths, float* col_sum, float* col_sumsq, void* stream) {
   if (!y || !col_sum || !col_sumsq || rows <= 0 || rows > 0x7fffffffLL || C <= 0 || C % 8 || ld % 8 || ld < C)
     return set_error(XV_ERR_INVALID, "xv_col_stats: bad arguments");
-  dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
+  dim3 grid(ceil_div(C, SCH), ceil_div(rows, STREAM_ROWS));
   col_stats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), bias, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, col_sum,
       col_sumsq);
@@ -588,16 +624,17 @@ extern "C" int xv_bn_act_bwd_reduce(const void* y, const void* da, const float* 
     return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_reduce: bad arguments");
   int rc = check_act_layout("xv_bn_act_bwd_reduce", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_reduce: rows must fit in int32");
-  dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
+  dim3 grid(ceil_div(C, SCH), ceil_div(rows, STREAM_ROWS));
   PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
-  if (pooled)
-    bn_act_bwd_reduce_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(y), nullptr, scale, shift, save_mean, save_rstd, alpha, act, static_cast<int>(rows), C, ld,
-        seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps);
-  else
-    bn_act_bwd_reduce_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (pooled) {
+    XV_ACT_DISPATCH(act, (bn_act_bwd_reduce_kernel<true, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), nullptr, scale, shift, save_mean, save_rstd, alpha,
+        static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps)));
+  } else {
+    XV_ACT_DISPATCH(act, (bn_act_bwd_reduce_kernel<false, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), scale, shift, save_mean, save_rstd,
-        alpha, act, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps);
+        alpha, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps)));
+  }
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
@@ -614,15 +651,16 @@ extern "C" int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, cons
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_apply: rows must fit in int32");
   PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
   dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
-  if (pooled)
-    bn_act_bwd_apply_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (pooled) {
+    XV_ACT_DISPATCH(act, (bn_act_bwd_apply_kernel<true, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), nullptr, static_cast<__nv_bfloat16*>(dy), scale, shift, save_mean,
-        save_rstd, dgamma, dbeta, 1.0f / count, alpha, act, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, ps);
-  else
-    bn_act_bwd_apply_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        save_rstd, dgamma, dbeta, 1.0f / count, alpha, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, ps)));
+  } else {
+    XV_ACT_DISPATCH(act, (bn_act_bwd_apply_kernel<false, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dy),
-        scale, shift, save_mean, save_rstd, dgamma, dbeta, 1.0f / count, alpha, act, static_cast<int>(rows), C, ld,
-        seg_len, seg_valid, lengths, ps);
+        scale, shift, save_mean, save_rstd, dgamma, dbeta, 1.0f / count, alpha, static_cast<int>(rows), C, ld,
+        seg_len, seg_valid, lengths, ps)));
+  }
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
