@@ -650,7 +650,7 @@ extern "C" int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, cons
   int rc = check_act_layout("xv_bn_act_bwd_apply", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_apply: rows must fit in int32");
   PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
-  dim3 grid(ceil_div(C, 256), ceil_div(rows, STREAM_ROWS));
+  dim3 grid(ceil_div(C, SCH), ceil_div(rows, STREAM_ROWS));
   if (pooled) {
     XV_ACT_DISPATCH(act, (bn_act_bwd_apply_kernel<true, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), nullptr, static_cast<__nv_bfloat16*>(dy), scale, shift, save_mean,
