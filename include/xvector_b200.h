@@ -107,7 +107,7 @@ typedef struct {
   int32_t epilogue;      /* xv_epilogue                                                             */
   int32_t seg_len;       /* row validity for statistics: row m valid iff (m % seg_len) < seg_valid   */
   int32_t seg_valid;     /* (seg_len = 0: all rows < M valid)                                       */
-  int32_t _pad;
+  int32_t accumulate;    /* XV_EPI_BF16 only: out = bf16(acc + out) (gradient fan-in of a shared activation)  */
   void* out;
   int64_t ldc;
   const float* bias;     /* optional [N]                                                            */

@@ -38,7 +38,7 @@ class HeadArgs(C.Structure):
 class GemmArgs(C.Structure):
     _fields_ = [("a", Operand), ("b", Operand), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("splits", C.c_int32), ("epilogue", C.c_int32), ("seg_len", C.c_int32), ("seg_valid", C.c_int32),
-                ("_pad", C.c_int32), ("out", C.c_void_p), ("ldc", C.c_int64), ("bias", C.c_void_p),
+                ("accumulate", C.c_int32), ("out", C.c_void_p), ("ldc", C.c_int64), ("bias", C.c_void_p),
                 ("col_sum", C.c_void_p), ("col_sumsq", C.c_void_p), ("head", HeadArgs)]
 
 
@@ -86,12 +86,13 @@ def operand(t, mn_major=False, div=0, tap_rows=0, rows=None, cols=None):
 
 
 def gemm(a_op, b_op, M, N, K, out, epilogue=EPI_BF16, splits=1, bias=None, col_sum=None, col_sumsq=None,
-         seg_len=0, seg_valid=0, head=None, ldc=None):
+         seg_len=0, seg_valid=0, head=None, ldc=None, accumulate=False):
     args = GemmArgs()
     args.a, args.b = a_op, b_op
     args.M, args.N, args.K = M, N, K
     args.splits, args.epilogue = splits, epilogue
     args.seg_len, args.seg_valid = seg_len, seg_valid
+    args.accumulate = 1 if accumulate else 0
     args.out = out.data_ptr()
     args.ldc = out.stride(0) if ldc is None else ldc
     args.bias = 0 if bias is None else bias.data_ptr()

@@ -74,6 +74,7 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   splits = (kp.num_kb + kp.kb_per_split - 1) / kp.kb_per_split;   // no empty split
   kp.splits = splits;
   kp.seg_len = a->seg_len; kp.seg_valid = a->seg_valid;
+  kp.accumulate = (a->epilogue == XV_EPI_BF16) ? a->accumulate : 0;
   kp.out = a->out; kp.ldc = a->ldc; kp.bias = a->bias; kp.col_sum = a->col_sum; kp.col_sumsq = a->col_sumsq;
   kp.head = a->head;
 

@@ -37,6 +37,7 @@ struct alignas(64) GemmKernelParams {
   int a_mn, b_mn;
   int num_m, num_n, splits, num_kb, kb_per_split;
   int seg_len, seg_valid;
+  int accumulate;
   void* out;
   long long ldc;
   const float* bias;
@@ -287,6 +288,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldc + nc0;
             if (full_chunk) {
               uint32_t pk[16];
+              if (p.accumulate) {      // gradient fan-in: add the tile already in memory (tiles are exclusive)
+                const uint4* o4 = reinterpret_cast<const uint4*>(dst);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 o = o4[j];
+                  const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                    v[8 * j + 2 * k] += f.x;
+                    v[8 * j + 2 * k + 1] += f.y;
+                  }
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float lo = v[2 * j], hi = v[2 * j + 1];
@@ -299,7 +314,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (nc0 + j < p.N) dst[j] = __float2bfloat16(v[j] + (p.bias ? __ldg(p.bias + nc0 + j) : 0.f));
+                if (nc0 + j < p.N)
+                  dst[j] = __float2bfloat16(v[j] + (p.bias ? __ldg(p.bias + nc0 + j) : 0.f) +
+                                            (p.accumulate ? __bfloat162float(dst[j]) : 0.f));
             }
           }
           if (do_stats) {

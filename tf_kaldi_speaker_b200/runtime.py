@@ -440,10 +440,12 @@ class Engine(object):
                           splits=self.splits_for(K, cout_pad, R))
                 if x.needs_grad:
                     # dgrad: dX[q, c] = sum_j dY[q-j, :] W_j[c, :]^T
-                    dx = self.buf(x.name + "/grad", (R, x.ld), torch.bfloat16)
+                    # a shared activation (e.g. tdnn4_relu feeding tdnn5 and the attention key net) gets the sum
+                    fan_in = x.grad is not None
+                    dx = x.grad if fan_in else self.buf(x.name + "/grad", (R, x.ld), torch.bfloat16)
                     self.gemm(L.operand(dy, False, div=(cout_pad if k > 1 else 0), tap_rows=(-1 if k > 1 else 0)),
                               L.operand(W, False, div=(cout_pad if k > 1 else 0), tap_rows=(x.ld if k > 1 else 0)),
-                              R, x.ld, k * cout_pad, dx, epilogue=L.EPI_BF16)
+                              R, x.ld, k * cout_pad, dx, epilogue=L.EPI_BF16, accumulate=fan_in)
                     x.grad = dx
             self.tape.append(bwd)
             aa.needs_grad = True
