@@ -90,8 +90,8 @@ typedef struct {
   const int32_t* labels; /* [M]                                                                     */
   const float* xnorm;    /* [M] max(||x_i||, 1e-12)                                                 */
   /* forward outputs */
-  float* part_max;       /* [num_n_blocks, M]                                                       */
-  float* part_sum;       /* [num_n_blocks, M]                                                       */
+  float* part_max;       /* [2*ceil(N/256), M]: online-LSE running max per 128-column half tile      */
+  float* part_sum;       /* [2*ceil(N/256), M]: matching sum of exp(z - part_max)                   */
   float* target_logit;   /* [M] modified target logit z'_{i,y_i}                                    */
   float* logits_out;     /* optional [M, ldc] f32 pre-margin logits (endpoints["logits"]); may be 0 */
   /* backward inputs / outputs */
@@ -172,6 +172,43 @@ XV_API int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int B, 
                              const float* shift, const float* alpha, int act, void* stream);
 XV_API int xv_stats_pool_bwd(const void* x, const float* pooled, const float* dpooled, void* dx, int B, int seg_len,
                              int seg_valid, const int32_t* lengths, int c_real, int cpad, int64_t ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * self_attention pooling (model/pooling.py:37-192).  The key / value nets are frame layers (xv_gemm_bf16 +
+ * xv_bn_act_*); these entries replace the einsum / softmax / weighted-moment / penalty ops of pooling.py:147-189
+ * and the gradients TF autodiff derives for them.  key / value: bf16 flat-time [B*seg_len, ld]; scores, weights,
+ * dweights: f32 [B, H, seg_len]; frames t >= lengths[b] (or seg_valid) get weight 0.
+ * qpad f32 [H, ldk] is the query expanded to the key's padded width: qpad[h, d] = query[h, d] (att_split_key false)
+ * or qpad[h, h*dq + d] = query[h, d] and 0 elsewhere (att_split_key true, pooling.py:150-153), so that
+ * scores[b,h,t] = scale * <key[b,t,:], qpad[h,:]>  (scale = rsqrt(dq) when att_use_scale, pooling.py:155-156).
+ * ------------------------------------------------------------------------------------------ */
+XV_API int xv_att_expand_query(const float* query, float* qpad, int H, int dq, int ldk, int split_key, void* stream);
+XV_API int xv_att_fold_query_grad(const float* dqpad, float* dquery, int H, int dq, int ldk, int split_key, void* stream);
+XV_API int xv_att_scores_fwd(const void* key, const float* qpad, float* scores, int B, int seg_len, int seg_valid,
+                             const int32_t* lengths, int H, int ldk, float scale, void* stream);
+/* weights = softmax over the valid frames (pooling.py:159); may run in place. */
+XV_API int xv_att_softmax_fwd(const float* scores, float* weights, int B, int H, int seg_len, int seg_valid,
+                              const int32_t* lengths, void* stream);
+/* out f32 [B, 2*cpad] = [weighted mean | sqrt(max(weighted var, 1e-12))] (pooling.py:162-170); head h owns channels
+ * [h*c_real/H, (h+1)*c_real/H) (split_heads, model/common.py:239-249); out_split as in xv_stats_pool_fwd. */
+XV_API int xv_att_pool_fwd(const void* value, const float* weights, float* out, void* out_split, int B, int H,
+                           int seg_len, int seg_valid, const int32_t* lengths, int c_real, int cpad, int64_t ld,
+                           void* stream);
+/* dvalue bf16 [B*seg_len, ld] (= or += when accumulate) and dweights f32 [B, H, seg_len] from dpooled. */
+XV_API int xv_att_pool_bwd(const void* value, const float* weights, const float* pooled, const float* dpooled,
+                           void* dvalue, float* dweights, int B, int H, int seg_len, int seg_valid,
+                           const int32_t* lengths, int c_real, int cpad, int64_t ld, int accumulate, void* stream);
+/* penalty[0] += coef/B * sum_b ||W_b W_b^T - I||_F^2 (pooling.py:185-188); gram f32 [B, H, H] = W W^T - I. */
+XV_API int xv_att_penalty_fwd(const float* weights, float* gram, float* penalty, int B, int H, int seg_len,
+                              int seg_valid, const int32_t* lengths, float coef, void* stream);
+/* dweights (in) -> dscores (out, in place): adds the penalty gradient 4 coef/B (gram W) when gram != NULL, applies the
+ * softmax Jacobian and the score scale. */
+XV_API int xv_att_softmax_bwd(const float* weights, float* dweights, const float* gram, int B, int H, int seg_len,
+                              int seg_valid, const int32_t* lengths, float penalty_coef, float scale, void* stream);
+/* dkey bf16 [B*seg_len, ldk] (= or +=) = sum_h dscores[b,h,t] qpad[h,:];  dqpad f32 [H, ldk] += sum_m dscores * key. */
+XV_API int xv_att_scores_bwd(const void* key, const float* qpad, const float* dscores, void* dkey, float* dqpad, int B,
+                             int seg_len, int seg_valid, const int32_t* lengths, int H, int ldk, int accumulate,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Utterance-level layers (tdnn6/tdnn7 BN + activation on f32 [B, C], model/tdnn.py:147-189).

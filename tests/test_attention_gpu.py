@@ -1,0 +1,259 @@
+"""GPU parity of the self-attention pooling kernels (csrc/xv_attention.cu) through the C ABI:
+  * forward against the committed golden vectors generated from the reference's NumPy known-answer code
+    (model/test_utils.py:321-376 -> tests/golden/attention.npz);
+  * forward + backward against fp64 autograd of the oracle's self_attention on the SAME bf16 inputs (multi-head with
+    heads straddling 8-channel vectors, split / shared keys, ragged lengths, penalty term);
+  * one full training step of the shipped attention configuration (nnet_conf/..._tdnn4_att.json shape, scaled down)
+    against the fp64 oracle: loss rel <= 1e-3, embedding cosine >= 0.999."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xvector_oracle as O
+from tests.xv_testlib import base_params, head_params, make_batch, rel_fro, min_cosine
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad(n, m):
+    return (n + m - 1) // m * m
+
+
+def _run_kernels(key, value, query, H, split, use_scale, coef, lengths=None, dpooled=None):
+    """key f32 [B,T,dk], value f32 [B,T,dv] (already bf16-representable), query f32 [H,dq] -> dict of torch results."""
+    from tf_kaldi_speaker_b200 import _lib as L
+    lib = L.load()
+    dev = "cuda"
+    B, T, dk = key.shape
+    dv = value.shape[2]
+    ldk, cpad = _pad(dk, 64), _pad(dv, 64)
+    kd = torch.zeros(B * T, ldk, dtype=torch.bfloat16, device=dev)
+    vd = torch.zeros(B * T, cpad, dtype=torch.bfloat16, device=dev)
+    kd[:, :dk] = key.reshape(B * T, dk).to(dev).to(torch.bfloat16)
+    vd[:, :dv] = value.reshape(B * T, dv).to(dev).to(torch.bfloat16)
+    q = query.to(dev).float().contiguous()
+    dq = q.shape[1]
+    scale = 1.0 / math.sqrt(dq) if use_scale else 1.0
+    ln = None if lengths is None else lengths.to(dev).to(torch.int32)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    qpad = torch.empty(H, ldk, device=dev)
+    L.check(lib.xv_att_expand_query(L.ptr(q), L.ptr(qpad), H, dq, ldk, int(split), s))
+    w = torch.full((B, H, T), float("nan"), device=dev)
+    L.check(lib.xv_att_scores_fwd(L.ptr(kd), L.ptr(qpad), L.ptr(w), B, T, T, L.ptr(ln), H, ldk, C.c_float(scale), s))
+    L.check(lib.xv_att_softmax_fwd(L.ptr(w), L.ptr(w), B, H, T, T, L.ptr(ln), s))
+    out = torch.empty(B, 2 * cpad, device=dev)
+    out3 = torch.empty(B, 6 * cpad, dtype=torch.bfloat16, device=dev)
+    L.check(lib.xv_att_pool_fwd(L.ptr(vd), L.ptr(w), L.ptr(out), L.ptr(out3), B, H, T, T, L.ptr(ln), dv, cpad,
+                                C.c_int64(cpad), s))
+    pen = torch.zeros(1, device=dev)
+    gram = torch.empty(B, H, H, device=dev)
+    L.check(lib.xv_att_penalty_fwd(L.ptr(w), L.ptr(gram), L.ptr(pen), B, H, T, T, L.ptr(ln), C.c_float(coef), s))
+    res = {"weights": w.clone(), "att": torch.cat([out[:, :dv], out[:, cpad:cpad + dv]], 1), "penalty": pen.clone(),
+           "out3": out3, "out": out, "cpad": cpad}
+    if dpooled is not None:
+        dp = torch.zeros(B, 2 * cpad, device=dev)
+        dp[:, :dv] = dpooled[:, :dv].to(dev)
+        dp[:, cpad:cpad + dv] = dpooled[:, dv:].to(dev)
+        dvd = torch.full((B * T, cpad), float("nan"), dtype=torch.bfloat16, device=dev)
+        dw = torch.empty(B, H, T, device=dev)
+        L.check(lib.xv_att_pool_bwd(L.ptr(vd), L.ptr(w), L.ptr(out), L.ptr(dp), L.ptr(dvd), L.ptr(dw), B, H, T, T,
+                                    L.ptr(ln), dv, cpad, C.c_int64(cpad), 0, s))
+        L.check(lib.xv_att_softmax_bwd(L.ptr(w), L.ptr(dw), L.ptr(gram if coef != 0 else None), B, H, T, T, L.ptr(ln),
+                                       C.c_float(coef), C.c_float(scale), s))
+        dkd = torch.full((B * T, ldk), float("nan"), dtype=torch.bfloat16, device=dev)
+        dqpad = torch.zeros(H, ldk, device=dev)
+        L.check(lib.xv_att_scores_bwd(L.ptr(kd), L.ptr(qpad), L.ptr(dw), L.ptr(dkd), L.ptr(dqpad), B, T, T, L.ptr(ln), H,
+                                      ldk, 0, s))
+        dqv = torch.zeros(H, dq, device=dev)
+        L.check(lib.xv_att_fold_query_grad(L.ptr(dqpad), L.ptr(dqv), H, dq, ldk, int(split), s))
+        # accumulate mode: a second pass on top of the first must double the gradient
+        dvd2 = dvd.clone()
+        dw2 = torch.empty(B, H, T, device=dev)
+        L.check(lib.xv_att_pool_bwd(L.ptr(vd), L.ptr(w), L.ptr(out), L.ptr(dp), L.ptr(dvd2), L.ptr(dw2), B, H, T, T,
+                                    L.ptr(ln), dv, cpad, C.c_int64(cpad), 1, s))
+        torch.cuda.synchronize()
+        res.update(dvalue=dvd.float().reshape(B, T, cpad)[:, :, :dv], dkey=dkd.float().reshape(B, T, ldk)[:, :, :dk],
+                   dquery=dqv, dvalue_pad=dvd.float().reshape(B, T, cpad)[:, :, dv:],
+                   dkey_pad=dkd.float().reshape(B, T, ldk)[:, :, dk:], dvalue2=dvd2.float().reshape(B, T, cpad)[:, :, :dv])
+    torch.cuda.synchronize()
+    return res
+
+
+def _oracle(key, value, query, H, split, use_scale, coef, lengths=None):
+    p = O.ParamsPlain(att_value_input="v", att_key_input="k", att_key_num_nodes=[], att_value_num_nodes=[],
+                      att_key_network_type=0, att_value_network_type=0, att_num_heads=H, att_split_key=bool(split),
+                      att_use_scale=bool(use_scale), att_penalty_term=coef, batchnorm_momentum=0.99)
+    ep = {"v": value, "k": key}
+    att, pen = O.self_attention(ep, {"tdnn/attention/query": query}, p, True, None, lengths)
+    return att, pen, ep["attention_weights"]
+
+
+def test_attention_forward_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "attention.npz"))
+    for tag in ("h4_split", "h1_shared", "h2_shared_noscale"):
+        heads, split, scale = [int(v) for v in g[tag + "/cfg"]]
+        # the kernels read bf16 activations: round the fixture inputs and evaluate the oracle on the rounded values too
+        value = torch.from_numpy(g[tag + "/value"]).to(torch.bfloat16).float()
+        key = torch.from_numpy(g[tag + "/key"]).to(torch.bfloat16).float()
+        query = torch.from_numpy(g[tag + "/query"])
+        r = _run_kernels(key, value, query, heads, split, scale, 0.5)
+        att_o, pen_o, w_o = _oracle(key.double(), value.double(), query.double(), heads, split, scale, 0.5)
+        dv = value.shape[2]
+        att = r["att"].cpu().double()
+        assert torch.allclose(r["weights"].cpu().double(), w_o, rtol=2e-5, atol=1e-7), tag
+        assert torch.allclose(att[:, :dv], att_o[:, :dv], rtol=1e-5, atol=1e-6), tag
+        # rows with (near-)constant values sit on the 1e-12 variance floor where fp32 cancellation decides: atol 2e-5
+        assert torch.allclose(att[:, dv:], att_o[:, dv:], rtol=2e-4, atol=2e-5), tag
+        assert abs(r["penalty"].item() - pen_o.item()) <= 1e-5 * abs(pen_o.item()), tag
+        # and against the reference's own NumPy output (fixture inputs differ only by the bf16 rounding of the inputs)
+        ref = torch.from_numpy(g[tag + "/att"])
+        rows = [4, 5]          # rows 0-3 are the adversarial scales (1e-8, 0, 100x, const) where bf16 input rounding dominates
+        assert torch.allclose(att[rows, :dv], ref[rows, :dv], rtol=1e-2, atol=1e-2), tag
+
+
+CASES = [
+    # B, T, dk, dv, H, split, scale, coef, ragged
+    (3, 37, 1500, 1500, 1, False, True, 0.0, False),      # shipped configuration (H=1, shared key)
+    (3, 37, 1500, 1500, 4, True, True, 0.5, False),       # 375 channels per head: vectors straddle heads
+    (4, 50, 512, 1536, 8, False, False, 0.1, True),       # shared key, 8 heads, ragged lengths
+    (2, 300, 64, 128, 16, True, True, 0.01, True),        # max heads, long segments
+]
+
+
+@pytest.mark.parametrize("B,T,dk,dv,H,split,scale,coef,ragged", CASES)
+def test_attention_forward_backward(B, T, dk, dv, H, split, scale, coef, ragged):
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    key = torch.tanh(torch.randn(B, T, dk, generator=g)).to(torch.bfloat16).float()
+    value = (torch.relu(torch.randn(B, T, dv, generator=g)) + 0.1 * torch.randn(B, 1, dv, generator=g)).to(torch.bfloat16).float()
+    dq = dk // H if split else dk
+    query = (torch.randn(H, dq, generator=g) * 0.3).float()
+    lengths = None
+    if ragged:
+        lengths = torch.randint(5, T + 1, (B,), generator=g)
+        lengths[0] = T
+    dpooled = torch.randn(B, 2 * dv, generator=g)
+    r = _run_kernels(key, value, query, H, split, scale, coef, lengths, dpooled)
+
+    k64 = key.double().requires_grad_(True)
+    v64 = value.double().requires_grad_(True)
+    q64 = query.double().requires_grad_(True)
+    att_o, pen_o, w_o = _oracle(k64, v64, q64, H, split, scale, coef, lengths)
+    total = (att_o * dpooled.double()).sum() + pen_o
+    gk, gv, gq = torch.autograd.grad(total, [k64, v64, q64])
+
+    assert torch.allclose(r["weights"].cpu().double(), w_o.detach(), rtol=1e-4, atol=1e-7)
+    assert rel_fro(r["att"].cpu(), att_o.detach()) <= 1e-5
+    assert abs(r["penalty"].item() - pen_o.item()) <= 1e-4 * max(abs(pen_o.item()), 1e-6)
+    # gradients are emitted as bf16 (frame-level) / fp32 (query)
+    assert rel_fro(r["dvalue"].cpu(), gv) <= 4e-3, rel_fro(r["dvalue"].cpu(), gv)
+    assert rel_fro(r["dkey"].cpu(), gk) <= 4e-3, rel_fro(r["dkey"].cpu(), gk)
+    assert rel_fro(r["dquery"].cpu(), gq) <= 1e-4, rel_fro(r["dquery"].cpu(), gq)
+    assert float(r["dvalue_pad"].abs().max()) == 0.0 if r["dvalue_pad"].numel() else True
+    assert float(r["dkey_pad"].abs().max()) == 0.0 if r["dkey_pad"].numel() else True
+    assert rel_fro(r["dvalue2"].cpu(), 2 * gv) <= 8e-3
+    if lengths is not None:     # frames beyond the length: zero weight, zero gradient
+        for b in range(B):
+            n = int(lengths[b])
+            assert float(r["weights"][b, :, n:].abs().max() if n < T else 0.0) == 0.0
+            assert float(r["dvalue"][b, n:].abs().max() if n < T else 0.0) == 0.0
+            assert float(r["dkey"][b, n:].abs().max() if n < T else 0.0) == 0.0
+
+
+ATT_CASES = [
+    ("tdnn4_att_h1", dict(att_key_input="tdnn4_relu", att_key_num_nodes=[96, 96], att_key_network_type=3,
+                          att_value_input="tdnn5_relu", att_value_num_nodes=[], att_value_network_type=0,
+                          att_apply_nonlinear=False, att_use_scale=True, att_num_heads=1, att_split_key=False,
+                          att_penalty_term=0.0)),
+    ("multihead_split_penalty_postbn", dict(att_key_input="tdnn4_relu", att_key_num_nodes=[128], att_key_network_type=2,
+                                            att_value_input="tdnn5_relu", att_value_num_nodes=[120],
+                                            att_value_network_type=1, att_apply_nonlinear=True, att_use_scale=False,
+                                            att_num_heads=4, att_split_key=True, att_penalty_term=0.05)),
+]
+
+
+@pytest.mark.parametrize("name,att", ATT_CASES, ids=[c[0] for c in ATT_CASES])
+def test_attention_train_step(name, att):
+    from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
+    from tf_kaldi_speaker_b200.model.trainer import Trainer
+    loss_type = "additive_margin_softmax"
+    B, T, D, Cn = 12, 60, 30, 200
+    pd = base_params(**head_params(loss_type))
+    pd.update(att)
+    pd.update(pooling_type="self_attention", feature_norm=True, feature_scaling_factor=30, num_nodes_pooling_layer=200)
+    x, y = make_batch(B, T, D, Cn, seed=2)
+    po = O.ParamsPlain(**dict(pd))
+    P = O.init_params(D, po, Cn, loss_type, seed=4)
+    gen = torch.Generator().manual_seed(6)
+    for k in P:
+        if k.endswith("/gamma"):
+            P[k] = P[k] + 0.2 * torch.randn(P[k].shape, generator=gen, dtype=torch.float64)
+        elif k.endswith("/beta") or k.endswith("/bias"):
+            P[k] = P[k] + 0.1 * torch.randn(P[k].shape, generator=gen, dtype=torch.float64)
+    P["tdnn/attention/query"] = P["tdnn/attention/query"] * 3.0       # make the weights visibly non-uniform
+    gstep, lr = 300000, 0.01
+    loss_o, total_o, _, newP_o, _, ep_o = O.train_step(P, {}, x.double(), y, po, loss_type, lr, gstep)
+    grads_o = ep_o["__raw_grads"]
+
+    tr = Trainer(ParamsPlain(**dict(pd)), "/tmp/xv_test_model_att")
+    tr.build("train", D, loss_type, Cn)
+    st = tr.engine.store
+    assert set(st.specs.keys()) == set(P.keys()), set(st.specs.keys()) ^ set(P.keys())
+    st.load_tf({k: v.numpy() for k, v in P.items()})
+    res = tr.train_step(x, y, lr, gstep, fetch_loss=True)
+    torch.cuda.synchronize()
+    loss_rel = abs(res["raw_loss"] - loss_o.item()) / abs(loss_o.item())
+    total_rel = abs(res["loss"] - total_o.item()) / abs(total_o.item())
+    emb = tr.endpoints["tdnn6_dense"].dense().cpu().numpy()
+    cos = min_cosine(emb, ep_o["tdnn6_dense"].detach().numpy())
+    w_cuda = tr.endpoints["attention_weights"].cpu().double()
+    w_err = float((w_cuda - ep_o["attention_weights"].detach()).abs().max())
+    print(name, "loss_rel %.2e total_rel %.2e emb_cos %.6f weights max abs err %.2e" % (loss_rel, total_rel, cos, w_err))
+    assert loss_rel <= 1e-3 and total_rel <= 1e-3
+    assert cos >= 0.999
+    assert w_err <= 5e-3      # bf16 keys: score noise ~1e-2 on peaked weights
+    ge = st.export_tf(grads=True)
+    s = float(pd["weight_l2_regularizer"])
+    worst = {}
+    for n, go in grads_o.items():
+        gv = ge[n].astype(np.float64)
+        if O.l2_regularised(n):
+            gv = gv + s * P[n].numpy()
+        if np.linalg.norm(go.numpy()) < 1e-9:
+            assert float(np.abs(gv).max()) <= 1e-3, n
+            continue
+        worst[n] = rel_fro(gv, go.numpy())
+        c = float(np.dot(gv.ravel(), go.numpy().ravel()) / (np.linalg.norm(gv) * np.linalg.norm(go.numpy()) + 1e-300))
+        assert worst[n] <= 0.30 and c >= 0.95, (n, worst[n], c)
+    print("  worst grads vs fp64:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    # the graphed replay must reproduce the eager step on the updated parameters (static shapes, fan-in accumulate)
+    newv = st.export_tf()
+    for n in ("tdnn/attention/query", "tdnn/tdnn4_dense/kernel"):
+        assert rel_fro(newv[n], newP_o[n].numpy()) <= 5e-2, n
+
+
+def test_attention_predict_ragged_matches_single():
+    """Batched variable-length extraction with attention pooling == one call per utterance (masked softmax)."""
+    from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
+    from tf_kaldi_speaker_b200.model.trainer import Trainer
+    pd = base_params()
+    pd.update(ATT_CASES[0][1])
+    pd.update(pooling_type="self_attention", num_nodes_pooling_layer=200)
+    D = 24
+    tr = Trainer(ParamsPlain(**dict(pd)), "/tmp/xv_test_model_att2")
+    tr.build("predict", D)
+    g = torch.Generator().manual_seed(9)
+    lens = [90, 40, 64]
+    feats = np.zeros((3, 90, D), dtype=np.float32)
+    singles = []
+    for i, n in enumerate(lens):
+        f = torch.randn(n, D, generator=g).numpy()
+        feats[i, :n] = f
+        singles.append(tr.predict(f))
+    batched = tr.predict_batch_padded(feats, lens)
+    for i in range(3):
+        c = float(np.dot(batched[i], singles[i]) / (np.linalg.norm(batched[i]) * np.linalg.norm(singles[i])))
+        assert c >= 0.9999, (i, c)

@@ -35,6 +35,22 @@ static int make_tmap(CUtensorMap* map, const xv_operand& op, int box_rows_kmajor
   return XV_OK;
 }
 
+// Output tensor map for the epilogue's TMA stores: box = 32 rows x 128 bytes (64 bf16 or 32 f32 columns), 128B swizzle.
+static int make_out_tmap(CUtensorMap* map, void* out, int M, int N, long long ldc, bool f32) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(XV_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  const int esz = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(XV_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (CUresult %d)", static_cast<int>(r));
+  return XV_OK;
+}
+
 }  // namespace xv
 
 extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
@@ -77,6 +93,18 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   kp.accumulate = (a->epilogue == XV_EPI_BF16) ? a->accumulate : 0;
   kp.out = a->out; kp.ldc = a->ldc; kp.bias = a->bias; kp.col_sum = a->col_sum; kp.col_sumsq = a->col_sumsq;
   kp.head = a->head;
+  // Matrix outputs leave through TMA stores (split-K partials through the TMA reduce-add unit) whenever the layout
+  // allows a tensor map; the gradient fan-in mode (read-modify-write of bf16) keeps the direct path.
+  kp.use_tma_out = 0;
+  if (a->epilogue != XV_EPI_HEAD_FWD && !(a->epilogue == XV_EPI_BF16 && a->accumulate)) {
+    const bool f32 = a->epilogue == XV_EPI_F32;
+    const bool aligned = (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->ldc * (f32 ? 4 : 2)) % 16 == 0 && a->ldc >= a->N;
+    if (aligned) {
+      rc = make_out_tmap(&kp.tma_out, a->out, a->M, a->N, a->ldc, f32);
+      if (rc) return rc;
+      kp.use_tma_out = 1;
+    }
+  }
 
   int sms = 0;
   rc = device_sm_count(&sms);

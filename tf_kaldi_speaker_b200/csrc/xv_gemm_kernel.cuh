@@ -1,8 +1,9 @@
 // Persistent, warp-specialised implicit-GEMM for sm_100a:
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM,
-//   128 x 256 tile, double-buffered accumulator = all 512 TMEM columns) -> tcgen05.ld epilogue.
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
-// allocator, warp 3 idle, warps 4..7 = epilogue (TMEM lane quadrant = warp_idx % 4).
+//   128 x 256 tile, double-buffered accumulator = all 512 TMEM columns) -> tcgen05.ld epilogue -> swizzled smem
+//   staging -> TMA store (bf16 / f32) or TMA reduce-add (f32 split-K).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
+// allocator, warp 3 idle, warps 4..11 = epilogue (TMEM lane quadrant = warp_idx % 4, column half = (warp_idx-4)/4).
 //
 // One kernel serves every contraction of the x-vector step (see include/xvector_b200.h):
 //   forward  conv/dense : A = activations (K-major, tap rows +j), B = kernel [k*Cin, Cout] (MN-major)
@@ -25,13 +26,21 @@ constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int CHUNK_BYTES = 64 * BLOCK_K * 2;          // one MN-major 64x64 box = 8 KB
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 256;
-constexpr int STATS_BYTES = 4 * 2 * BLOCK_N * 4;       // [epilogue warp][sum|sumsq][col]
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STATS_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr int NUM_THREADS = 384;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_COLS = BLOCK_N / 2;                  // columns per epilogue warp (column half)
+constexpr int STAGING_BYTES = 32 * 128;                // per epilogue warp: one 32-row x 128-byte TMA store box
+constexpr int STATS_BYTES = 2 * BLOCK_N * 4;           // [sum|sumsq][col], accumulated with shared-memory atomics
+constexpr int BAR_BYTES = 256;
+// The dynamic shared-memory window is declared 1024-byte aligned (128B-swizzle atom); no slack is reserved.
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + STATS_BYTES + BAR_BYTES;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 struct alignas(64) GemmKernelParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
+  CUtensorMap tma_out;    // output matrix (box 32 rows x 128 bytes, 128B swizzle); valid when use_tma_out
+  int use_tma_out;
   int M, N, K;
   int a_div, a_tap, b_div, b_tap;
   int a_mn, b_mn;
@@ -107,15 +116,22 @@ __device__ __forceinline__ MarginOut margin_target(const xv_head_args& h, float 
   return o;
 }
 
+// 128B-swizzled staging tile of one epilogue warp (32 rows x 128 bytes): logical 16-byte chunk j of row r lives at
+// chunk position j ^ (r & 7) -- the layout CU_TENSOR_MAP_SWIZZLE_128B expects, and conflict-free for a warp
+// whose lanes each write 16 bytes of their own row.
+__device__ __forceinline__ void stage_store16(uint8_t* stg, int row, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmKernelParams p) {
   const bool A_MN = p.a_mn != 0, B_MN = p.b_mn != 0;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STATS_BYTES);
+  uint8_t* smem_stg = smem + STAGES * STAGE_BYTES;
+  float* s_stats = reinterpret_cast<float*>(smem_stg + NUM_EPI_WARPS * STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_stats) + STATS_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
@@ -125,9 +141,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("xv: dynamic shared memory base is not 1024-byte aligned (0x%x)\n", smem_u32(smem));
+    __trap();
+  }
   if (warp_idx == 0 && lane == 0) {
     prefetch_tmap(&p.tma_a);
     prefetch_tmap(&p.tma_b);
+    if (p.use_tma_out) prefetch_tmap(&p.tma_out);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -136,7 +157,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -144,6 +165,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     tmem_alloc(tmem_ptr, TMEM_COLS);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += NUM_THREADS) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -163,33 +185,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        // Tile coordinates are walked incrementally: the only integer divisions happen here, once per tile
+        // (a division per k-block made this single thread slower than the MMAs it feeds).
+        int a_col, a_row, b_col, b_row;
+        if (!A_MN) {
+          const int kk = kb0 * BLOCK_K;
+          a_col = p.a_div ? (kk % p.a_div) : kk;
+          a_row = m0 + (p.a_div ? (kk / p.a_div) * p.a_tap : 0);
+        } else {
+          a_col = p.a_div ? (m0 % p.a_div) : m0;
+          a_row = kb0 * BLOCK_K + (p.a_div ? (m0 / p.a_div) * p.a_tap : 0);
+        }
+        if (!B_MN) {
+          const int kk = kb0 * BLOCK_K;
+          b_col = p.b_div ? (kk % p.b_div) : kk;
+          b_row = n0 + (p.b_div ? (kk / p.b_div) * p.b_tap : 0);
+        } else {
+          b_col = p.b_div ? (n0 % p.b_div) : n0;
+          b_row = kb0 * BLOCK_K + (p.b_div ? (n0 / p.b_div) * p.b_tap : 0);
+        }
+        const int a_wrap = (!A_MN && p.a_div) ? p.a_div : 0x7fffffff;
+        const int b_wrap = (!B_MN && p.b_div) ? p.b_div : 0x7fffffff;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int kk = kb * BLOCK_K;
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
           if (!A_MN) {
-            const int col = p.a_div ? (kk % p.a_div) : kk;
-            const int row = m0 + (p.a_div ? (kk / p.a_div) * p.a_tap : 0);
-            tma_load_2d(sa, &p.tma_a, &full_bar[stage], col, row);
+            tma_load_2d(sa, &p.tma_a, &full_bar[stage], a_col, a_row);
+            a_col += BLOCK_K;
+            if (a_col >= a_wrap) { a_col = 0; a_row += p.a_tap; }
           } else {
-            const int col = p.a_div ? (m0 % p.a_div) : m0;
-            const int row = kk + (p.a_div ? (m0 / p.a_div) * p.a_tap : 0);
 #pragma unroll
             for (int c = 0; c < BLOCK_M / 64; ++c)
-              tma_load_2d(sa + c * CHUNK_BYTES, &p.tma_a, &full_bar[stage], col + 64 * c, row);
+              tma_load_2d(sa + c * CHUNK_BYTES, &p.tma_a, &full_bar[stage], a_col + 64 * c, a_row);
+            a_row += BLOCK_K;
           }
           if (!B_MN) {
-            const int col = p.b_div ? (kk % p.b_div) : kk;
-            const int row = n0 + (p.b_div ? (kk / p.b_div) * p.b_tap : 0);
-            tma_load_2d(sb, &p.tma_b, &full_bar[stage], col, row);
+            tma_load_2d(sb, &p.tma_b, &full_bar[stage], b_col, b_row);
+            b_col += BLOCK_K;
+            if (b_col >= b_wrap) { b_col = 0; b_row += p.b_tap; }
           } else {
-            const int col = p.b_div ? (n0 % p.b_div) : n0;
-            const int row = kk + (p.b_div ? (n0 / p.b_div) * p.b_tap : 0);
 #pragma unroll
             for (int c = 0; c < BLOCK_N / 64; ++c)
-              tma_load_2d(sb + c * CHUNK_BYTES, &p.tma_b, &full_bar[stage], col + 64 * c, row);
+              tma_load_2d(sb + c * CHUNK_BYTES, &p.tma_b, &full_bar[stage], b_col + 64 * c, b_row);
+            b_row += BLOCK_K;
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -204,6 +244,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       const uint32_t a_lbo = A_MN ? CHUNK_BYTES : 16, b_lbo = B_MN ? CHUNK_BYTES : 16;
       const uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per UMMA_K
       const uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      // descriptors of stage 0 / k = 0; the start-address field (bits 0..13, 16-byte units) is advanced by adds
+      const uint64_t da0 = make_smem_desc(smem_u32(smem_a), a_lbo, 1024);
+      const uint64_t db0 = make_smem_desc(smem_u32(smem_b), b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -219,14 +262,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+          const uint64_t da = da0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
+          const uint64_t db = db0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024);
-            const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(d_tmem, da + static_cast<uint64_t>((k * a_kstep) >> 4), db + static_cast<uint64_t>((k * b_kstep) >> 4),
+                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -235,8 +276,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
   } else if (warp_idx >= 4) {
     // ============================== epilogue ==============================
-    const int ew = warp_idx - 4;            // == warp_idx % 4 == TMEM lane quadrant
-    const int et = threadIdx.x - 128;       // 0..127
+    const int e = warp_idx - 4;             // 0..7
+    const int qd = warp_idx & 3;            // TMEM lane quadrant this warp may read
+    const int hf = e >> 2;                  // column half of the tile
+    const int et = threadIdx.x - 128;       // 0..255
+    uint8_t* stg = smem_stg + e * STAGING_BYTES;
+    const bool tma_out = p.use_tma_out != 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int n_blk = tile % p.num_n;
@@ -245,11 +290,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int m = m0 + ew * 32 + lane;
+      const int row0 = m0 + qd * 32;
+      const int m = row0 + lane;
       const bool row_ok = m < p.M;
+      const int cbase = n0 + hf * EPI_COLS;                       // first global column of this warp
+      const int ncols = max(0, min(EPI_COLS, p.N - cbase));
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * BLOCK_N + hf * EPI_COLS;
 
       const bool do_stats = (EPI == XV_EPI_BF16 || EPI == XV_EPI_HEAD_BWD) && p.col_sum != nullptr;
       bool row_valid = row_ok;
@@ -267,27 +315,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
         }
       }
 
-      const int ncols = min(BLOCK_N, p.N - n0);
       for (int c = 0; c * 32 < ncols; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);
         tmem_ld_wait();
-        const int nc0 = n0 + c * 32;
+        const int nc0 = cbase + c * 32;
         const bool full_chunk = (nc0 + 32 <= p.N);
+        const bool last_chunk = (c + 1) * 32 >= ncols;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 
         if (EPI == XV_EPI_BF16) {
-          float q[32];
           if (do_stats) {
+            float s[32], q[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) q[j] = row_valid ? v[j] : 0.f;
+            for (int j = 0; j < 32; ++j) { s[j] = row_valid ? v[j] : 0.f; q[j] = s[j] * s[j]; }
+            warp_column_sums(s, lane);
+            warp_column_sums(q, lane);
+            atomicAdd(&s_stats[hf * EPI_COLS + c * 32 + lane], s[0]);
+            atomicAdd(&s_stats[BLOCK_N + hf * EPI_COLS + c * 32 + lane], q[0]);
           }
-          if (row_ok) {
+          if (p.bias) {
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc0) + j);
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += (nc0 + j < p.N) ? __ldg(p.bias + nc0 + j) : 0.f;
+            }
+          }
+          if (tma_out) {
+            // two 32-column chunks fill one 64-column (128-byte) store box; columns >= N are clipped by the TMA unit
+            const int cc = c & 1;
+            if (cc == 0) {
+              if (lane == 0) bulk_wait_read_all();      // the previous box has left the staging tile
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              stage_store16(stg, lane, cc * 4 + j,
+                            make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
+            if (cc == 1 || last_chunk) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&p.tma_out, stg, nc0 - cc * 32, row0);
+                bulk_commit();
+              }
+            }
+          } else if (row_ok) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldc + nc0;
             if (full_chunk) {
-              uint32_t pk[16];
               if (p.accumulate) {      // gradient fan-in: add the tile already in memory (tiles are exclusive)
                 const uint4* o4 = reinterpret_cast<const uint4*>(dst);
 #pragma unroll
@@ -302,68 +385,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
                   }
                 }
               }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float lo = v[2 * j], hi = v[2 * j + 1];
-                if (p.bias) { lo += __ldg(p.bias + nc0 + 2 * j); hi += __ldg(p.bias + nc0 + 2 * j + 1); }
-                pk[j] = pack_bf16x2(lo, hi);
-              }
               uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              for (int j = 0; j < 4; ++j)
+                d4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (nc0 + j < p.N)
-                  dst[j] = __float2bfloat16(v[j] + (p.bias ? __ldg(p.bias + nc0 + j) : 0.f) +
-                                            (p.accumulate ? __bfloat162float(dst[j]) : 0.f));
+                  dst[j] = __float2bfloat16(v[j] + (p.accumulate ? __bfloat162float(dst[j]) : 0.f));
             }
           }
-          if (do_stats) {
-            float s[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { s[j] = q[j]; q[j] = q[j] * q[j]; }
-            warp_column_sums(s, lane);
-            warp_column_sums(q, lane);
-            s_stats[(ew * 2 + 0) * BLOCK_N + c * 32 + lane] = s[0];
-            s_stats[(ew * 2 + 1) * BLOCK_N + c * 32 + lane] = q[0];
-          }
         } else if (EPI == XV_EPI_F32) {
-          if (row_ok) {
+          if (p.bias != nullptr && split == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (nc0 + j < p.N) ? __ldg(p.bias + nc0 + j) : 0.f;
+          }
+          if (tma_out) {
+            // one 32-column f32 chunk = one 128-byte store box; split-K partial tiles are combined by the TMA
+            // reduce-add unit in L2 (no per-thread atomics)
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              stage_store16(stg, lane, j,
+                            make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.splits > 1) tma_reduce_add_2d(&p.tma_out, stg, nc0, row0);
+              else tma_store_2d(&p.tma_out, stg, nc0, row0);
+              bulk_commit();
+            }
+          } else if (row_ok) {
             float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldc + nc0;
-            const bool add_bias = p.bias != nullptr && split == 0;
-            if (p.splits > 1) {
-              if (full_chunk) {      // 16-byte vector reductions: 8 RED instructions per 32 columns instead of 32
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                  if (add_bias) {
-                    o.x += __ldg(p.bias + nc0 + 4 * j); o.y += __ldg(p.bias + nc0 + 4 * j + 1);
-                    o.z += __ldg(p.bias + nc0 + 4 * j + 2); o.w += __ldg(p.bias + nc0 + 4 * j + 3);
-                  }
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(o.x), "f"(o.y),
-                               "f"(o.z), "f"(o.w) : "memory");
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (nc0 + j < p.N) atomicAdd(dst + j, v[j] + (add_bias ? __ldg(p.bias + nc0 + j) : 0.f));
+            for (int j = 0; j < 32; ++j) {
+              if (nc0 + j < p.N) {
+                if (p.splits > 1) atomicAdd(dst + j, v[j]);
+                else dst[j] = v[j];
               }
-            } else if (full_chunk) {
-              float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (add_bias) {
-                  o.x += __ldg(p.bias + nc0 + 4 * j); o.y += __ldg(p.bias + nc0 + 4 * j + 1);
-                  o.z += __ldg(p.bias + nc0 + 4 * j + 2); o.w += __ldg(p.bias + nc0 + 4 * j + 3);
-                }
-                d4[j] = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nc0 + j < p.N) dst[j] = v[j] + (add_bias ? __ldg(p.bias + nc0 + j) : 0.f);
             }
           }
         } else if (EPI == XV_EPI_HEAD_FWD) {
@@ -430,23 +493,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             }
             d[j] = g;
           }
-          if (row_ok) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldc + nc0;
-            if (full_chunk) {
-              uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                d4[j] = make_uint4(pack_bf16x2(d[8 * j], d[8 * j + 1]), pack_bf16x2(d[8 * j + 2], d[8 * j + 3]),
-                                   pack_bf16x2(d[8 * j + 4], d[8 * j + 5]), pack_bf16x2(d[8 * j + 6], d[8 * j + 7]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nc0 + j < p.N) dst[j] = __float2bfloat16(d[j]);
+          if (tma_out) {
+            const int cc = c & 1;
+            if (cc == 0) {
+              if (lane == 0) bulk_wait_read_all();
+              __syncwarp();
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              stage_store16(stg, lane, cc * 4 + j,
+                            make_uint4(pack_bf16x2(d[8 * j], d[8 * j + 1]), pack_bf16x2(d[8 * j + 2], d[8 * j + 3]),
+                                       pack_bf16x2(d[8 * j + 4], d[8 * j + 5]), pack_bf16x2(d[8 * j + 6], d[8 * j + 7])));
+            if (cc == 1 || last_chunk) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&p.tma_out, stg, nc0 - cc * 32, row0);
+                bulk_commit();
+              }
+            }
+          } else if (row_ok) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldc + nc0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc0 + j < p.N) dst[j] = __float2bfloat16(d[j]);
           }
           if (do_stats) {   // bias gradient of the plain softmax head: column sums of dLoss/dlogit
             warp_column_sums(d, lane);
-            s_stats[(ew * 2 + 0) * BLOCK_N + c * 32 + lane] = d[0];
+            atomicAdd(&s_stats[hf * EPI_COLS + c * 32 + lane], d[0]);
           }
         }
       }
@@ -456,24 +530,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
 
       if (EPI == XV_EPI_HEAD_FWD && row_ok) {
-        p.head.part_max[static_cast<long long>(n_blk) * p.M + m] = run_max;
-        p.head.part_sum[static_cast<long long>(n_blk) * p.M + m] = run_sum;
+        p.head.part_max[static_cast<long long>(n_blk * 2 + hf) * p.M + m] = run_max;
+        p.head.part_sum[static_cast<long long>(n_blk * 2 + hf) * p.M + m] = run_sum;
       }
-      if (do_stats) {
-        named_bar_sync(1, 128);
-        for (int col = et; col < ncols; col += 128) {
-          float s = 0.f, q = 0.f;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            s += s_stats[(w * 2 + 0) * BLOCK_N + col];
-            if (EPI == XV_EPI_BF16) q += s_stats[(w * 2 + 1) * BLOCK_N + col];
-          }
-          atomicAdd(p.col_sum + n0 + col, s);
-          if (EPI == XV_EPI_BF16) atomicAdd(p.col_sumsq + n0 + col, q);
+      if (do_stats) {   // flush this tile's column sums: one global atomic per (tile, column)
+        named_bar_sync(1, NUM_EPI_WARPS * 32);
+        if (n0 + et < p.N) {
+          atomicAdd(p.col_sum + n0 + et, s_stats[et]);
+          if (EPI == XV_EPI_BF16) atomicAdd(p.col_sumsq + n0 + et, s_stats[BLOCK_N + et]);
         }
-        named_bar_sync(1, 128);
+        s_stats[et] = 0.f;
+        s_stats[BLOCK_N + et] = 0.f;
+        named_bar_sync(1, NUM_EPI_WARPS * 32);
       }
     }
+    if (lane == 0) bulk_wait_all();     // outstanding TMA stores read this CTA's shared memory
   }
 
   tc_fence_before();
@@ -496,8 +567,6 @@ int launch_gemm(const GemmKernelParams& kp, int grid, cudaStream_t stream) {
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
-
-
 
 // explicit instantiations live in xv_gemm_epi*.cu (one TU per epilogue keeps the parallel build short)
 extern template int launch_gemm<0>(const GemmKernelParams&, int, cudaStream_t);

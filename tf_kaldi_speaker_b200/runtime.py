@@ -48,7 +48,12 @@ class VarSpec(object):
         assert tuple(arr.shape) == self.tf_shape, "%s: expected %s, got %s" % (self.name, self.tf_shape, arr.shape)
         out = np.full(self.ishape, self.pad_value, dtype=np.float32)
         if len(self.ishape) == 1:
-            out[:arr.size] = arr.reshape(-1)
+            if self.row_map is not None:      # 1-D index map (e.g. [mean | std] halves of a channel-padded vector)
+                if self.pad_value != 0.0:
+                    out[:] = self.pad_value
+                out[self.row_map] = arr.reshape(-1)
+            else:
+                out[:arr.size] = arr.reshape(-1)
             return out
         a2 = arr.reshape(-1, arr.shape[-1])
         rows = np.arange(a2.shape[0]) if self.row_map is None else self.row_map
@@ -63,6 +68,8 @@ class VarSpec(object):
     def to_tf(self, arr):
         arr = np.asarray(arr, dtype=np.float32).reshape(self.ishape)
         if len(self.ishape) == 1:
+            if self.row_map is not None:
+                return arr[self.row_map].reshape(self.tf_shape).copy()
             return arr[:int(np.prod(self.tf_shape))].reshape(self.tf_shape).copy()
         ncol = self.tf_shape[-1]
         nrow = int(np.prod(self.tf_shape[:-1]))
@@ -479,6 +486,93 @@ class Engine(object):
             u.needs_grad = True
         return u
 
+    def att_pool(self, key, value, query, H, split_key, use_scale, penalty_coef, training):
+        """Attentive statistics pooling (model/pooling.py:120-189): scores = <key, query_h> (* rsqrt(dk)), softmax over the
+        valid frames, weighted mean / stddev of the value per head, optional multi-head penalty.
+        key / value: FrameAct (materialised bf16); returns (UttAct [B, 2*dv], weights f32 [B, H, T] view)."""
+        st = self.store
+        assert key.B == value.B and key.T == value.T and key.valid == value.valid, "key and value must have the same length"
+        B, T, valid = value.B, value.T, value.valid
+        lengths = value.lengths
+        lp = L.ptr(lengths)
+        kd, vd = key.materialize(), value.materialize()
+        ldk, cpad = key.ld, value.ld
+        q = st.view(query)                               # f32 [H, dq]
+        dq = q.shape[1]
+        scale = (1.0 / math.sqrt(dq)) if use_scale else 1.0
+        s = L.stream_ptr
+        qpad = self.buf("att/qpad", (H, ldk), torch.float32)
+        self.call(self.lib.xv_att_expand_query, L.ptr(q), L.ptr(qpad), H, dq, ldk, int(split_key), s())
+        w = self.buf("att/weights", (B, H, T), torch.float32)
+        self.call(self.lib.xv_att_scores_fwd, L.ptr(kd), L.ptr(qpad), L.ptr(w), B, T, valid, lp, H, ldk,
+                  C.c_float(scale), s())
+        self.call(self.lib.xv_att_softmax_fwd, L.ptr(w), L.ptr(w), B, H, T, valid, lp, s())
+        out = self.buf("pool/out", (B, 2 * cpad), torch.float32)
+        out3 = self.buf("pool/out3", (B, 6 * cpad), torch.bfloat16)
+        self.call(self.lib.xv_att_pool_fwd, L.ptr(vd), L.ptr(w), L.ptr(out), L.ptr(out3), B, H, T, valid, lp, value.C, cpad,
+                  C.c_int64(cpad), s())
+        gram = None
+        if penalty_coef != 0.0:
+            gram = self.buf("att/gram", (B, H, H), torch.float32)
+            self.call(self.lib.xv_att_penalty_fwd, L.ptr(w), L.ptr(gram), L.ptr(self.scalars[3:4]), B, H, T, valid, lp,
+                      C.c_float(penalty_coef), s())
+        u = UttAct(out, out3, "pool", (value.C, cpad))
+        if training:
+            def bwd():
+                if u.grad is None:
+                    return
+                dw = self.buf("att/dweights", (B, H, T), torch.float32)
+                acc_v = value.grad is not None
+                dv = value.grad if acc_v else self.buf(value.name + "/grad", (B * T, cpad), torch.bfloat16)
+                self.call(self.lib.xv_att_pool_bwd, L.ptr(vd), L.ptr(w), L.ptr(out), L.ptr(u.grad), L.ptr(dv), L.ptr(dw), B,
+                          H, T, valid, lp, value.C, cpad, C.c_int64(cpad), int(acc_v), s())
+                value.grad = dv
+                self.call(self.lib.xv_att_softmax_bwd, L.ptr(w), L.ptr(dw), L.ptr(gram), B, H, T, valid, lp,
+                          C.c_float(penalty_coef), C.c_float(scale), s())
+                dqpad = self.buf("att/dqpad", (H, ldk), torch.float32, zero=True)
+                acc_k = key.grad is not None
+                dk = key.grad if acc_k else self.buf(key.name + "/grad", (B * T, ldk), torch.bfloat16)
+                self.call(self.lib.xv_att_scores_bwd, L.ptr(kd), L.ptr(qpad), L.ptr(dw), L.ptr(dk), L.ptr(dqpad), B, T,
+                          valid, lp, H, ldk, int(acc_k), s())
+                key.grad = dk
+                self.call(self.lib.xv_att_fold_query_grad, L.ptr(dqpad), L.ptr(st.grad(query)), H, dq, ldk,
+                          int(split_key), s())
+            self.tape.append(bwd)
+            u.needs_grad = True
+        return u, w[:, :, :valid]
+
+    def utt_bn_act(self, u, bn, name, training, act=L.ACT_RELU, alpha=None, momentum=0.99):
+        """BN over the batch + activation on an utterance-level tensor without a preceding dense layer
+        (att_post_bn / att_post_relu, model/pooling.py:175-182).  Returns (BN output UttAct, activation UttAct)."""
+        st = self.store
+        B, Cn = u.data.shape
+        mode = 1 if training else 2
+        a = self.buf(name + "/a", (B, Cn), torch.float32)
+        a3 = self.buf(name + "/a3", (B, 3 * Cn), torch.bfloat16)
+        bn_out = self.buf(name + "/bn", (B, Cn), torch.float32)
+        smean = self.buf(name + "/save_mean", (Cn,), torch.float32)
+        srstd = self.buf(name + "/save_rstd", (Cn,), torch.float32)
+        g = lambda i: L.ptr(st.view(bn[i]))
+        alpha_t = None if alpha is None else st.view(alpha)
+        self.call(self.lib.xv_bn_rows_fwd, L.ptr(u.data), B, Cn, mode, g(0), g(1), g(2), g(3), C.c_float(momentum),
+                  C.c_float(BN_EPS), L.ptr(alpha_t), act, L.ptr(bn_out), L.ptr(a), L.ptr(a3), 3, L.ptr(smean),
+                  L.ptr(srstd), L.stream_ptr())
+        au = UttAct(a, a3, name + "/a", u.col_map)
+        bu = UttAct(bn_out, None, name + "/bn", u.col_map)
+        if training:
+            def bwd():
+                if au.grad is None:
+                    return
+                du = self.buf(u.name + "/grad_bn", (B, Cn), torch.float32)
+                self.call(self.lib.xv_bn_rows_bwd, L.ptr(u.data), L.ptr(au.grad), B, Cn, mode, g(0), g(1), L.ptr(smean),
+                          L.ptr(srstd), L.ptr(alpha_t), act, L.ptr(du), L.ptr(None), L.ptr(st.grad(bn[0])),
+                          L.ptr(st.grad(bn[1])), L.ptr(None if alpha is None else st.grad(alpha)), L.ptr(None),
+                          L.stream_ptr())
+                u.grad = du
+            self.tape.append(bwd)
+            au.needs_grad = True
+        return bu, au
+
     # ---- utterance-level ops ----------------------------------------------------------------------
     def utt_affine(self, u, kernel, bias, name, training, bn=None, act=L.ACT_RELU, alpha=None, momentum=0.99):
         """dense -> [BN over the batch] -> activation on fp32 [B, C] (tdnn6 / tdnn7, model/tdnn.py:147-189).
@@ -553,7 +647,7 @@ class Engine(object):
         self.call(self.lib.xv_head_prep_features, L.ptr(u.data), C.c_float(scaling), L.ptr(x), L.ptr(x3), L.ptr(xnorm),
                   L.ptr(urinv), B, E, L.stream_ptr())
         labels = labels.to(device=self.device, dtype=torch.int32).contiguous()
-        nblk = (Cn + 255) // 256
+        nblk = 2 * ((Cn + 255) // 256)      # one (max, sum) partial per 128-column half tile (two epilogue warps per row)
         pmax = self.buf("head/pmax", (nblk, B), torch.float32)
         psum = self.buf("head/psum", (nblk, B), torch.float32)
         tgt = self.buf("head/target", (B,), torch.float32)
