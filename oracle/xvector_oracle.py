@@ -346,7 +346,7 @@ def tdnn(features, P, params, is_training=False, updates=None, lengths=None, mir
         x = batch_norm(x, P, "tdnn/%s_bn" % name, mom, is_training, updates,
                        unbiased_moving_var=(mirror_tf_fused_bn and kind == "conv"),
                        store=bf16_ste if emulate_bf16 else None,
-                       stats_from_stored=(name in ("tdnn1", "tdnn4", "tdnn5")))
+                       stats_from_stored=False)   # every layer: statistics from the fp32 accumulators (GEMM epilogue)
         ep["%s_bn" % name] = x
         x = _activation(x, P, "tdnn/%s_relu" % name, relu_type)
         if not (name == "tdnn5" and params.pooling_type == "statistics_pooling"):

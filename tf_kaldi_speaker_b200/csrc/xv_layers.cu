@@ -125,6 +125,8 @@ __global__ void bn_finalize_infer_kernel(const float* __restrict__ gamma, const 
 constexpr int STREAM_ROWS = 64;
 constexpr int SV = 4;                 // channels per thread
 constexpr int SCH = 32 * SV;          // channels per warp / block column
+constexpr int RU = 2;                 // rows a warp keeps in flight per tensor (8 in flight measured SLOWER in the step:
+                                      // 125 registers -> 2 blocks/SM and no load/compute overlap inside a block)
 
 __device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&f)[4]) {
   const uint2 r = *reinterpret_cast<const uint2*>(p);
@@ -194,18 +196,18 @@ __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* 
   for (int j = 0; j < SV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
   const int r0 = blockIdx.y * STREAM_ROWS;
   const int r1 = min(r0 + STREAM_ROWS, rows);
-  for (int m = r0 + w; m < r1; m += 32) {
-    float v[4][SV];
-    bool in[4], valid[4];
+  for (int m = r0 + w; m < r1; m += 8 * RU) {
+    float v[RU][SV];
+    bool in[RU], valid[RU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < RU; ++u) {
       const int mm = m + 8 * u;
       in[u] = mm < r1;
       valid[u] = in[u] && row_is_valid(mm, seg_len, seg_valid, lengths);
       if (valid[u]) load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < RU; ++u) {
       if (!in[u]) continue;
       float o[SV];
 #pragma unroll
@@ -232,17 +234,17 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
     for (int j = 0; j < SV; ++j) bs[j] = bias ? bias[c0 + j] : 0.f;
     const int r0 = blockIdx.y * STREAM_ROWS;
     const int r1 = min(r0 + STREAM_ROWS, rows);
-    for (int m = r0 + w; m < r1; m += 32) {
-      float v[4][SV];
-      bool ok[4];
+    for (int m = r0 + w; m < r1; m += 8 * RU) {
+      float v[RU][SV];
+      bool ok[RU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < RU; ++u) {
         const int mm = m + 8 * u;
         ok[u] = mm < r1 && row_is_valid(mm, seg_len, seg_valid, lengths);
         if (ok[u]) load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < RU; ++u) {
         if (!ok[u]) continue;
 #pragma unroll
         for (int j = 0; j < SV; ++j) {
@@ -289,11 +291,11 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     pc.b = -1;
     const int r0 = blockIdx.y * STREAM_ROWS;
     const int r1 = min(r0 + STREAM_ROWS, rows);
-    for (int m = r0 + w; m < r1; m += 16) {
-      float v[2][SV], d[2][SV];
-      bool ok[2];
+    for (int m = r0 + w; m < r1; m += 8 * RU) {
+      float v[RU][SV], d[RU][SV];
+      bool ok[RU];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < RU; ++u) {
         const int mm = m + 8 * u;
         ok[u] = mm < r1 && row_is_valid(mm, seg_len, seg_valid, lengths);
         if (ok[u]) {
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < RU; ++u) {
         if (!ok[u]) continue;
         if (FUSED_POOL) pool_coef_load(pc, ps, (m + 8 * u) / seg_len, c0, seg_valid, lengths);
 #pragma unroll
@@ -359,11 +361,11 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
   pc.b = -1;
   const int r0 = blockIdx.y * STREAM_ROWS;
   const int r1 = min(r0 + STREAM_ROWS, rows);
-  for (int m = r0 + w; m < r1; m += 16) {
-    float v[2][SV], d[2][SV];
-    bool in[2], valid[2];
+  for (int m = r0 + w; m < r1; m += 8 * RU) {
+    float v[RU][SV], d[RU][SV];
+    bool in[RU], valid[RU];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < RU; ++u) {
       const int mm = m + 8 * u;
       in[u] = mm < r1;
       valid[u] = in[u] && row_is_valid(mm, seg_len, seg_valid, lengths);
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < RU; ++u) {
       if (!in[u]) continue;
       float o[SV];
       if (valid[u]) {
