@@ -248,11 +248,13 @@ XV_API int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, i
  * hyper (device f32[8]): lr, momentum, beta1, beta2, adam_eps, adam_t, clip_norm (<=0 off), unused.
  * blk_* arrays have one entry per 1024-element block: L2 coefficient, offset of the block's bf16 shadow
  * (-1: none) and, for the 3-term split shadows, the element stride between the hi / lo / hi copies (0: plain).
+ * l2_loss_out (optional): += sum l2/2 * w^2 of the PRE-update parameters, i.e. the regularisation loss of this step
+ * (tf.losses.get_regularization_loss, trainer.py:357) without a separate pass over the parameters.
  * ------------------------------------------------------------------------------------------ */
 XV_API int xv_grad_sumsq(const float* params, const float* grads, const float* blk_l2, int64_t n, float* out, void* stream);
 XV_API int xv_opt_step(float* params, const float* grads, float* state1, float* state2, const float* blk_l2,
                        const int64_t* blk_shadow, const int64_t* blk_split_stride, void* shadow, int64_t n, int opt,
-                       const float* hyper, const float* gsumsq, void* stream);
+                       const float* hyper, const float* gsumsq, float* l2_loss_out, void* stream);
 XV_API int xv_shadow_refresh(const float* params, const int64_t* blk_shadow, const int64_t* blk_split_stride,
                              void* shadow, int64_t n, void* stream);
 XV_API int xv_l2_loss(const float* params, const float* blk_l2, int64_t n, float* out, void* stream);

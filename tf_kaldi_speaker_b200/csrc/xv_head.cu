@@ -20,17 +20,19 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 
 // w f32 [E, C] (TF layout, C contiguous) -> wn3 bf16 [3E, ldw] = [hi(wn); lo(wn); hi(wn)], wn = w * rsqrt(max(sum_e w^2, 1e-12))
 // (tf.nn.l2_normalize(w, dim=0), loss.py:104,213,299).  normalize = 0 keeps w (plain softmax head).
-// Block = 32 x 8 threads: 64 columns (two per thread, 8-byte loads) x 8 row groups; column sums go through smem.
-__global__ void __launch_bounds__(256) head_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wn3,
+// Block = 32 x HROWG threads: 64 columns (two per thread, 8-byte loads) x HROWG row groups; column sums go through smem.
+// (8 row groups = 113 blocks x 8 warps for 7200 speakers left 90 % of the SM's warp slots empty: 28 us for 37 MB.)
+constexpr int HROWG = 32;
+__global__ void __launch_bounds__(32 * HROWG) head_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wn3,
                                                                 float* __restrict__ inv_norm, int E, int C, long long ldw,
                                                                 int normalize) {
-  __shared__ float red[8][64];
+  __shared__ float red[HROWG][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + tx * 2;
   const bool ok = c < C;                      // C is even (padded to a multiple of 8)
   float s0 = 0.f, s1 = 0.f;
   if (normalize && ok) {
-    for (int e = ty; e < E; e += 8) {
+    for (int e = ty; e < E; e += HROWG) {
       const float2 v = *reinterpret_cast<const float2*>(w + static_cast<long long>(e) * C + c);
       s0 += v.x * v.x;
       s1 += v.y * v.y;
@@ -43,13 +45,13 @@ __global__ void __launch_bounds__(256) head_prep_weights_kernel(const float* __r
   if (normalize) {
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { a0 += red[k][tx * 2]; a1 += red[k][tx * 2 + 1]; }
+    for (int k = 0; k < HROWG; ++k) { a0 += red[k][tx * 2]; a1 += red[k][tx * 2 + 1]; }
     i0 = rsqrtf(fmaxf(a0, 1e-12f));
     i1 = rsqrtf(fmaxf(a1, 1e-12f));
   }
   if (!ok) return;
   if (inv_norm && ty == 0) { inv_norm[c] = i0; inv_norm[c + 1] = i1; }
-  for (int e = ty; e < E; e += 8) {
+  for (int e = ty; e < E; e += HROWG) {
     const float2 v = *reinterpret_cast<const float2*>(w + static_cast<long long>(e) * C + c);
     const float v0 = v.x * i0, v1 = v.y * i1;
     const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
@@ -147,9 +149,9 @@ __global__ void head_finish_dx_kernel(const float* __restrict__ dxg, const float
 }
 
 // dW_j = (dWn_j - wn_j <wn_j, dWn_j>) * inv_norm_j   (in place on the gradient buffer); same 64 x 8 blocking.
-__global__ void __launch_bounds__(256) head_finish_dw_kernel(float* __restrict__ dw, const float* __restrict__ w,
-                                                             const float* __restrict__ inv_norm, int E, int C) {
-  __shared__ float red[8][64];
+__global__ void __launch_bounds__(32 * HROWG) head_finish_dw_kernel(float* __restrict__ dw, const float* __restrict__ w,
+                                                                    const float* __restrict__ inv_norm, int E, int C) {
+  __shared__ float red[HROWG][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + tx * 2;
   const bool ok = c < C;
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256) head_finish_dw_kernel(float* __restrict__
   if (ok) {
     i0 = inv_norm[c];
     i1 = inv_norm[c + 1];
-    for (int e = ty; e < E; e += 8) {
+    for (int e = ty; e < E; e += HROWG) {
       const long long idx = static_cast<long long>(e) * C + c;
       const float2 wv = *reinterpret_cast<const float2*>(w + idx);
       const float2 gv = *reinterpret_cast<const float2*>(dw + idx);
@@ -171,9 +173,9 @@ __global__ void __launch_bounds__(256) head_finish_dw_kernel(float* __restrict__
   if (!ok) return;
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { a0 += red[k][tx * 2]; a1 += red[k][tx * 2 + 1]; }
+  for (int k = 0; k < HROWG; ++k) { a0 += red[k][tx * 2]; a1 += red[k][tx * 2 + 1]; }
   const bool cl0 = (i0 >= 1e6f), cl1 = (i1 >= 1e6f);     // rsqrt(1e-12): the norm was clamped, no projection term
-  for (int e = ty; e < E; e += 8) {
+  for (int e = ty; e < E; e += HROWG) {
     const long long idx = static_cast<long long>(e) * C + c;
     const float2 wv = *reinterpret_cast<const float2*>(w + idx);
     float2 gv = *reinterpret_cast<const float2*>(dw + idx);
@@ -190,7 +192,7 @@ using namespace xv;
 extern "C" int xv_head_prep_weights(const float* w, void* wn3, float* inv_norm, int E, int C, int64_t ldw, int normalize,
                                     void* stream) {
   if (!w || !wn3 || E <= 0 || C <= 0 || (C & 1) || ldw < C || ldw % 8) return set_error(XV_ERR_INVALID, "xv_head_prep_weights: bad arguments (C must be even, ldw a multiple of 8)");
-  head_prep_weights_kernel<<<ceil_div(C, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  head_prep_weights_kernel<<<ceil_div(C, 64), 32 * HROWG, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<__nv_bfloat16*>(wn3), inv_norm, E, C, ldw, normalize);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -228,7 +230,7 @@ extern "C" int xv_head_finish_dx(const float* dx_gemm, const float* gnorm, const
 
 extern "C" int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, int E, int C, void* stream) {
   if (!dw || !w || !inv_norm || E <= 0 || C <= 0 || (C & 1)) return set_error(XV_ERR_INVALID, "xv_head_finish_dw: bad arguments (C must be even)");
-  head_finish_dw_kernel<<<ceil_div(C, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw, w, inv_norm, E, C);
+  head_finish_dw_kernel<<<ceil_div(C, 64), 32 * HROWG, 0, static_cast<cudaStream_t>(stream)>>>(dw, w, inv_norm, E, C);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

@@ -146,6 +146,36 @@ __device__ __forceinline__ void load4f(const float* p, float (&f)[4]) {
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
 }
 
+// A block of the row-streaming kernels owns rows [t0, t1) of ONE segment b, so row validity is a compare (t < L) and the
+// per-segment pooling coefficients are loaded once per block; the only integer division is this one, per block.
+// (A division per row per thread made these kernels issue-bound: ~36 warp instructions per element.)
+struct RowChunk {
+  int b, t0, t1, L;
+  long long m_base;     // first row of the segment
+};
+struct RowGrid {
+  int seg_len, chunks, rows_per_chunk;   // seg_len = rows when the tensor has no segment structure
+  int col_groups;                        // channel groups of SCH channels; blockIdx.x = row_chunk * col_groups + group
+};
+static inline RowGrid make_row_grid(long long rows, int seg_len, int C) {
+  RowGrid g;
+  g.col_groups = (C + SCH - 1) / SCH;
+  g.seg_len = seg_len > 0 ? seg_len : static_cast<int>(rows);
+  g.chunks = (g.seg_len + STREAM_ROWS - 1) / STREAM_ROWS;
+  g.rows_per_chunk = (g.seg_len + g.chunks - 1) / g.chunks;
+  return g;
+}
+__device__ __forceinline__ RowChunk row_chunk(int block_y, const RowGrid& g, int seg_len, int seg_valid, const int* lengths) {
+  RowChunk c;
+  c.b = block_y / g.chunks;
+  const int ch = block_y - c.b * g.chunks;
+  c.t0 = ch * g.rows_per_chunk;
+  c.t1 = min(c.t0 + g.rows_per_chunk, g.seg_len);
+  c.L = seg_len > 0 ? (lengths ? lengths[c.b] : seg_valid) : g.seg_len;
+  c.m_base = static_cast<long long>(c.b) * g.seg_len;
+  return c;
+}
+
 template <int ACT>
 __device__ __forceinline__ float actf(float z, float alpha) { return act_fwd(ACT, z, alpha); }
 template <int ACT>
@@ -184,35 +214,36 @@ __device__ __forceinline__ void pool_coef_load(PoolCoef& pc, const PoolGradSrc& 
 template <int ACT>
 __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ alpha, int rows, int C, long long ld,
+                                    const float* __restrict__ alpha, RowGrid rg, int C, long long ld,
                                     int seg_len, int seg_valid, const int* __restrict__ lengths) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * SCH + lane * SV;
+  const int cg_ = blockIdx.x % rg.col_groups, by_ = blockIdx.x / rg.col_groups;
+  const int c0 = cg_ * SCH + lane * SV;
   if (c0 >= C) return;
+  const RowChunk rc = row_chunk(by_, rg, seg_len, seg_valid, lengths);
   float sc[SV], sh[SV], al[SV];
   load4f(scale + c0, sc);
   load4f(shift + c0, sh);
 #pragma unroll
   for (int j = 0; j < SV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
-  const int r0 = blockIdx.y * STREAM_ROWS;
-  const int r1 = min(r0 + STREAM_ROWS, rows);
-  for (int m = r0 + w; m < r1; m += 8 * RU) {
-    float v[RU][SV];
-    bool in[RU], valid[RU];
+  constexpr int FU = 4;      // rows in flight per warp
+  for (int t = rc.t0 + w; t < rc.t1; t += 8 * FU) {
+    float v[FU][SV];
+    bool in[FU], valid[FU];
 #pragma unroll
-    for (int u = 0; u < RU; ++u) {
-      const int mm = m + 8 * u;
-      in[u] = mm < r1;
-      valid[u] = in[u] && row_is_valid(mm, seg_len, seg_valid, lengths);
-      if (valid[u]) load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
+    for (int u = 0; u < FU; ++u) {
+      const int tt = t + 8 * u;
+      in[u] = tt < rc.t1;
+      valid[u] = tt < rc.t1 && tt < rc.L;
+      if (valid[u]) load4(y + (rc.m_base + tt) * ld + c0, v[u]);
     }
 #pragma unroll
-    for (int u = 0; u < RU; ++u) {
+    for (int u = 0; u < FU; ++u) {
       if (!in[u]) continue;
       float o[SV];
 #pragma unroll
       for (int j = 0; j < SV; ++j) o[j] = valid[u] ? actf<ACT>(fmaf(v[u][j], sc[j], sh[j]), al[j]) : 0.f;
-      store4(a + static_cast<long long>(m + 8 * u) * ld + c0, o);
+      store4(a + (rc.m_base + t + 8 * u) * ld + c0, o);
     }
   }
 }
@@ -220,11 +251,12 @@ __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* 
 // Per-channel sum / sum of squares of (y - bias) over the valid rows: the BN batch statistics of layers whose GEMM is
 // too short (K <= 512) to hide a reduction epilogue.
 __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
-                                                        int rows, int C, long long ld, int seg_len, int seg_valid,
+                                                        RowGrid rg, int C, long long ld, int seg_len, int seg_valid,
                                                         const int* __restrict__ lengths, float* col_sum, float* col_sumsq) {
   __shared__ float red[8][2][SCH];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * SCH + lane * SV;
+  const int cg_ = blockIdx.x % rg.col_groups, by_ = blockIdx.x / rg.col_groups;
+  const int c0 = cg_ * SCH + lane * SV;
   float s1[SV], s2[SV];
 #pragma unroll
   for (int j = 0; j < SV; ++j) s1[j] = s2[j] = 0.f;
@@ -232,16 +264,16 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
     float bs[SV];
 #pragma unroll
     for (int j = 0; j < SV; ++j) bs[j] = bias ? bias[c0 + j] : 0.f;
-    const int r0 = blockIdx.y * STREAM_ROWS;
-    const int r1 = min(r0 + STREAM_ROWS, rows);
-    for (int m = r0 + w; m < r1; m += 8 * RU) {
+    const RowChunk rc = row_chunk(by_, rg, seg_len, seg_valid, lengths);
+    const int t1 = min(rc.t1, rc.L);
+    for (int t = rc.t0 + w; t < t1; t += 8 * RU) {
       float v[RU][SV];
       bool ok[RU];
 #pragma unroll
       for (int u = 0; u < RU; ++u) {
-        const int mm = m + 8 * u;
-        ok[u] = mm < r1 && row_is_valid(mm, seg_len, seg_valid, lengths);
-        if (ok[u]) load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
+        const int tt = t + 8 * u;
+        ok[u] = tt < t1;
+        if (ok[u]) load4(y + (rc.m_base + tt) * ld + c0, v[u]);
       }
 #pragma unroll
       for (int u = 0; u < RU; ++u) {
@@ -258,7 +290,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
 #pragma unroll
   for (int j = 0; j < SV; ++j) { red[w][0][lane * SV + j] = s1[j]; red[w][1][lane * SV + j] = s2[j]; }
   __syncthreads();
-  const int c = blockIdx.x * SCH + threadIdx.x;
+  const int c = cg_ * SCH + threadIdx.x;
   if (threadIdx.x < SCH && c < C) {
     float a = 0.f, q = 0.f;
 #pragma unroll
@@ -273,11 +305,12 @@ template <bool FUSED_POOL, int ACT>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
-    const float* __restrict__ alpha, int rows, int C, long long ld, int seg_len, int seg_valid,
+    const float* __restrict__ alpha, RowGrid rg, int C, long long ld, int seg_len, int seg_valid,
     const int* __restrict__ lengths, float* dgamma, float* dbeta, float* dalpha, PoolGradSrc ps) {
   __shared__ float red[8][3][SCH];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * SCH + lane * SV;
+  const int cg_ = blockIdx.x % rg.col_groups, by_ = blockIdx.x / rg.col_groups;
+  const int c0 = cg_ * SCH + lane * SV;
   const bool c_ok = c0 < C;
   float sg[SV], sgy[SV], sal[SV];
 #pragma unroll
@@ -287,26 +320,26 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     load4f(scale + c0, sc); load4f(shift + c0, sh); load4f(save_mean + c0, mu); load4f(save_rstd + c0, rs);
 #pragma unroll
     for (int j = 0; j < SV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+    const RowChunk rc = row_chunk(by_, rg, seg_len, seg_valid, lengths);
     PoolCoef pc;
     pc.b = -1;
-    const int r0 = blockIdx.y * STREAM_ROWS;
-    const int r1 = min(r0 + STREAM_ROWS, rows);
-    for (int m = r0 + w; m < r1; m += 8 * RU) {
+    if (FUSED_POOL) pool_coef_load(pc, ps, rc.b, c0, seg_valid, lengths);
+    const int t1 = min(rc.t1, rc.L);
+    for (int t = rc.t0 + w; t < t1; t += 8 * RU) {
       float v[RU][SV], d[RU][SV];
       bool ok[RU];
 #pragma unroll
       for (int u = 0; u < RU; ++u) {
-        const int mm = m + 8 * u;
-        ok[u] = mm < r1 && row_is_valid(mm, seg_len, seg_valid, lengths);
+        const int tt = t + 8 * u;
+        ok[u] = tt < t1;
         if (ok[u]) {
-          load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
-          if (!FUSED_POOL) load4(da + static_cast<long long>(mm) * ld + c0, d[u]);
+          load4(y + (rc.m_base + tt) * ld + c0, v[u]);
+          if (!FUSED_POOL) load4(da + (rc.m_base + tt) * ld + c0, d[u]);
         }
       }
 #pragma unroll
       for (int u = 0; u < RU; ++u) {
         if (!ok[u]) continue;
-        if (FUSED_POOL) pool_coef_load(pc, ps, (m + 8 * u) / seg_len, c0, seg_valid, lengths);
 #pragma unroll
         for (int j = 0; j < SV; ++j) {
           const float z = fmaf(v[u][j], sc[j], sh[j]);
@@ -326,7 +359,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     red[w][2][lane * SV + j] = sal[j];
   }
   __syncthreads();
-  const int c = blockIdx.x * SCH + threadIdx.x;
+  const int c = cg_ * SCH + threadIdx.x;
   if (threadIdx.x < SCH && c < C) {
     float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
@@ -343,10 +376,11 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dy,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ save_mean,
     const float* __restrict__ save_rstd, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-    float inv_count, const float* __restrict__ alpha, int rows, int C, long long ld, int seg_len,
+    float inv_count, const float* __restrict__ alpha, RowGrid rg, int C, long long ld, int seg_len,
     int seg_valid, const int* __restrict__ lengths, PoolGradSrc ps) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * SCH + lane * SV;
+  const int cg_ = blockIdx.x % rg.col_groups, by_ = blockIdx.x / rg.col_groups;
+  const int c0 = cg_ * SCH + lane * SV;
   if (c0 >= C) return;
   float sc[SV], sh[SV], mu[SV], rs[SV], dg[SV], db[SV], al[SV];
   load4f(scale + c0, sc); load4f(shift + c0, sh); load4f(save_mean + c0, mu); load4f(save_rstd + c0, rs);
@@ -357,21 +391,21 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     dg[j] *= inv_count;
     db[j] *= inv_count;
   }
+  const RowChunk rc = row_chunk(by_, rg, seg_len, seg_valid, lengths);
   PoolCoef pc;
   pc.b = -1;
-  const int r0 = blockIdx.y * STREAM_ROWS;
-  const int r1 = min(r0 + STREAM_ROWS, rows);
-  for (int m = r0 + w; m < r1; m += 8 * RU) {
+  if (FUSED_POOL) pool_coef_load(pc, ps, rc.b, c0, seg_valid, lengths);
+  for (int t = rc.t0 + w; t < rc.t1; t += 8 * RU) {
     float v[RU][SV], d[RU][SV];
     bool in[RU], valid[RU];
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
-      const int mm = m + 8 * u;
-      in[u] = mm < r1;
-      valid[u] = in[u] && row_is_valid(mm, seg_len, seg_valid, lengths);
+      const int tt = t + 8 * u;
+      in[u] = tt < rc.t1;
+      valid[u] = tt < rc.t1 && tt < rc.L;
       if (valid[u]) {
-        load4(y + static_cast<long long>(mm) * ld + c0, v[u]);
-        if (!FUSED_POOL) load4(da + static_cast<long long>(mm) * ld + c0, d[u]);
+        load4(y + (rc.m_base + tt) * ld + c0, v[u]);
+        if (!FUSED_POOL) load4(da + (rc.m_base + tt) * ld + c0, d[u]);
       }
     }
 #pragma unroll
@@ -379,7 +413,6 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
       if (!in[u]) continue;
       float o[SV];
       if (valid[u]) {
-        if (FUSED_POOL) pool_coef_load(pc, ps, (m + 8 * u) / seg_len, c0, seg_valid, lengths);
 #pragma unroll
         for (int j = 0; j < SV; ++j) {
           const float z = fmaf(v[u][j], sc[j], sh[j]);
@@ -392,7 +425,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
 #pragma unroll
         for (int j = 0; j < SV; ++j) o[j] = 0.f;
       }
-      store4(dy + static_cast<long long>(m + 8 * u) * ld + c0, o);
+      store4(dy + (rc.m_base + t + 8 * u) * ld + c0, o);
     }
   }
 }
@@ -588,10 +621,12 @@ extern "C" int xv_bn_act_apply(const void* y, void* a, const float* scale, const
   if (!y || !a || !scale || !shift || rows <= 0) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: bad arguments");
   int rc = check_act_layout("xv_bn_act_apply", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: rows must fit in int32");
-  dim3 grid(ceil_div(C, SCH), ceil_div(rows, STREAM_ROWS));
+  if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
+  const RowGrid rg = make_row_grid(rows, seg_len, C);
+  const unsigned grid = static_cast<unsigned>(ceil_div(C, SCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
   XV_ACT_DISPATCH(act, (bn_act_apply_kernel<A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha,
-      static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths)));
+      rg, C, ld, seg_len, seg_valid, lengths)));
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
@@ -600,9 +635,11 @@ extern "C" int xv_col_stats(const void* y, const float* bias, int64_t rows, int 
                             const int32_t* lengths, float* col_sum, float* col_sumsq, void* stream) {
   if (!y || !col_sum || !col_sumsq || rows <= 0 || rows > 0x7fffffffLL || C <= 0 || C % 8 || ld % 8 || ld < C)
     return set_error(XV_ERR_INVALID, "xv_col_stats: bad arguments");
-  dim3 grid(ceil_div(C, SCH), ceil_div(rows, STREAM_ROWS));
+  if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
+  const RowGrid rg = make_row_grid(rows, seg_len, C);
+  const unsigned grid = static_cast<unsigned>(ceil_div(C, SCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
   col_stats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), bias, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, col_sum,
+      static_cast<const __nv_bfloat16*>(y), bias, rg, C, ld, seg_len, seg_valid, lengths, col_sum,
       col_sumsq);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -626,16 +663,18 @@ extern "C" int xv_bn_act_bwd_reduce(const void* y, const void* da, const float* 
     return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_reduce: bad arguments");
   int rc = check_act_layout("xv_bn_act_bwd_reduce", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_reduce: rows must fit in int32");
-  dim3 grid(ceil_div(C, SCH), ceil_div(rows, STREAM_ROWS));
+  if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
+  const RowGrid rg = make_row_grid(rows, seg_len, C);
+  const unsigned grid = static_cast<unsigned>(ceil_div(C, SCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
   PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
   if (pooled) {
     XV_ACT_DISPATCH(act, (bn_act_bwd_reduce_kernel<true, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), nullptr, scale, shift, save_mean, save_rstd, alpha,
-        static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps)));
+        rg, C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps)));
   } else {
     XV_ACT_DISPATCH(act, (bn_act_bwd_reduce_kernel<false, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), scale, shift, save_mean, save_rstd,
-        alpha, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps)));
+        alpha, rg, C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps)));
   }
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -652,15 +691,17 @@ extern "C" int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, cons
   int rc = check_act_layout("xv_bn_act_bwd_apply", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_apply: rows must fit in int32");
   PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
-  dim3 grid(ceil_div(C, SCH), ceil_div(rows, STREAM_ROWS));
+  if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
+  const RowGrid rg = make_row_grid(rows, seg_len, C);
+  const unsigned grid = static_cast<unsigned>(ceil_div(C, SCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
   if (pooled) {
     XV_ACT_DISPATCH(act, (bn_act_bwd_apply_kernel<true, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), nullptr, static_cast<__nv_bfloat16*>(dy), scale, shift, save_mean,
-        save_rstd, dgamma, dbeta, 1.0f / count, alpha, static_cast<int>(rows), C, ld, seg_len, seg_valid, lengths, ps)));
+        save_rstd, dgamma, dbeta, 1.0f / count, alpha, rg, C, ld, seg_len, seg_valid, lengths, ps)));
   } else {
     XV_ACT_DISPATCH(act, (bn_act_bwd_apply_kernel<false, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dy),
-        scale, shift, save_mean, save_rstd, dgamma, dbeta, 1.0f / count, alpha, static_cast<int>(rows), C, ld,
+        scale, shift, save_mean, save_rstd, dgamma, dbeta, 1.0f / count, alpha, rg, C, ld,
         seg_len, seg_valid, lengths, ps)));
   }
   XV_CUDA_CHECK(cudaGetLastError());

@@ -38,13 +38,19 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict
 }
 
 // hyper (device): [0] lr, [1] momentum, [2] beta1, [3] beta2, [4] adam eps, [5] adam step t (>=1), [6] clip norm (<=0: off)
+// Each CTA walks OPT_UNROLL 1024-element blocks per iteration with all their loads issued up front (one block per
+// iteration left ~2 x 16 B in flight per thread: 40 % of HBM).  l2_out (optional) += sum l2/2 * w_old^2, the
+// regularisation loss of the step (tf.losses.get_regularization_loss, trainer.py:357), so no separate pass reads w.
+constexpr int OPT_UNROLL = 4;
 __global__ void __launch_bounds__(256) opt_step_kernel(float* __restrict__ params, const float* __restrict__ grads,
                                                        float* __restrict__ s1, float* __restrict__ s2,
                                                        const float* __restrict__ blk_l2,
                                                        const long long* __restrict__ blk_shadow,
                                                        const long long* __restrict__ blk_split_stride,
                                                        __nv_bfloat16* __restrict__ shadow, long long n, int opt,
-                                                       const float* __restrict__ hyper, const float* __restrict__ gsumsq) {
+                                                       const float* __restrict__ hyper, const float* __restrict__ gsumsq,
+                                                       float* l2_out) {
+  __shared__ float sh[8];
   const float lr = hyper[0];
   float gscale = 1.f;
   if (hyper[6] > 0.f && gsumsq) {
@@ -53,55 +59,80 @@ __global__ void __launch_bounds__(256) opt_step_kernel(float* __restrict__ param
   }
   float lr_t = lr;
   if (opt == OPT_ADAM) lr_t = lr * sqrtf(1.f - powf(hyper[3], hyper[5])) / (1.f - powf(hyper[2], hyper[5]));
-  for (long long blk = blockIdx.x; blk * OPT_BLOCK < n; blk += gridDim.x) {
-    const float l2 = blk_l2[blk];
-    const long long base = blk * OPT_BLOCK + threadIdx.x * 4;
-    if (base + 3 >= n) continue;
-    const float4 g4 = *reinterpret_cast<const float4*>(grads + base);
-    float4 w4 = *reinterpret_cast<const float4*>(params + base);
-    float g[4] = {g4.x, g4.y, g4.z, g4.w};
-    float w[4] = {w4.x, w4.y, w4.z, w4.w};
-    float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-    if (opt != OPT_SGD) {
-      const float4 t = *reinterpret_cast<const float4*>(s1 + base);
-      a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
-    }
-    if (opt == OPT_ADAM) {
-      const float4 t = *reinterpret_cast<const float4*>(s2 + base);
-      b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
-    }
+  const long long nblk = (n + OPT_BLOCK - 1) / OPT_BLOCK;
+  float l2acc = 0.f;
+  for (long long blk0 = static_cast<long long>(blockIdx.x) * OPT_UNROLL; blk0 < nblk;
+       blk0 += static_cast<long long>(gridDim.x) * OPT_UNROLL) {
+    float4 g4[OPT_UNROLL], w4[OPT_UNROLL], a4[OPT_UNROLL], b4[OPT_UNROLL];
+    float l2[OPT_UNROLL];
+    bool ok[OPT_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gr = (g[j] + l2 * w[j]) * gscale;
-      if (opt == OPT_SGD) {
-        w[j] -= lr * gr;
-      } else if (opt == OPT_MOMENTUM || opt == OPT_NESTEROV) {
-        a[j] = a[j] * hyper[1] + gr;                                 // accum = momentum*accum + grad
-        w[j] -= lr * ((opt == OPT_NESTEROV) ? (gr + hyper[1] * a[j]) : a[j]);
-      } else {
-        a[j] = a[j] * hyper[2] + (1.f - hyper[2]) * gr;
-        b[j] = b[j] * hyper[3] + (1.f - hyper[3]) * gr * gr;
-        w[j] -= lr_t * a[j] / (sqrtf(b[j]) + hyper[4]);
+    for (int u = 0; u < OPT_UNROLL; ++u) {
+      const long long blk = blk0 + u;
+      const long long base = blk * OPT_BLOCK + threadIdx.x * 4;
+      ok[u] = blk < nblk && base + 3 < n;
+      a4[u] = b4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok[u]) {
+        l2[u] = blk_l2[blk];
+        g4[u] = *reinterpret_cast<const float4*>(grads + base);
+        w4[u] = *reinterpret_cast<const float4*>(params + base);
+        if (opt != OPT_SGD) a4[u] = *reinterpret_cast<const float4*>(s1 + base);
+        if (opt == OPT_ADAM) b4[u] = *reinterpret_cast<const float4*>(s2 + base);
       }
     }
-    *reinterpret_cast<float4*>(params + base) = make_float4(w[0], w[1], w[2], w[3]);
-    if (opt != OPT_SGD) *reinterpret_cast<float4*>(s1 + base) = make_float4(a[0], a[1], a[2], a[3]);
-    if (opt == OPT_ADAM) *reinterpret_cast<float4*>(s2 + base) = make_float4(b[0], b[1], b[2], b[3]);
-    const long long so = blk_shadow[blk];
-    if (so >= 0) {
-      const long long stride = blk_split_stride[blk];
-      __nv_bfloat16* d = shadow + so + threadIdx.x * 4;
-      __nv_bfloat16 h[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = __float2bfloat16(w[j]);
-      *reinterpret_cast<uint2*>(d) = *reinterpret_cast<uint2*>(h);
-      if (stride > 0) {
-        __nv_bfloat16 l[4];
+    for (int u = 0; u < OPT_UNROLL; ++u) {
+      if (!ok[u]) continue;
+      const long long blk = blk0 + u;
+      const long long base = blk * OPT_BLOCK + threadIdx.x * 4;
+      float g[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+      float w[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+      float a[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+      float b[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w};
+      l2acc += 0.5f * l2[u] * (w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) l[j] = __float2bfloat16(w[j] - __bfloat162float(h[j]));
-        *reinterpret_cast<uint2*>(d + stride) = *reinterpret_cast<uint2*>(l);
-        *reinterpret_cast<uint2*>(d + 2 * stride) = *reinterpret_cast<uint2*>(h);
+      for (int j = 0; j < 4; ++j) {
+        const float gr = (g[j] + l2[u] * w[j]) * gscale;
+        if (opt == OPT_SGD) {
+          w[j] -= lr * gr;
+        } else if (opt == OPT_MOMENTUM || opt == OPT_NESTEROV) {
+          a[j] = a[j] * hyper[1] + gr;                                 // accum = momentum*accum + grad
+          w[j] -= lr * ((opt == OPT_NESTEROV) ? (gr + hyper[1] * a[j]) : a[j]);
+        } else {
+          a[j] = a[j] * hyper[2] + (1.f - hyper[2]) * gr;
+          b[j] = b[j] * hyper[3] + (1.f - hyper[3]) * gr * gr;
+          w[j] -= lr_t * a[j] / (sqrtf(b[j]) + hyper[4]);
+        }
       }
+      *reinterpret_cast<float4*>(params + base) = make_float4(w[0], w[1], w[2], w[3]);
+      if (opt != OPT_SGD) *reinterpret_cast<float4*>(s1 + base) = make_float4(a[0], a[1], a[2], a[3]);
+      if (opt == OPT_ADAM) *reinterpret_cast<float4*>(s2 + base) = make_float4(b[0], b[1], b[2], b[3]);
+      const long long so = blk_shadow[blk];
+      if (so >= 0) {
+        const long long stride = blk_split_stride[blk];
+        __nv_bfloat16* d = shadow + so + threadIdx.x * 4;
+        __nv_bfloat16 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __float2bfloat16(w[j]);
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<uint2*>(h);
+        if (stride > 0) {
+          __nv_bfloat16 l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) l[j] = __float2bfloat16(w[j] - __bfloat162float(h[j]));
+          *reinterpret_cast<uint2*>(d + stride) = *reinterpret_cast<uint2*>(l);
+          *reinterpret_cast<uint2*>(d + 2 * stride) = *reinterpret_cast<uint2*>(h);
+        }
+      }
+    }
+  }
+  if (l2_out) {
+    for (int o = 16; o > 0; o >>= 1) l2acc += __shfl_xor_sync(0xffffffffu, l2acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = l2acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += sh[i];
+      atomicAdd(l2_out, t);
     }
   }
 }
@@ -181,16 +212,17 @@ extern "C" int xv_grad_sumsq(const float* params, const float* grads, const floa
 
 extern "C" int xv_opt_step(float* params, const float* grads, float* state1, float* state2, const float* blk_l2,
                            const int64_t* blk_shadow, const int64_t* blk_split_stride, void* shadow, int64_t n, int opt,
-                           const float* hyper, const float* gsumsq, void* stream) {
+                           const float* hyper, const float* gsumsq, float* l2_loss_out, void* stream) {
   if (!params || !grads || !blk_l2 || !blk_shadow || !blk_split_stride || !hyper || n <= 0 || n % OPT_BLOCK)
     return set_error(XV_ERR_INVALID, "xv_opt_step: bad arguments (n must be a positive multiple of 1024)");
   if (opt < OPT_SGD || opt > OPT_ADAM) { set_error(XV_ERR_INVALID, "Optimizer %d is not supported.", opt); return XV_ERR_INVALID; }
   if (opt != OPT_SGD && !state1) return set_error(XV_ERR_INVALID, "xv_opt_step: momentum/adam need state1");
   if (opt == OPT_ADAM && !state2) return set_error(XV_ERR_INVALID, "xv_opt_step: adam needs state2");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
-  opt_step_kernel<<<opt_grid(n, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  opt_step_kernel<<<opt_grid((n + OPT_UNROLL - 1) / OPT_UNROLL, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       params, grads, state1, state2, blk_l2, reinterpret_cast<const long long*>(blk_shadow),
-      reinterpret_cast<const long long*>(blk_split_stride), static_cast<__nv_bfloat16*>(shadow), n, opt, hyper, gsumsq);
+      reinterpret_cast<const long long*>(blk_split_stride), static_cast<__nv_bfloat16*>(shadow), n, opt, hyper, gsumsq,
+      l2_loss_out);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

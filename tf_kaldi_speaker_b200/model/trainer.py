@@ -123,15 +123,17 @@ class Trainer(object):
             labels = labels.to(dev, dtype=torch.int32, non_blocking=True)
         return features, labels
 
-    def _fwd_bwd(self, features, labels):
-        """Forward + backward of one device-resident batch; gradients are left in the flat gradient buffer."""
+    def _fwd_bwd(self, features, labels, l2_loss=True):
+        """Forward + backward of one device-resident batch; gradients are left in the flat gradient buffer.
+        ``l2_loss=False``: the regularisation loss is left to the optimizer kernel (same pass over the parameters)."""
         eng = self.engine
         eng.begin_step(True)
         out, endpoints = self.entire_network(features, self.params, True, True)
         loss, endpoints_loss = self.loss_network(out, labels, self.num_speakers, self.params, True, True)
         endpoints.update(endpoints_loss)
         self.endpoints = endpoints
-        eng.l2_loss()
+        if l2_loss:
+            eng.l2_loss()
         eng.backward()
 
     def forward_backward(self, features, labels, global_step):
@@ -174,14 +176,14 @@ class Trainer(object):
             self.adam_t += 1
         clip = bool(self.params.dict.get("clip_gradient", False))
         eng.set_hyper(float(learning_rate), float(self.params.dict.get("momentum", 0.0)), float(max(self.adam_t, 1)),
-                      float(self.params.dict.get("clip_gradient_norm", 0.0)) if clip else 0.0)
+                      float(self.params.dict.get("clip_gradient_norm", 0.0)) if clip else 0.0, flush=False)
         eng.set_sched(*margin_schedule(self.loss_type, self.params, global_step))
 
         def part_a():
-            self._fwd_bwd(st["x"], st["y"])
+            self._fwd_bwd(st["x"], st["y"], l2_loss=False)
 
         def part_b():
-            eng.optimizer_step(self.opt, clip=clip)
+            eng.optimizer_step(self.opt, clip=clip, with_l2_loss=True)
 
         if st["graphs"] is not None:
             ga, gb = st["graphs"]

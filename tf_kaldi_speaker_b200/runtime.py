@@ -26,6 +26,7 @@ from . import _lib as L
 
 ALIGN = 1024
 BN_EPS = 1e-3
+ZERO_ARENA = 1 << 20          # floats (4 MB) of step-start-zero scratch behind the gradient buffer
 
 
 def _pad_to(n, m):
@@ -114,7 +115,12 @@ class ParamStore(object):
         self.n = max(off, ALIGN)
         dev = self.device
         self.params = torch.zeros(self.n, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        # gradients + a "zero arena" in ONE allocation: every accumulator that must start a step at zero (BN statistics,
+        # split-K outputs, loss scalars) is carved from the arena, so a step begins with a single fill kernel
+        self.grads_ext = torch.zeros(self.n + ZERO_ARENA, dtype=torch.float32, device=dev)
+        self.grads = self.grads_ext[:self.n]
+        self.arena = self.grads_ext[self.n:]
+        self.arena_used = 0
         self.state1 = None
         self.state2 = None
         self.shadow = torch.zeros(max(soff, ALIGN), dtype=torch.bfloat16, device=dev)
@@ -289,24 +295,57 @@ class Engine(object):
             raise L.XvError("xvector_b200 kernels are sm_100a only (found cc %d.%d)" % (info[1], info[2]))
         self.store = ParamStore(self.device)
         self.ws = {}
+        self._arena_bufs = set()
         self.tape = []
         self.penalties = []
         self.launches = 0
-        self.hyper = torch.zeros(8, dtype=torch.float32, device=self.device)
-        self.sched = torch.tensor([1.0, 0.0], dtype=torch.float32, device=self.device)
-        self.scalars = torch.zeros(8, dtype=torch.float32, device=self.device)   # [0] loss, [1] l2 loss, [2] grad sumsq, [3] penalty
+        self._hs = torch.zeros(16, dtype=torch.float32, device=self.device)      # host-fed scalars, one launch per step
+        self._hs[8] = 1.0
+        self.hyper = self._hs[:8]
+        self.sched = self._hs[8:10]                                              # (fa, fs) of the margin schedule
+        self._hs_host = [0.0] * 8 + [1.0, 0.0]
+        self._scalars = None             # [0] loss, [1] l2 loss, [2] grad sumsq, [3] penalty (lives in the zero arena)
         self.inv_global_batch = None     # set by the data-parallel wrapper (1 / (N * B))
         self.capturing = False           # True while a CUDA graph of the step is being captured
         self.epilogue_stats = True       # False: BN batch statistics from the separate xv_col_stats pass (tests)
 
     # ---- memory
+    @property
+    def scalars(self):
+        if self._scalars is None:
+            self._scalars = self._arena_alloc(8)
+            if self._scalars is None:
+                self._scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
+        return self._scalars
+
+    def _arena_alloc(self, numel):
+        st = self.store
+        if not st.finalized:
+            return None
+        n = _pad_to(numel, 32)
+        if st.arena_used + n > st.arena.numel():
+            return None
+        t = st.arena[st.arena_used:st.arena_used + numel]
+        st.arena_used += n
+        return t
+
     def buf(self, name, shape, dtype, zero=False):
+        """Named workspace tensor (allocated once per name/shape).  ``zero=True``: the buffer starts every step at zero;
+        fp32 buffers come from the zero arena cleared by begin_step's single fill, others are cleared here."""
         key = (name, tuple(shape), dtype)
         t = self.ws.get(key)
         if t is None:
+            if zero and dtype == torch.float32:
+                flat = self._arena_alloc(int(np.prod(shape)))
+                if flat is not None:
+                    t = flat.view(*shape)
+                    self.ws[key] = t
+                    self._arena_bufs.add(key)
+                    t.zero_()
+                    return t
             t = torch.zeros(shape, dtype=dtype, device=self.device)
             self.ws[key] = t
-        elif zero:
+        elif zero and key not in self._arena_bufs:
             t.zero_()
         return t
 
@@ -341,9 +380,14 @@ class Engine(object):
         self.tape = []
         self.penalties = []
         self.training = training
-        self.scalars.zero_()
+        sc = self.scalars                   # make sure the scalars exist before the fill
+        st = self.store
+        if sc.data_ptr() < st.arena.data_ptr() or sc.data_ptr() >= st.arena.data_ptr() + 4 * st.arena.numel():
+            sc.zero_()
         if training:
-            self.store.grads.zero_()
+            st.grads_ext.zero_()            # gradients + zero arena (BN statistics, split-K outputs, loss scalars)
+        else:
+            st.arena[:max(st.arena_used, 32)].zero_()
 
     def backward(self):
         for fn in reversed(self.tape):
@@ -693,10 +737,8 @@ class Engine(object):
                 if normalize:
                     self.call(self.lib.xv_head_finish_dw, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), E, cpad, L.stream_ptr())
                 # dx[i, e] = sum_c d[i, c] wn[e, c]
-                dxg = self.buf("head/dxg", (B, E), torch.float32)
+                dxg = self.buf("head/dxg", (B, E), torch.float32, zero=True)
                 sp = self.splits_for(B, E, Cn)
-                if sp > 1:
-                    dxg.zero_()
                 self.gemm(L.operand(d, False, cols=Cn), L.operand(wn3, False, rows=E, cols=Cn), B, E, Cn, dxg,
                           epilogue=L.EPI_F32, splits=sp)
                 du = self.buf(u.name + "/grad", (B, E), torch.float32)
@@ -718,19 +760,25 @@ class Engine(object):
         arr = (C.c_float * len(vals))(*[float(v) for v in vals])
         L.check(self.lib.xv_set_scalars(L.ptr(dst), arr, len(vals), L.stream_ptr()))
 
-    def set_hyper(self, lr, momentum=0.0, adam_t=1.0, clip_norm=0.0):
+    def set_hyper(self, lr, momentum=0.0, adam_t=1.0, clip_norm=0.0, flush=True):
         """Host -> device scalars (the learning rate placeholder is fed every step, trainer.py:326,493-494)."""
         if self.capturing:
             return
-        self._set_scalars(self.hyper, [lr, momentum, 0.9, 0.999, 1e-8, adam_t, clip_norm, 0.0])
+        self._hs_host[:8] = [lr, momentum, 0.9, 0.999, 1e-8, adam_t, clip_norm, 0.0]
+        if flush:
+            self._set_scalars(self._hs, self._hs_host)
 
     def set_sched(self, fa, fs):
-        """Margin annealing factors of loss.py:144-147 for the current global_step."""
+        """Margin annealing factors of loss.py:144-147 for the current global_step (one launch also carries the
+        hyper-parameters staged by set_hyper(flush=False))."""
         if self.capturing:
             return
-        self._set_scalars(self.sched, [fa, fs])
+        self._hs_host[8:10] = [fa, fs]
+        self._set_scalars(self._hs, self._hs_host)
 
-    def optimizer_step(self, opt, clip=False):
+    def optimizer_step(self, opt, clip=False, with_l2_loss=False):
+        """Fused L2 + clip + optimizer + bf16 shadow refresh; ``with_l2_loss`` also accumulates the regularisation
+        loss of the (pre-update) parameters into scalars[1], replacing the separate l2_loss() pass."""
         st = self.store
         st.ensure_opt_state(opt)
         gs = None
@@ -740,7 +788,7 @@ class Engine(object):
                       L.ptr(gs), L.stream_ptr())
         self.call(self.lib.xv_opt_step, L.ptr(st.params), L.ptr(st.grads), L.ptr(st.state1), L.ptr(st.state2),
                   L.ptr(st.blk_l2), L.ptr(st.blk_shadow), L.ptr(st.blk_stride), L.ptr(st.shadow), C.c_int64(st.n), opt,
-                  L.ptr(self.hyper), L.ptr(gs), L.stream_ptr())
+                  L.ptr(self.hyper), L.ptr(gs), L.ptr(self.scalars[1:2] if with_l2_loss else None), L.stream_ptr())
 
 
 _default_engine = None
