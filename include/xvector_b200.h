@@ -100,6 +100,22 @@ typedef struct {
   float* gnorm;          /* [M] dLoss/d||x_i|| through the margin term                              */
 } xv_head_args;
 
+/* Optional fusion for a dgrad GEMM (XV_EPI_BF16 producing dX = dLoss/d act(BN(y))): the epilogue also accumulates the
+ * batch-norm backward reductions of the layer that owns y,
+ *   col_sum[n]   += sum_m g,   col_sumsq[n] += sum_m g * (y - mean[n]) * rstd[n],   g = dX * act'(y*scale[n] + shift[n])
+ * (= dbeta / dgamma of tf.layers.batch_normalization), saving the separate xv_bn_act_bwd_reduce pass over y and dX.
+ * act' is 1 for z > 0 and neg_slope otherwise (relu 0, leaky_relu 0.2, identity 1).  y = NULL disables the fusion. */
+typedef struct {
+  const void* y;         /* bf16 [M, ldy]                                                            */
+  int64_t ldy;
+  const float* scale;    /* [N] gamma * rstd                                                         */
+  const float* shift;    /* [N] beta - mean * scale                                                  */
+  const float* mean;     /* [N] batch mean saved by the forward pass                                 */
+  const float* rstd;     /* [N]                                                                      */
+  float neg_slope;
+  int32_t _pad;
+} xv_bn_bwd_args;
+
 typedef struct {
   xv_operand a, b;
   int32_t M, N, K;
@@ -114,6 +130,7 @@ typedef struct {
   float* col_sum;        /* optional [N]: += sum over valid rows of acc (bias excluded)             */
   float* col_sumsq;      /* optional [N]: += sum over valid rows of acc^2                           */
   xv_head_args head;
+  xv_bn_bwd_args bn_bwd; /* XV_EPI_BF16 only; needs col_sum (-> dbeta) and col_sumsq (-> dgamma), N % 32 == 0 */
 } xv_gemm_args;
 
 XV_API int xv_gemm_bf16(const xv_gemm_args* args, void* stream);
@@ -166,10 +183,18 @@ XV_API int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, const fl
  * (model/multitask_v1/pooling.py:9-40): out f32 [B, 2*cpad] = [mean | std]; channels >= c_real read as 0.
  * out_split (optional) = bf16 [B, 6*cpad] = [hi | hi | lo] of out, the A operand of tdnn6_dense.
  * scale != NULL fuses the preceding BN + activation: x is then the pre-BN tensor and a = act(x*scale + shift) is
- * pooled without tdnn5_relu ever being written to HBM. */
+ * pooled without tdnn5_relu ever being written to HBM.
+ * bwd_sums (optional, needs the fused BN and save_mean / save_rstd; not for prelu): f32 [B, 4, cpad] per-(segment,
+ * channel) sums S1..S4 of act'(z), act'(z) a, act'(z) yhat, act'(z) a yhat from which xv_pool_bn_bwd_reduce forms the
+ * BN dgamma / dbeta of that layer without another pass over the activation. */
 XV_API int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int B, int seg_len, int seg_valid,
                              const int32_t* lengths, int c_real, int cpad, int64_t ld, const float* scale,
-                             const float* shift, const float* alpha, int act, void* stream);
+                             const float* shift, const float* alpha, int act, const float* save_mean,
+                             const float* save_rstd, float* bwd_sums, void* stream);
+/* dgamma[c] += sum_b ca S3 + cb S4, dbeta[c] += sum_b ca S1 + cb S2 with (ca, cb) the pooling-gradient coefficients
+ * da_t = ca + cb a_t derived from pooled = [mean | std] and dpooled (model/pooling.py:22-32 backward). */
+XV_API int xv_pool_bn_bwd_reduce(const float* pooled, const float* dpooled, const float* bwd_sums, int B, int seg_valid,
+                                 const int32_t* lengths, int c_real, int cpad, float* dgamma, float* dbeta, void* stream);
 XV_API int xv_stats_pool_bwd(const void* x, const float* pooled, const float* dpooled, void* dx, int B, int seg_len,
                              int seg_valid, const int32_t* lengths, int c_real, int cpad, int64_t ld, void* stream);
 

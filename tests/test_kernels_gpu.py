@@ -128,12 +128,17 @@ def test_stats_pool_forward_backward(use_lengths, fused):
     out = torch.zeros(B, 2 * cpad, device=dev)
     out3 = torch.zeros(B, 6 * cpad, device=dev, dtype=torch.bfloat16)
     nul = L.ptr(None)
+    # saved BN statistics of the producing layer (arbitrary but consistent: yhat = (y - mean) * rstd)
+    mean = (0.1 * torch.randn(cpad, generator=g, device=dev)).contiguous()
+    rstd = (1 + 0.3 * torch.rand(cpad, generator=g, device=dev)).contiguous()
+    sums = torch.full((B, 4, cpad), float("nan"), device=dev)
     if fused:
         L.check(lib.xv_stats_pool_fwd(L.ptr(y), L.ptr(out), L.ptr(out3), B, T, valid, L.ptr(lengths), c_real, cpad,
-                                      C.c_int64(cpad), L.ptr(scale), L.ptr(shift), nul, 1, L.stream_ptr()))
+                                      C.c_int64(cpad), L.ptr(scale), L.ptr(shift), nul, 1, L.ptr(mean), L.ptr(rstd),
+                                      L.ptr(sums), L.stream_ptr()))
     else:
         L.check(lib.xv_stats_pool_fwd(L.ptr(y), L.ptr(out), L.ptr(out3), B, T, valid, L.ptr(lengths), c_real, cpad,
-                                      C.c_int64(cpad), nul, nul, nul, 0, L.stream_ptr()))
+                                      C.c_int64(cpad), nul, nul, nul, 0, nul, nul, nul, L.stream_ptr()))
     got = torch.cat([out[:, :c_real], out[:, cpad:cpad + c_real]], 1).double().cpu()
     assert torch.allclose(got, ref.detach(), rtol=2e-5, atol=2e-6), (got - ref).abs().max()
     assert (out[:, c_real:cpad] == 0).all() and (out[:, cpad + c_real:] == 0).all()
@@ -153,8 +158,6 @@ def test_stats_pool_forward_backward(use_lengths, fused):
         assert (dx.view(B, T, cpad)[:, :, c_real:] == 0).all()
     else:
         # fused: the BN backward of the producing layer evaluates the pooling gradient on the fly
-        mean = torch.zeros(cpad, device=dev)
-        rstd = torch.ones(cpad, device=dev)
         dgamma = torch.zeros(cpad, device=dev)
         dbeta = torch.zeros(cpad, device=dev)
         L.check(lib.xv_bn_act_bwd_reduce(L.ptr(y), nul, L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(rstd), nul, 1,
@@ -164,8 +167,16 @@ def test_stats_pool_forward_backward(use_lengths, fused):
         gz = gx * (z > 0)
         dbeta_ref = gz.sum((0, 1))
         assert torch.allclose(dbeta[:c_real].double().cpu(), dbeta_ref, rtol=1e-3, atol=1e-6), (dbeta[:c_real].double().cpu() - dbeta_ref).abs().max()
-        yh = y.double().view(B, T, cpad)[:, :, :c_real].cpu()          # mean 0, rstd 1 -> yhat = y
+        yh = ((y.double() - mean.double()) * rstd.double()).view(B, T, cpad)[:, :, :c_real].cpu()
         assert torch.allclose(dgamma[:c_real].double().cpu(), (gz * yh).sum((0, 1)), rtol=1e-3, atol=1e-6)
+        # the same reductions from the per-(segment, channel) sums emitted by the forward kernel
+        dgamma2 = torch.zeros(cpad, device=dev)
+        dbeta2 = torch.zeros(cpad, device=dev)
+        L.check(lib.xv_pool_bn_bwd_reduce(L.ptr(out), L.ptr(gp), L.ptr(sums), B, valid, L.ptr(lengths), c_real, cpad,
+                                          L.ptr(dgamma2), L.ptr(dbeta2), L.stream_ptr()))
+        assert torch.allclose(dbeta2[:c_real].double().cpu(), dbeta_ref, rtol=1e-3, atol=2e-6), (dbeta2[:c_real].double().cpu() - dbeta_ref).abs().max()
+        assert torch.allclose(dgamma2[:c_real].double().cpu(), (gz * yh).sum((0, 1)), rtol=1e-3, atol=2e-6)
+        assert float(dbeta2[c_real:].abs().max()) == 0.0 and float(dgamma2[c_real:].abs().max()) == 0.0
         dy = torch.zeros(R, cpad, device=dev, dtype=torch.bfloat16)
         L.check(lib.xv_bn_act_bwd_apply(L.ptr(y), nul, L.ptr(dy), L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(rstd),
                                         L.ptr(dgamma), L.ptr(dbeta), C.c_float(float(ln.sum())), nul, 1, C.c_int64(R), cpad,
@@ -190,7 +201,7 @@ def test_stats_pool_golden(golden_dir):
     out = torch.zeros(B, 2 * Cn, device="cuda")
     nul = L.ptr(None)
     L.check(lib.xv_stats_pool_fwd(L.ptr(xb), L.ptr(out), nul, B, T, T, L.ptr(ln), Cn, Cn, C.c_int64(Cn), nul, nul, nul, 0,
-                                  L.stream_ptr()))
+                                  nul, nul, nul, L.stream_ptr()))
     # exact reference on the bf16-rounded inputs, and the reference's own golden output within bf16 input rounding
     ref_b = O.statistics_pooling(xb.double().view(B, T, Cn).cpu(), ln.long().cpu())
     assert torch.allclose(out.double().cpu(), ref_b, rtol=2e-5, atol=2e-6)

@@ -35,11 +35,16 @@ class HeadArgs(C.Structure):
                 ("lse", C.c_void_p), ("inv_batch", C.c_float), ("gnorm", C.c_void_p)]
 
 
+class BnBwdArgs(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("ldy", C.c_int64), ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p),
+                ("rstd", C.c_void_p), ("neg_slope", C.c_float), ("_pad", C.c_int32)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [("a", Operand), ("b", Operand), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("splits", C.c_int32), ("epilogue", C.c_int32), ("seg_len", C.c_int32), ("seg_valid", C.c_int32),
                 ("accumulate", C.c_int32), ("out", C.c_void_p), ("ldc", C.c_int64), ("bias", C.c_void_p),
-                ("col_sum", C.c_void_p), ("col_sumsq", C.c_void_p), ("head", HeadArgs)]
+                ("col_sum", C.c_void_p), ("col_sumsq", C.c_void_p), ("head", HeadArgs), ("bn_bwd", BnBwdArgs)]
 
 
 _lib = None
@@ -86,7 +91,7 @@ def operand(t, mn_major=False, div=0, tap_rows=0, rows=None, cols=None):
 
 
 def gemm(a_op, b_op, M, N, K, out, epilogue=EPI_BF16, splits=1, bias=None, col_sum=None, col_sumsq=None,
-         seg_len=0, seg_valid=0, head=None, ldc=None, accumulate=False):
+         seg_len=0, seg_valid=0, head=None, ldc=None, accumulate=False, bn_bwd=None):
     args = GemmArgs()
     args.a, args.b = a_op, b_op
     args.M, args.N, args.K = M, N, K
@@ -100,4 +105,10 @@ def gemm(a_op, b_op, M, N, K, out, epilogue=EPI_BF16, splits=1, bias=None, col_s
     args.col_sumsq = 0 if col_sumsq is None else col_sumsq.data_ptr()
     if head is not None:
         args.head = head
+    if bn_bwd is not None:       # (y, scale, shift, mean, rstd, neg_slope): fused BN-backward reductions (dgrad epilogue)
+        y, scale, shift, mean, rstd, neg_slope = bn_bwd
+        args.bn_bwd.y, args.bn_bwd.ldy = y.data_ptr(), y.stride(0)
+        args.bn_bwd.scale, args.bn_bwd.shift = scale.data_ptr(), shift.data_ptr()
+        args.bn_bwd.mean, args.bn_bwd.rstd = mean.data_ptr(), rstd.data_ptr()
+        args.bn_bwd.neg_slope = float(neg_slope)
     check(load().xv_gemm_bf16(C.byref(args), stream_ptr()))

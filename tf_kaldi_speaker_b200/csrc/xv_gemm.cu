@@ -93,6 +93,14 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   kp.accumulate = (a->epilogue == XV_EPI_BF16) ? a->accumulate : 0;
   kp.out = a->out; kp.ldc = a->ldc; kp.bias = a->bias; kp.col_sum = a->col_sum; kp.col_sumsq = a->col_sumsq;
   kp.head = a->head;
+  memset(&kp.bnb, 0, sizeof(kp.bnb));
+  if (a->bn_bwd.y != nullptr) {
+    if (a->epilogue != XV_EPI_BF16 || !a->col_sum || !a->col_sumsq || (a->N % 32) || !a->bn_bwd.scale || !a->bn_bwd.shift ||
+        !a->bn_bwd.mean || !a->bn_bwd.rstd || a->bn_bwd.ldy % 8 || a->bn_bwd.ldy < a->N ||
+        (reinterpret_cast<uintptr_t>(a->bn_bwd.y) & 15))
+      return set_error(XV_ERR_INVALID, "bn_bwd fusion needs the bf16 epilogue, col_sum/col_sumsq, N %% 32 == 0 and a 16-byte aligned y with ldy %% 8 == 0");
+    kp.bnb = a->bn_bwd;
+  }
   // Matrix outputs leave through TMA stores (split-K partials through the TMA reduce-add unit) whenever the layout
   // allows a tensor map; the gradient fan-in mode (read-modify-write of bf16) keeps the direct path.
   kp.use_tma_out = 0;

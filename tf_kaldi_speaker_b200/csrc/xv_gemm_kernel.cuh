@@ -53,6 +53,7 @@ struct alignas(64) GemmKernelParams {
   float* col_sum;
   float* col_sumsq;
   xv_head_args head;
+  xv_bn_bwd_args bnb;     // y != nullptr: BN-backward reductions of the layer whose activation gradient this GEMM emits
 };
 
 // Sum over the 32 lanes of a warp of v[j] for each of 32 columns j, in 31 shuffles (recursive halving).
@@ -329,8 +330,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
         if (EPI == XV_EPI_BF16) {
           if (do_stats) {
             float s[32], q[32];
+            if (p.bnb.y == nullptr) {        // forward: per-column sum / sum of squares of the bias-free accumulator
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { s[j] = row_valid ? v[j] : 0.f; q[j] = s[j] * s[j]; }
+              for (int j = 0; j < 32; ++j) { s[j] = row_valid ? v[j] : 0.f; q[j] = s[j] * s[j]; }
+            } else {
+              // dgrad: v = dLoss/d act(BN(y)).  g = v * act'(z); dbeta += g, dgamma += g * yhat.  Rows >= M carry a zero
+              // accumulator (TMA zero fill) and invalid rows a zero gradient, so only the y loads need the row guard.
+              uint4 yq[4];
+              const uint4* yrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bnb.y) +
+                                                                 static_cast<long long>(m) * p.bnb.ldy + nc0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) yq[j] = row_ok ? __ldg(yrow + j) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 sc4 = __ldg(reinterpret_cast<const float4*>(p.bnb.scale + nc0) + j4);
+                const float4 sh4 = __ldg(reinterpret_cast<const float4*>(p.bnb.shift + nc0) + j4);
+                const float4 mu4 = __ldg(reinterpret_cast<const float4*>(p.bnb.mean + nc0) + j4);
+                const float4 rs4 = __ldg(reinterpret_cast<const float4*>(p.bnb.rstd + nc0) + j4);
+                const uint4 yy = yq[j4 >> 1];
+                const uint32_t w0 = (j4 & 1) ? yy.z : yy.x, w1 = (j4 & 1) ? yy.w : yy.y;
+                const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
+                const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
+                const float yv[4] = {y01.x, y01.y, y23.x, y23.y};
+                const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+                const float muv[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const int j = 4 * j4 + jj;
+                  const float z = fmaf(yv[jj], scv[jj], shv[jj]);
+                  const float g = v[j] * (z > 0.f ? 1.0f : p.bnb.neg_slope);
+                  s[j] = g;
+                  q[j] = g * (yv[jj] - muv[jj]) * rsv[jj];
+                }
+              }
+            }
             warp_column_sums(s, lane);
             warp_column_sums(q, lane);
             atomicAdd(&s_stats[hf * EPI_COLS + c * 32 + lane], s[0]);

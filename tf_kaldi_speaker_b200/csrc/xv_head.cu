@@ -95,22 +95,29 @@ __global__ void head_prep_features_kernel(const float* __restrict__ u, float sca
 }
 
 // lse_i = log sum_j exp(z'_ij) from the per-N-tile (max, sum) partials; loss += sum_i (lse_i - z'_{i,y_i}) * inv_batch
-__global__ void head_combine_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                                    const float* __restrict__ target_logit, int nblk, int B, float inv_batch,
-                                    float* __restrict__ lse, float* __restrict__ loss_rows, float* loss) {
+// One warp per batch row (lanes stride over the partials; the first version walked them serially per thread).
+__global__ void __launch_bounds__(128) head_combine_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                                                           const float* __restrict__ target_logit, int nblk, int B,
+                                                           float inv_batch, float* __restrict__ lse,
+                                                           float* __restrict__ loss_rows, float* loss) {
   __shared__ float sh[32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   float li = 0.f;
   if (i < B) {
     float gmax = -INFINITY;
-    for (int k = 0; k < nblk; ++k) gmax = fmaxf(gmax, part_max[static_cast<long long>(k) * B + i]);
+    for (int k = lane; k < nblk; k += 32) gmax = fmaxf(gmax, part_max[static_cast<long long>(k) * B + i]);
+    for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     float s = 0.f;
-    for (int k = 0; k < nblk; ++k)
+    for (int k = lane; k < nblk; k += 32)
       s += part_sum[static_cast<long long>(k) * B + i] * expf(part_max[static_cast<long long>(k) * B + i] - gmax);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float l = logf(s) + gmax;
-    lse[i] = l;
-    li = l - target_logit[i];
-    if (loss_rows) loss_rows[i] = li;
+    if (lane == 0) {
+      lse[i] = l;
+      li = l - target_logit[i];
+      if (loss_rows) loss_rows[i] = li;
+    }
   }
   const float tot = block_sum(li, sh);
   if (threadIdx.x == 0) atomicAdd(loss, tot * inv_batch);
@@ -212,7 +219,7 @@ extern "C" int xv_head_combine(const float* part_max, const float* part_sum, con
                                float inv_batch, float* lse, float* loss_rows, float* loss, void* stream) {
   if (!part_max || !part_sum || !target_logit || !lse || !loss || nblk <= 0 || B <= 0)
     return set_error(XV_ERR_INVALID, "xv_head_combine: bad arguments");
-  head_combine_kernel<<<ceil_div(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(part_max, part_sum, target_logit,
+  head_combine_kernel<<<ceil_div(B, 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(part_max, part_sum, target_logit,
                                                                                       nblk, B, inv_batch, lse, loss_rows, loss);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;

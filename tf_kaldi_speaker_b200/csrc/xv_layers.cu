@@ -69,18 +69,28 @@ struct PoolGradSrc {
 };
 // ------------------------------------------------------------------------------------------------
 // Input packing: features f32 [B, T, D] -> bf16 im2col rows [B*T, ldo], out[m, j*dpad + c] = x[b, t+j, c].
-__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int T, int D,
-                                  int k, int dpad, long long ldo) {
-  const long long total = static_cast<long long>(B) * T * ldo;
+// One thread per (row m, tap slot j): it converts one feature frame (D floats) into one dpad-wide bf16 slot with
+// 16-byte stores; slots j >= k and channels c >= D are zero padding.  (The first version did four integer divisions
+// and a 2-byte store per ELEMENT: 23 us for 13 MB.)
+__global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B,
+                                                         int T, int D, int k, int dpad, long long ldo) {
+  const int slots = static_cast<int>((ldo + dpad - 1) / dpad);     // the last slot may be narrower than dpad
+  const long long total = static_cast<long long>(B) * T * slots;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / ldo;
-    const int col = static_cast<int>(i % ldo);
-    const int j = col / dpad, c = col % dpad;
-    const int b = static_cast<int>(m / T), t = static_cast<int>(m % T);
-    float v = 0.f;
-    if (j < k && c < D && t + j < T) v = x[(static_cast<long long>(b) * T + t + j) * D + c];
-    out[i] = __float2bfloat16(v);
+    const long long m = i / slots;
+    const int j = static_cast<int>(i - m * slots);
+    const int t = static_cast<int>(m % T);
+    const bool live = j < k && t + j < T;
+    const float* src = x + (m + j) * D;          // frame (b, t + j): rows of one segment are contiguous
+    __nv_bfloat16* dst = out + m * ldo + static_cast<long long>(j) * dpad;
+    const int width = min(dpad, static_cast<int>(ldo - static_cast<long long>(j) * dpad));
+    for (int c0 = 0; c0 < width; c0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = (live && c0 + q < D) ? __ldg(src + c0 + q) : 0.f;
+      store8(dst + c0, f);
+    }
   }
 }
 
@@ -434,60 +444,103 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
 // Statistics pooling (model/pooling.py:22-32; masked form multitask_v1/pooling.py:22-38).
 // grid = (Cpad/256, B); block = 256 = 8 warps striding over time; shifted one-pass moments
 // (shift = first frame) so that var = E[(x-x0)^2] - E[x-x0]^2 does not cancel catastrophically.
+//
+// Training with the fused tdnn5 BN + activation also emits, per (segment, channel), the four sums the BN backward
+// needs.  The pooling gradient is affine in the activation, da_t = ca + cb * a_t (PoolCoef), so with g' = act'(z):
+//   dbeta  = sum_{b,t} da g'          = sum_b ca S1 + cb S2,   S1 = sum_t g',      S2 = sum_t g' a
+//   dgamma = sum_{b,t} da g' yhat     = sum_b ca S3 + cb S4,   S3 = sum_t g' yhat, S4 = sum_t g' a yhat
+// which turns the backward column-reduction pass over the largest activation of the network (78 MB) into a
+// [B, C]-sized kernel (pool_bn_bwd_reduce_kernel).
+template <int N>
+__device__ __forceinline__ void loadN(const __nv_bfloat16* p, float (&f)[N]);
+template <>
+__device__ __forceinline__ void loadN<8>(const __nv_bfloat16* p, float (&f)[8]) { load8(p, f); }
+template <>
+__device__ __forceinline__ void loadN<4>(const __nv_bfloat16* p, float (&f)[4]) { load4(p, f); }
+template <int N>
+__device__ __forceinline__ void loadNf(const float* p, float (&f)[N]);
+template <>
+__device__ __forceinline__ void loadNf<8>(const float* p, float (&f)[8]) { load8f(p, f); }
+template <>
+__device__ __forceinline__ void loadNf<4>(const float* p, float (&f)[4]) { load4f(p, f); }
+
+// CPT = channels per thread (8: 16-byte loads; 4 when the extra sums would push the kernel past 128 registers).
+template <bool BWD_SUMS, int CPT>
 __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ out3, int seg_len,
                                                              int seg_valid, const int* __restrict__ lengths,
                                                              int c_real, int cpad, long long ld,
                                                              const float* __restrict__ scale,
                                                              const float* __restrict__ shift,
-                                                             const float* __restrict__ alpha, int act) {
+                                                             const float* __restrict__ alpha, int act,
+                                                             const float* __restrict__ save_mean,
+                                                             const float* __restrict__ save_rstd,
+                                                             float* __restrict__ bwd_sums) {
   // scale != nullptr: x is the PRE-BN tensor and the pooled quantity is act(x*scale + shift) (fused tdnn5 BN+ReLU)
-  __shared__ float red[8][2][256];
+  constexpr int BC = 32 * CPT;     // channels per block
+  __shared__ float red[8][2][BC];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int c0 = blockIdx.x * BC + lane * CPT;
   const int L = lengths ? lengths[b] : seg_valid;
   const __nv_bfloat16* xb = x + static_cast<long long>(b) * seg_len * ld;
-  float s1[8], s2[8], x0[8];
+  float s1[CPT], s2[CPT], x0[CPT];
+  float q1[CPT], q2[CPT], q3[CPT], q4[CPT];     // dead code (and registers) when !BWD_SUMS
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = x0[j] = 0.f;
+  for (int j = 0; j < CPT; ++j) s1[j] = s2[j] = x0[j] = 0.f;
+  if (BWD_SUMS) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) q1[j] = q2[j] = q3[j] = q4[j] = 0.f;
+  }
   if (c0 < cpad && L > 0) {
-    float sc[8], sh[8], al[8];
+    float sc[CPT], sh[CPT], al[CPT], mu[CPT], rs[CPT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; al[j] = 0.f; }
+    for (int j = 0; j < CPT; ++j) { sc[j] = 1.f; sh[j] = 0.f; al[j] = 0.f; }
     if (scale) {
-      load8f(scale + c0, sc);
-      load8f(shift + c0, sh);
-      if (act == ACT_PRELU) load8f(alpha + c0, al);
+      loadNf<CPT>(scale + c0, sc);
+      loadNf<CPT>(shift + c0, sh);
+      if (act == ACT_PRELU) loadNf<CPT>(alpha + c0, al);
     }
-    load8(xb + c0, x0);
+    if (BWD_SUMS) { loadNf<CPT>(save_mean + c0, mu); loadNf<CPT>(save_rstd + c0, rs); }
+    loadN<CPT>(xb + c0, x0);
     if (scale) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x0[j] = act_fwd(act, fmaf(x0[j], sc[j], sh[j]), al[j]);
+      for (int j = 0; j < CPT; ++j) x0[j] = act_fwd(act, fmaf(x0[j], sc[j], sh[j]), al[j]);
     }
     for (int t = w; t < L; t += 16) {
-      float v[2][8];
+      float v[2][CPT];
       const bool ok1 = (t + 8) < L;
-      load8(xb + static_cast<long long>(t) * ld + c0, v[0]);
-      if (ok1) load8(xb + static_cast<long long>(t + 8) * ld + c0, v[1]);
+      loadN<CPT>(xb + static_cast<long long>(t) * ld + c0, v[0]);
+      if (ok1) loadN<CPT>(xb + static_cast<long long>(t + 8) * ld + c0, v[1]);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         if (u == 1 && !ok1) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = scale ? act_fwd(act, fmaf(v[u][j], sc[j], sh[j]), al[j]) : v[u][j];
+        for (int j = 0; j < CPT; ++j) {
+          const float z = fmaf(v[u][j], sc[j], sh[j]);
+          const float a = scale ? act_fwd(act, z, al[j]) : v[u][j];
           const float d = a - x0[j];
           s1[j] += d;
           s2[j] += d * d;
+          if (BWD_SUMS) {
+            const float gp = act_grad(act, z, al[j]);
+            const float yh = (v[u][j] - mu[j]) * rs[j];
+            const float ga = gp * a;
+            q1[j] += gp;
+            q2[j] += ga;
+            q3[j] = fmaf(gp, yh, q3[j]);
+            q4[j] = fmaf(ga, yh, q4[j]);
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { red[w][0][lane * 8 + j] = s1[j]; red[w][1][lane * 8 + j] = s2[j]; }
+  for (int j = 0; j < CPT; ++j) { red[w][0][lane * CPT + j] = s1[j]; red[w][1][lane * CPT + j] = s2[j]; }
   __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < cpad) {
+  const int c = blockIdx.x * BC + threadIdx.x;
+  const bool c_own = threadIdx.x < BC && c < cpad;
+  if (c_own) {
     float a = 0.f, q = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; q += red[k][1][threadIdx.x]; }
@@ -514,6 +567,56 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
       o3[5 * cpad + c] = __float2bfloat16(sd - __bfloat162float(sh));
     }
   }
+  if (BWD_SUMS) {
+    float* sb = bwd_sums + static_cast<long long>(b) * 4 * cpad;
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        red[w][0][lane * CPT + j] = round ? q3[j] : q1[j];
+        red[w][1][lane * CPT + j] = round ? q4[j] : q2[j];
+      }
+      __syncthreads();
+      if (c_own) {
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; q += red[k][1][threadIdx.x]; }
+        sb[(2 * round) * cpad + c] = (c < c_real) ? a : 0.f;
+        sb[(2 * round + 1) * cpad + c] = (c < c_real) ? q : 0.f;
+      }
+    }
+  }
+}
+
+// BN backward reductions of the layer feeding the statistics pooling, from the per-(segment, channel) sums above:
+// grid = (cpad/256, segment groups); one thread per channel walks its group's segments, one atomic pair per thread.
+__global__ void __launch_bounds__(256) pool_bn_bwd_reduce_kernel(const float* __restrict__ pooled,
+                                                                 const float* __restrict__ dpooled,
+                                                                 const float* __restrict__ sums, int B, int seg_valid,
+                                                                 const int* __restrict__ lengths, int c_real, int cpad,
+                                                                 float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= c_real) return;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(b0 + per, B);
+  float db = 0.f, dg = 0.f;
+  for (int b = b0; b < b1; ++b) {
+    const float invl = 1.0f / (static_cast<float>(lengths ? lengths[b] : seg_valid) + 1e-16f);
+    const float* pb = pooled + static_cast<long long>(b) * 2 * cpad;
+    const float* gb = dpooled + static_cast<long long>(b) * 2 * cpad;
+    const float* sb = sums + static_cast<long long>(b) * 4 * cpad;
+    const float mu = pb[c], sd = pb[cpad + c];
+    float ca = gb[c] * invl, cb = 0.f;
+    if (sd * sd > 1.0000001e-12f) {       // same rule as pool_coef_load
+      cb = gb[cpad + c] * invl / sd;
+      ca -= cb * mu;
+    }
+    db += ca * sb[c] + cb * sb[cpad + c];
+    dg += ca * sb[2 * cpad + c] + cb * sb[3 * cpad + c];
+  }
+  atomicAdd(dbeta + c, db);
+  atomicAdd(dgamma + c, dg);
 }
 
 // dx_t = gmean/L + 1[var>floor] * gstd * (x_t - mean) / (L * std) on valid frames, 0 elsewhere.
@@ -576,9 +679,10 @@ static inline int grid_for(long long work_items, int block, int sms) {
 using namespace xv;
 
 extern "C" int xv_pack_input(const float* x, void* out, int B, int T, int D, int k, int dpad, int64_t ldo, void* stream) {
-  if (!x || !out || B <= 0 || T <= 0 || D <= 0 || D > dpad || k * dpad > ldo) return set_error(XV_ERR_INVALID, "xv_pack_input: bad arguments");
+  if (!x || !out || B <= 0 || T <= 0 || D <= 0 || D > dpad || k * dpad > ldo || dpad % 8 || ldo % 8)
+    return set_error(XV_ERR_INVALID, "xv_pack_input: bad arguments (dpad and ldo must be multiples of 8)");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
-  const long long total = static_cast<long long>(B) * T * ldo;
+  const long long total = static_cast<long long>(B) * T * ((ldo + dpad - 1) / dpad);
   pack_input_kernel<<<grid_for(total, 256, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<__nv_bfloat16*>(out), B, T, D, k, dpad, ldo);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -710,14 +814,35 @@ extern "C" int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, cons
 
 extern "C" int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int B, int seg_len, int seg_valid,
                                  const int32_t* lengths, int c_real, int cpad, int64_t ld, const float* scale,
-                                 const float* shift, const float* alpha, int act, void* stream) {
+                                 const float* shift, const float* alpha, int act, const float* save_mean,
+                                 const float* save_rstd, float* bwd_sums, void* stream) {
   if (scale && (!shift || (act == ACT_PRELU && !alpha))) return set_error(XV_ERR_INVALID, "xv_stats_pool_fwd: fused BN needs shift (and alpha for prelu)");
   if (!x || !out || B <= 0 || seg_len <= 0 || cpad % 8 || c_real > cpad || ld % 8 || ld < cpad)
     return set_error(XV_ERR_INVALID, "xv_stats_pool_fwd: bad arguments");
-  dim3 grid(ceil_div(cpad, 256), B);
-  stats_pool_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), out, static_cast<__nv_bfloat16*>(out_split), seg_len, seg_valid, lengths,
-      c_real, cpad, ld, scale, shift, alpha, act);
+  if (bwd_sums && (!scale || !save_mean || !save_rstd || act == ACT_PRELU))
+    return set_error(XV_ERR_INVALID, "xv_stats_pool_fwd: backward sums need the fused BN (scale, shift, saved mean / rstd) and a non-prelu activation");
+  if (bwd_sums) {
+    dim3 grid(ceil_div(cpad, 128), B);
+    stats_pool_fwd_kernel<true, 4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), out, static_cast<__nv_bfloat16*>(out_split), seg_len, seg_valid, lengths,
+        c_real, cpad, ld, scale, shift, alpha, act, save_mean, save_rstd, bwd_sums);
+  } else {
+    dim3 grid(ceil_div(cpad, 256), B);
+    stats_pool_fwd_kernel<false, 8><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), out, static_cast<__nv_bfloat16*>(out_split), seg_len, seg_valid, lengths,
+        c_real, cpad, ld, scale, shift, alpha, act, nullptr, nullptr, nullptr);
+  }
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_pool_bn_bwd_reduce(const float* pooled, const float* dpooled, const float* bwd_sums, int B, int seg_valid,
+                                     const int32_t* lengths, int c_real, int cpad, float* dgamma, float* dbeta, void* stream) {
+  if (!pooled || !dpooled || !bwd_sums || !dgamma || !dbeta || B <= 0 || c_real <= 0 || c_real > cpad)
+    return set_error(XV_ERR_INVALID, "xv_pool_bn_bwd_reduce: bad arguments");
+  dim3 grid(ceil_div(c_real, 256), B < 16 ? B : 16);
+  pool_bn_bwd_reduce_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, dpooled, bwd_sums, B, seg_valid,
+                                                                                 lengths, c_real, cpad, dgamma, dbeta);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

@@ -28,35 +28,37 @@ __device__ __forceinline__ float uact_grad(int act, float z, float alpha) {
   }
 }
 
-// Block = 32 channels x 8 row groups (256 threads); sums over the B rows are combined through shared memory.
+// Block = 32 channels x UROWG row groups (1024 threads); sums over the B rows are combined through shared memory.
+// (Latency-bound: with 8 row groups a thread walked 16 dependent rows per pass for B = 128.)
+constexpr int UROWG = 32;
 __device__ __forceinline__ float rows_block_sum(float v, float (*red)[32], int tx, int ty) {
   __syncthreads();
   red[ty][tx] = v;
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) t += red[k][tx];
+  for (int k = 0; k < UROWG; ++k) t += red[k][tx];
   return t;
 }
 
 // mode: 0 = no BN (identity), 1 = training (batch statistics over the B rows), 2 = inference (moving stats)
-__global__ void __launch_bounds__(256) bn_rows_fwd_kernel(const float* __restrict__ y, int B, int C, int mode,
+__global__ void __launch_bounds__(32 * UROWG) bn_rows_fwd_kernel(const float* __restrict__ y, int B, int C, int mode,
                                    const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* moving_mean, float* moving_var, float momentum,
                                    float eps, const float* __restrict__ alpha, int act, float* __restrict__ bn_out,
                                    float* __restrict__ a, __nv_bfloat16* __restrict__ a_split, int split_terms,
                                    float* save_mean, float* save_rstd) {
-  __shared__ float red[8][32];
+  __shared__ float red[UROWG][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   const bool ok = c < C;
   float mean = 0.f, rstd = 1.f, g = 1.f, bt = 0.f;
   if (mode == 1) {
     float s = 0.f;
-    if (ok) for (int i = ty; i < B; i += 8) s += y[static_cast<long long>(i) * C + c];
+    if (ok) for (int i = ty; i < B; i += UROWG) s += y[static_cast<long long>(i) * C + c];
     mean = rows_block_sum(s, red, tx, ty) / B;
     float q = 0.f;
-    if (ok) for (int i = ty; i < B; i += 8) { const float d = y[static_cast<long long>(i) * C + c] - mean; q += d * d; }
+    if (ok) for (int i = ty; i < B; i += UROWG) { const float d = y[static_cast<long long>(i) * C + c] - mean; q += d * d; }
     const float var = rows_block_sum(q, red, tx, ty) / B;
     rstd = rsqrtf(var + eps);
     if (ok && ty == 0 && moving_mean) {   // rank-2 tensors take TF's unfused path: biased variance in the moving average
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(256) bn_rows_fwd_kernel(const float* __restric
   if (mode != 0) { g = gamma[c]; bt = beta[c]; }
   if (save_mean && ty == 0) { save_mean[c] = mean; save_rstd[c] = rstd; }
   const float al = (act == ACT_PRELU) ? alpha[c] : 0.f;
-  for (int i = ty; i < B; i += 8) {
+  for (int i = ty; i < B; i += UROWG) {
     const long long idx = static_cast<long long>(i) * C + c;
     const float z = (mode == 0) ? y[idx] : ((y[idx] - mean) * rstd * g + bt);
     if (bn_out) bn_out[idx] = z;
@@ -90,14 +92,14 @@ __global__ void __launch_bounds__(256) bn_rows_fwd_kernel(const float* __restric
 }
 
 // Backward of act(BN(y)) over B rows.  dy in fp32 and bf16 (the latter feeds the dgrad/wgrad GEMMs).
-__global__ void __launch_bounds__(256) bn_rows_bwd_kernel(const float* __restrict__ y, const float* __restrict__ da, int B,
+__global__ void __launch_bounds__(32 * UROWG) bn_rows_bwd_kernel(const float* __restrict__ y, const float* __restrict__ da, int B,
                                    int C, int mode,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
                                    const float* __restrict__ alpha, int act, float* __restrict__ dy,
                                    __nv_bfloat16* __restrict__ dy_bf16, float* dgamma, float* dbeta, float* dalpha,
                                    float* dbias) {
-  __shared__ float red[8][32];
+  __shared__ float red[UROWG][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   const bool ok = c < C;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(256) bn_rows_bwd_kernel(const float* __restric
   const float al = (act == ACT_PRELU && ok) ? alpha[c] : 0.f;
   float sg = 0.f, sgy = 0.f, sal = 0.f;
   if (ok) {
-    for (int i = ty; i < B; i += 8) {
+    for (int i = ty; i < B; i += UROWG) {
       const long long idx = static_cast<long long>(i) * C + c;
       const float yh = (y[idx] - mean) * rstd;
       const float z = (mode == 0) ? y[idx] : (yh * g + bt);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256) bn_rows_bwd_kernel(const float* __restric
   }
   float bias_grad = 0.f;
   if (ok) {
-    for (int i = ty; i < B; i += 8) {
+    for (int i = ty; i < B; i += UROWG) {
       const long long idx = static_cast<long long>(i) * C + c;
       const float yh = (y[idx] - mean) * rstd;
       const float z = (mode == 0) ? y[idx] : (yh * g + bt);
@@ -178,7 +180,7 @@ extern "C" int xv_bn_rows_fwd(const float* y, int B, int C, int mode, const floa
   if (mode == 2 && (!moving_mean || !moving_var)) return set_error(XV_ERR_INVALID, "xv_bn_rows_fwd: inference needs moving stats");
   if (act == ACT_PRELU && !alpha) return set_error(XV_ERR_INVALID, "xv_bn_rows_fwd: prelu needs alpha");
   if (a_split && split_terms != 1 && split_terms != 3) return set_error(XV_ERR_INVALID, "xv_bn_rows_fwd: split_terms must be 1 or 3");
-  bn_rows_fwd_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_rows_fwd_kernel<<<ceil_div(C, 32), 32 * UROWG, 0, static_cast<cudaStream_t>(stream)>>>(
       y, B, C, mode, gamma, beta, moving_mean, moving_var, momentum, eps, alpha, act, bn_out, a,
       static_cast<__nv_bfloat16*>(a_split), split_terms, save_mean, save_rstd);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -191,7 +193,7 @@ extern "C" int xv_bn_rows_bwd(const float* y, const float* da, int B, int C, int
                               float* dbias, void* stream) {
   if (!y || !da || B <= 0 || C <= 0 || mode < 0 || mode > 2) return set_error(XV_ERR_INVALID, "xv_bn_rows_bwd: bad arguments");
   if (mode != 0 && (!gamma || !beta || !save_mean || !save_rstd)) return set_error(XV_ERR_INVALID, "xv_bn_rows_bwd: BN needs saved statistics");
-  bn_rows_bwd_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_rows_bwd_kernel<<<ceil_div(C, 32), 32 * UROWG, 0, static_cast<cudaStream_t>(stream)>>>(
       y, da, B, C, mode, gamma, beta, save_mean, save_rstd, alpha, act, dy, static_cast<__nv_bfloat16*>(dy_bf16),
       dgamma, dbeta, dalpha, dbias);
   XV_CUDA_CHECK(cudaGetLastError());

@@ -227,6 +227,10 @@ class FrameAct(object):
         self.ld = data.shape[1] if data is not None else ld
         self.lazy = None          # (y, scale, shift, alpha, act): BN+activation not applied yet (fused into pooling)
         self.pool_grad = None     # (pooled, dpooled): upstream gradient given implicitly by the statistics pooling
+        self.consumers = 0        # layers reading this tensor (a single consumer lets its dgrad fuse our BN-backward reductions)
+        self.bn_bwd = None        # (y, scale, shift, mean, rstd, neg_slope, dgamma, dbeta) of the layer that produced us
+        self.bn_reduced = False   # dgamma / dbeta already accumulated by the consumer's dgrad epilogue
+        self.pool_sums = None     # [B, 4, C] sums of the fused pooling forward (BN backward reductions without a pass over y)
         self._materialize = None
 
     def materialize(self):
@@ -308,6 +312,7 @@ class Engine(object):
         self.inv_global_batch = None     # set by the data-parallel wrapper (1 / (N * B))
         self.capturing = False           # True while a CUDA graph of the step is being captured
         self.epilogue_stats = True       # False: BN batch statistics from the separate xv_col_stats pass (tests)
+        self.fuse_bn_bwd = True          # dgrad epilogues accumulate the producer layer's BN dgamma / dbeta
 
     # ---- memory
     @property
@@ -426,6 +431,7 @@ class Engine(object):
         if use_stats:
             stats = self.buf(name + "/stats", (2, cout_pad), torch.float32, zero=True)
         xd = x.materialize()
+        x.consumers += 1
         a_op = L.operand(xd, False, div=(x.ld if k > 1 else 0), tap_rows=(1 if k > 1 else 0))
         # BN statistics come out of the GEMM epilogue (warp-shuffle column sums + shared-memory atomics, one global
         # atomic per tile column): +4 us on the K=512 layers against 17-45 us for a separate pass over y.
@@ -469,10 +475,13 @@ class Engine(object):
             aa.data = a
         aa._materialize = apply_now
         if defer_apply:     # the consumer (statistics pooling) applies BN + activation on the fly
-            aa.lazy = (y, scale, shift, alpha_t, act)
+            aa.lazy = (y, scale, shift, alpha_t, act, smean, srstd)
         else:
             apply_now()
 
+        if training and bn is not None and alpha is None and act in (L.ACT_NONE, L.ACT_RELU, L.ACT_LRELU) and lengths is None:
+            neg = {L.ACT_NONE: 1.0, L.ACT_RELU: 0.0, L.ACT_LRELU: 0.2}[act]
+            aa.bn_bwd = (y, scale, shift, smean, srstd, neg, st.grad(bn[0]), st.grad(bn[1]))
         if training:
             def bwd():
                 if aa.grad is None and aa.pool_grad is None:
@@ -486,9 +495,15 @@ class Engine(object):
                     dgamma = self.buf(name + "/dgamma0", (cout_pad,), torch.float32, zero=True)
                     dbeta = st.grad(bias)
                 dalpha = None if alpha is None else st.grad(alpha)
-                self.call(self.lib.xv_bn_act_bwd_reduce, L.ptr(y), L.ptr(aa.grad), L.ptr(scale), L.ptr(shift),
-                          L.ptr(smean), L.ptr(srstd), L.ptr(alpha_t), act, C.c_int64(R), cout_pad, C.c_int64(cout_pad),
-                          x.T, valid, lp, L.ptr(dgamma), L.ptr(dbeta), L.ptr(dalpha), *pool_args, L.stream_ptr())
+                if aa.bn_reduced:
+                    pass        # the consumer's dgrad epilogue already accumulated dgamma / dbeta
+                elif fused and aa.pool_sums is not None and bn is not None:
+                    self.call(self.lib.xv_pool_bn_bwd_reduce, L.ptr(pooled), L.ptr(dpooled), L.ptr(aa.pool_sums), x.B, valid,
+                              lp, cout, cout_pad, L.ptr(dgamma), L.ptr(dbeta), L.stream_ptr())
+                else:
+                    self.call(self.lib.xv_bn_act_bwd_reduce, L.ptr(y), L.ptr(aa.grad), L.ptr(scale), L.ptr(shift),
+                              L.ptr(smean), L.ptr(srstd), L.ptr(alpha_t), act, C.c_int64(R), cout_pad, C.c_int64(cout_pad),
+                              x.T, valid, lp, L.ptr(dgamma), L.ptr(dbeta), L.ptr(dalpha), *pool_args, L.stream_ptr())
                 dy = self.buf(name + "/dy", (R, cout_pad), torch.bfloat16)
                 if bn is not None:
                     dg_used, db_used = dgamma, dbeta
@@ -507,9 +522,16 @@ class Engine(object):
                     # a shared activation (e.g. tdnn4_relu feeding tdnn5 and the attention key net) gets the sum
                     fan_in = x.grad is not None
                     dx = x.grad if fan_in else self.buf(x.name + "/grad", (R, x.ld), torch.bfloat16)
+                    # Sole consumer of x and a K loop long enough to hide it: this dgrad's epilogue also forms the
+                    # BN-backward reductions (dgamma, dbeta) of the layer that produced x from the dX tile it holds.
+                    fuse_bn = (self.fuse_bn_bwd and x.bn_bwd is not None and x.consumers == 1 and not fan_in
+                               and k * cout_pad >= 1024 and x.ld % 32 == 0)
+                    bnb = x.bn_bwd[:6] if fuse_bn else None
                     self.gemm(L.operand(dy, False, div=(cout_pad if k > 1 else 0), tap_rows=(-1 if k > 1 else 0)),
                               L.operand(W, False, div=(cout_pad if k > 1 else 0), tap_rows=(x.ld if k > 1 else 0)),
-                              R, x.ld, k * cout_pad, dx, epilogue=L.EPI_BF16, accumulate=fan_in)
+                              R, x.ld, k * cout_pad, dx, epilogue=L.EPI_BF16, accumulate=fan_in, bn_bwd=bnb,
+                              col_sum=x.bn_bwd[7] if fuse_bn else None, col_sumsq=x.bn_bwd[6] if fuse_bn else None)
+                    x.bn_reduced = fuse_bn
                     x.grad = dx
             self.tape.append(bwd)
             aa.needs_grad = True
@@ -517,16 +539,24 @@ class Engine(object):
 
     def stats_pool(self, x, training):
         cpad = x.ld
+        x.consumers += 1
         out = self.buf("pool/out", (x.B, 2 * cpad), torch.float32)
         out3 = self.buf("pool/out3", (x.B, 6 * cpad), torch.bfloat16)
         if x.lazy is not None:      # fused tdnn5 BN + activation: pool act(y*scale + shift) straight from y
-            y_, scale_, shift_, alpha_, act_ = x.lazy
+            y_, scale_, shift_, alpha_, act_, smean_, srstd_ = x.lazy
+            sums = None
+            if training and act_ != L.ACT_PRELU:
+                # per-(segment, channel) sums that give the BN dgamma / dbeta without another pass over y (78 MB)
+                sums = self.buf("pool/bwd_sums", (x.B, 4, cpad), torch.float32)
+            x.pool_sums = sums
             self.call(self.lib.xv_stats_pool_fwd, L.ptr(y_), L.ptr(out), L.ptr(out3), x.B, x.T, x.valid, x.lengths_ptr(),
-                      x.C, cpad, C.c_int64(cpad), L.ptr(scale_), L.ptr(shift_), L.ptr(alpha_), act_, L.stream_ptr())
+                      x.C, cpad, C.c_int64(cpad), L.ptr(scale_), L.ptr(shift_), L.ptr(alpha_), act_,
+                      L.ptr(smean_ if sums is not None else None), L.ptr(srstd_ if sums is not None else None),
+                      L.ptr(sums), L.stream_ptr())
         else:
             self.call(self.lib.xv_stats_pool_fwd, L.ptr(x.data), L.ptr(out), L.ptr(out3), x.B, x.T, x.valid,
                       x.lengths_ptr(), x.C, cpad, C.c_int64(cpad), L.ptr(None), L.ptr(None), L.ptr(None), 0,
-                      L.stream_ptr())
+                      L.ptr(None), L.ptr(None), L.ptr(None), L.stream_ptr())
         u = UttAct(out, out3, "pool", (x.C, cpad))
         if training:
             def bwd():
@@ -553,6 +583,8 @@ class Engine(object):
         lengths = value.lengths
         lp = L.ptr(lengths)
         kd, vd = key.materialize(), value.materialize()
+        key.consumers += 1
+        value.consumers += 1
         ldk, cpad = key.ld, value.ld
         q = st.view(query)                               # f32 [H, dq]
         dq = q.shape[1]
