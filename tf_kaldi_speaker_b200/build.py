@@ -17,6 +17,7 @@ LIB = os.path.join(HERE, "libxvector_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+CFLAGS += os.environ.get("XV_EXTRA_CFLAGS", "").split()       # tuning sweeps, e.g. XV_EXTRA_CFLAGS="-DXV_RU=4"
 
 
 def _sources():

@@ -1,4 +1,6 @@
 // Error reporting and device queries of the C ABI.
+#include <stdlib.h>
+
 #include "xv_internal.h"
 
 namespace xv {
@@ -25,6 +27,15 @@ int device_sm_count(int* out) {
   }
   *out = cached;
   return XV_OK;
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("XV_PDL");
+    cached = (e && e[0] == '1') ? 1 : 0;     // measured on B200: no gain inside the captured step (1.137 vs 1.131 ms), so opt-in
+  }
+  return cached != 0;
 }
 
 }  // namespace xv

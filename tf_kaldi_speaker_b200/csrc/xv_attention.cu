@@ -52,6 +52,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // query [H, dq] -> qpad [H, ldk]:  non-split: qpad[h, d] = q[h, d] (d < dq);  split: qpad[h, h*dq + d] = q[h, d].
 __global__ void att_expand_query_kernel(const float* __restrict__ q, float* __restrict__ qpad, int H, int dq, int ldk,
                                         int split) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * ldk) return;
   const int h = i / ldk, d = i % ldk;
@@ -61,6 +62,7 @@ __global__ void att_expand_query_kernel(const float* __restrict__ q, float* __re
 // dqpad [H, ldk] -> dq [H, dq] (+=)
 __global__ void att_fold_query_grad_kernel(const float* __restrict__ dqpad, float* __restrict__ dq, int H, int dqn,
                                            int ldk, int split) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * dqn) return;
   const int h = i / dqn, d = i % dqn;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(256) att_scores_fwd_kernel(const __nv_bfloat16
                                                              const float* __restrict__ qpad, float* __restrict__ scores,
                                                              int rows, int seg_len, int seg_valid,
                                                              const int* __restrict__ lengths, int H, int ldk, float scale) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= rows) return;
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(256) att_scores_fwd_kernel(const __nv_bfloat16
 __global__ void __launch_bounds__(256) att_softmax_fwd_kernel(const float* __restrict__ scores, float* __restrict__ w,
                                                               int H, int seg_len, int seg_valid,
                                                               const int* __restrict__ lengths) {
+  pdl_entry();
   __shared__ float red[8];
   __shared__ float bc;
   const int bh = blockIdx.x, b = bh / H;
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(256) att_pool_fwd_kernel(const __nv_bfloat16* 
                                                            int H, int seg_len, int seg_valid,
                                                            const int* __restrict__ lengths, int c_real, int cpad,
                                                            long long ld) {
+  pdl_entry();
   __shared__ float red[8][2][256];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(256) att_pool_bwd_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int H,
                                                            int seg_len, int seg_valid, const int* __restrict__ lengths,
                                                            int c_real, int cpad, long long ld, int accumulate) {
+  pdl_entry();
   extern __shared__ float sm[];       // [3][cpad]: mean | gm | gv
   float* s_mu = sm;
   float* s_gm = sm + cpad;
@@ -317,6 +323,7 @@ __global__ void __launch_bounds__(256) att_pool_bwd_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) att_penalty_fwd_kernel(const float* __restrict__ w, float* __restrict__ gram_out,
                                                               float* __restrict__ penalty, int H, int seg_len,
                                                               int seg_valid, const int* __restrict__ lengths, float coef_over_b) {
+  pdl_entry();
   __shared__ float red[8];
   const int b = blockIdx.x;
   const int L = lengths ? lengths[b] : seg_valid;
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(256) att_softmax_bwd_kernel(const float* __res
                                                               const float* __restrict__ gram, int H, int seg_len,
                                                               int seg_valid, const int* __restrict__ lengths,
                                                               float pen4, float scale) {
+  pdl_entry();
   __shared__ float red[8];
   __shared__ float bc;
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
@@ -387,6 +395,7 @@ __global__ void __launch_bounds__(256) att_scores_bwd_kernel(const __nv_bfloat16
                                                              __nv_bfloat16* __restrict__ dkey, float* __restrict__ dqpad,
                                                              int rows, int seg_len, int seg_valid,
                                                              const int* __restrict__ lengths, int H, int ldk, int accumulate) {
+  pdl_entry();
   extern __shared__ float sred[];     // [8][H][128]
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 128 + lane * 4;
@@ -473,7 +482,7 @@ extern "C" int xv_att_expand_query(const float* query, float* qpad, int H, int d
   if (!query || !qpad || dq <= 0 || ldk % 8 || (split_key ? H * dq : dq) > ldk)
     return set_error(XV_ERR_INVALID, "xv_att_expand_query: bad arguments");
   int rc = att_check_heads("xv_att_expand_query", H); if (rc) return rc;
-  att_expand_query_kernel<<<ceil_div(static_cast<long long>(H) * ldk, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((att_expand_query_kernel), ceil_div(static_cast<long long>(H) * ldk, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       query, qpad, H, dq, ldk, split_key);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -483,7 +492,7 @@ extern "C" int xv_att_fold_query_grad(const float* dqpad, float* dquery, int H, 
   if (!dqpad || !dquery || dq <= 0 || (split_key ? H * dq : dq) > ldk)
     return set_error(XV_ERR_INVALID, "xv_att_fold_query_grad: bad arguments");
   int rc = att_check_heads("xv_att_fold_query_grad", H); if (rc) return rc;
-  att_fold_query_grad_kernel<<<ceil_div(static_cast<long long>(H) * dq, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((att_fold_query_grad_kernel), ceil_div(static_cast<long long>(H) * dq, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       dqpad, dquery, H, dq, ldk, split_key);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -496,7 +505,7 @@ extern "C" int xv_att_scores_fwd(const void* key, const float* qpad, float* scor
   int rc = att_check_heads("xv_att_scores_fwd", H); if (rc) return rc;
   const long long rows = static_cast<long long>(B) * seg_len;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_att_scores_fwd: rows must fit in int32");
-  att_scores_fwd_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((att_scores_fwd_kernel), ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(key), qpad, scores, static_cast<int>(rows), seg_len, seg_valid, lengths, H, ldk, scale);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -506,7 +515,7 @@ extern "C" int xv_att_softmax_fwd(const float* scores, float* weights, int B, in
                                   const int32_t* lengths, void* stream) {
   if (!scores || !weights || B <= 0 || seg_len <= 0) return set_error(XV_ERR_INVALID, "xv_att_softmax_fwd: bad arguments");
   int rc = att_check_heads("xv_att_softmax_fwd", H); if (rc) return rc;
-  att_softmax_fwd_kernel<<<B * H, 256, 0, static_cast<cudaStream_t>(stream)>>>(scores, weights, H, seg_len, seg_valid, lengths);
+  ::xv::launch_pdl((att_softmax_fwd_kernel), B * H, 256, 0, static_cast<cudaStream_t>(stream), scores, weights, H, seg_len, seg_valid, lengths);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
@@ -519,7 +528,7 @@ extern "C" int xv_att_pool_fwd(const void* value, const float* weights, float* o
   int rc = att_check_heads("xv_att_pool_fwd", H); if (rc) return rc;
   if (c_real % H || c_real / H < 8) return set_error(XV_ERR_INVALID, "xv_att_pool_fwd: value dim must be divisible by the heads, >= 8 channels per head");
   dim3 grid(ceil_div(cpad, 256), B);
-  att_pool_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((att_pool_fwd_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(value), weights, out, static_cast<__nv_bfloat16*>(out_split), H, seg_len,
       seg_valid, lengths, c_real, cpad, ld);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -544,7 +553,7 @@ extern "C" int xv_att_pool_bwd(const void* value, const float* weights, const fl
     if (smem > 200 * 1024) return set_error(XV_ERR_UNSUPPORTED, "xv_att_pool_bwd: value dim too large");
   }
   dim3 grid(ceil_div(seg_len, 64), B);
-  att_pool_bwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((att_pool_bwd_kernel), grid, 256, smem, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(value), weights, pooled, dpooled, static_cast<__nv_bfloat16*>(dvalue), dweights, H,
       seg_len, seg_valid, lengths, c_real, cpad, ld, accumulate);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -555,7 +564,7 @@ extern "C" int xv_att_penalty_fwd(const float* weights, float* gram, float* pena
                                   int seg_valid, const int32_t* lengths, float coef, void* stream) {
   if (!weights || !gram || !penalty || B <= 0 || seg_len <= 0) return set_error(XV_ERR_INVALID, "xv_att_penalty_fwd: bad arguments");
   int rc = att_check_heads("xv_att_penalty_fwd", H); if (rc) return rc;
-  att_penalty_fwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(weights, gram, penalty, H, seg_len, seg_valid,
+  ::xv::launch_pdl((att_penalty_fwd_kernel), B, 256, 0, static_cast<cudaStream_t>(stream), weights, gram, penalty, H, seg_len, seg_valid,
                                                                             lengths, coef / static_cast<float>(B));
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -565,7 +574,7 @@ extern "C" int xv_att_softmax_bwd(const float* weights, float* dweights, const f
                                   int seg_valid, const int32_t* lengths, float penalty_coef, float scale, void* stream) {
   if (!weights || !dweights || B <= 0 || seg_len <= 0) return set_error(XV_ERR_INVALID, "xv_att_softmax_bwd: bad arguments");
   int rc = att_check_heads("xv_att_softmax_bwd", H); if (rc) return rc;
-  att_softmax_bwd_kernel<<<B * H, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((att_softmax_bwd_kernel), B * H, 256, 0, static_cast<cudaStream_t>(stream), 
       weights, dweights, gram, H, seg_len, seg_valid, lengths, 4.0f * penalty_coef / static_cast<float>(B), scale);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -588,7 +597,7 @@ extern "C" int xv_att_scores_bwd(const void* key, const float* qpad, const float
     }
   }
   dim3 grid(ceil_div(ldk, 128), ceil_div(rows, 64));
-  att_scores_bwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((att_scores_bwd_kernel), grid, 256, smem, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(key), qpad, dscores, static_cast<__nv_bfloat16*>(dkey), dqpad,
       static_cast<int>(rows), seg_len, seg_valid, lengths, H, ldk, accumulate);
   XV_CUDA_CHECK(cudaGetLastError());

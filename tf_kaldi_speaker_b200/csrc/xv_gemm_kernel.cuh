@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();      // the next kernel of the stream may be scheduled as SMs free up
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("xv: dynamic shared memory base is not 1024-byte aligned (0x%x)\n", smem_u32(smem));
     __trap();
@@ -171,6 +172,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Everything above (barrier init, TMEM allocation, tensor-map prefetch) is independent of earlier kernels; global
+  // memory is first touched below, after the previous kernel of the stream has completed.
+  pdl_wait();
 
   const int total_tiles = p.num_m * p.num_n * p.splits;
 
@@ -596,7 +600,7 @@ int launch_gemm(const GemmKernelParams& kp, int grid, cudaStream_t stream) {
     XV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(kp);
+  launch_pdl(kern, grid, NUM_THREADS, SMEM_BYTES, stream, kp);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

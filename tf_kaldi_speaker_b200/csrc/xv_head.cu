@@ -26,6 +26,7 @@ constexpr int HROWG = 32;
 __global__ void __launch_bounds__(32 * HROWG) head_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wn3,
                                                                 float* __restrict__ inv_norm, int E, int C, long long ldw,
                                                                 int normalize) {
+  pdl_entry();
   __shared__ float red[HROWG][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + tx * 2;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(32 * HROWG) head_prep_weights_kernel(const flo
 __global__ void head_prep_features_kernel(const float* __restrict__ u, float scaling, float* __restrict__ x,
                                           __nv_bfloat16* __restrict__ x3, float* __restrict__ xnorm,
                                           float* __restrict__ u_rinv, int E) {
+  pdl_entry();
   __shared__ float sh[32];
   const int i = blockIdx.x;
   const float* ur = u + static_cast<long long>(i) * E;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(128) head_combine_kernel(const float* __restri
                                                            const float* __restrict__ target_logit, int nblk, int B,
                                                            float inv_batch, float* __restrict__ lse,
                                                            float* __restrict__ loss_rows, float* loss) {
+  pdl_entry();
   __shared__ float sh[32];
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -128,6 +131,7 @@ __global__ void head_finish_dx_kernel(const float* __restrict__ dxg, const float
                                       const float* __restrict__ x, const float* __restrict__ xnorm,
                                       const float* __restrict__ u, const float* __restrict__ u_rinv, float scaling,
                                       float* __restrict__ du, int E) {
+  pdl_entry();
   __shared__ float sh[32];
   const int i = blockIdx.x;
   const long long off = static_cast<long long>(i) * E;
@@ -158,6 +162,7 @@ __global__ void head_finish_dx_kernel(const float* __restrict__ dxg, const float
 // dW_j = (dWn_j - wn_j <wn_j, dWn_j>) * inv_norm_j   (in place on the gradient buffer); same 64 x 8 blocking.
 __global__ void __launch_bounds__(32 * HROWG) head_finish_dw_kernel(float* __restrict__ dw, const float* __restrict__ w,
                                                                     const float* __restrict__ inv_norm, int E, int C) {
+  pdl_entry();
   __shared__ float red[HROWG][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + tx * 2;
@@ -199,7 +204,7 @@ using namespace xv;
 extern "C" int xv_head_prep_weights(const float* w, void* wn3, float* inv_norm, int E, int C, int64_t ldw, int normalize,
                                     void* stream) {
   if (!w || !wn3 || E <= 0 || C <= 0 || (C & 1) || ldw < C || ldw % 8) return set_error(XV_ERR_INVALID, "xv_head_prep_weights: bad arguments (C must be even, ldw a multiple of 8)");
-  head_prep_weights_kernel<<<ceil_div(C, 64), 32 * HROWG, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((head_prep_weights_kernel), ceil_div(C, 64), 32 * HROWG, 0, static_cast<cudaStream_t>(stream), 
       w, static_cast<__nv_bfloat16*>(wn3), inv_norm, E, C, ldw, normalize);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -209,7 +214,7 @@ extern "C" int xv_head_prep_features(const float* u, float scaling, float* x, vo
                                      int B, int E, void* stream) {
   if (!u || !x3 || B <= 0 || E <= 0) return set_error(XV_ERR_INVALID, "xv_head_prep_features: bad arguments");
   if (scaling > 0.f && !u_rinv) return set_error(XV_ERR_INVALID, "xv_head_prep_features: feature_norm needs u_rinv");
-  head_prep_features_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(u, scaling, x, static_cast<__nv_bfloat16*>(x3),
+  ::xv::launch_pdl((head_prep_features_kernel), B, 128, 0, static_cast<cudaStream_t>(stream), u, scaling, x, static_cast<__nv_bfloat16*>(x3),
                                                                               xnorm, u_rinv, E);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -219,7 +224,7 @@ extern "C" int xv_head_combine(const float* part_max, const float* part_sum, con
                                float inv_batch, float* lse, float* loss_rows, float* loss, void* stream) {
   if (!part_max || !part_sum || !target_logit || !lse || !loss || nblk <= 0 || B <= 0)
     return set_error(XV_ERR_INVALID, "xv_head_combine: bad arguments");
-  head_combine_kernel<<<ceil_div(B, 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(part_max, part_sum, target_logit,
+  ::xv::launch_pdl((head_combine_kernel), ceil_div(B, 4), 128, 0, static_cast<cudaStream_t>(stream), part_max, part_sum, target_logit,
                                                                                       nblk, B, inv_batch, lse, loss_rows, loss);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -230,14 +235,14 @@ extern "C" int xv_head_finish_dx(const float* dx_gemm, const float* gnorm, const
   if (!dx_gemm || !du || B <= 0 || E <= 0) return set_error(XV_ERR_INVALID, "xv_head_finish_dx: bad arguments");
   if (gnorm && (!x || !xnorm)) return set_error(XV_ERR_INVALID, "xv_head_finish_dx: margin term needs x and xnorm");
   if (scaling > 0.f && (!u || !u_rinv || !x)) return set_error(XV_ERR_INVALID, "xv_head_finish_dx: feature_norm needs u, u_rinv, x");
-  head_finish_dx_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(dx_gemm, gnorm, x, xnorm, u, u_rinv, scaling, du, E);
+  ::xv::launch_pdl((head_finish_dx_kernel), B, 128, 0, static_cast<cudaStream_t>(stream), dx_gemm, gnorm, x, xnorm, u, u_rinv, scaling, du, E);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
 
 extern "C" int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, int E, int C, void* stream) {
   if (!dw || !w || !inv_norm || E <= 0 || C <= 0 || (C & 1)) return set_error(XV_ERR_INVALID, "xv_head_finish_dw: bad arguments (C must be even)");
-  head_finish_dw_kernel<<<ceil_div(C, 64), 32 * HROWG, 0, static_cast<cudaStream_t>(stream)>>>(dw, w, inv_norm, E, C);
+  ::xv::launch_pdl((head_finish_dw_kernel), ceil_div(C, 64), 32 * HROWG, 0, static_cast<cudaStream_t>(stream), dw, w, inv_norm, E, C);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

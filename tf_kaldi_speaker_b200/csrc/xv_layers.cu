@@ -74,6 +74,7 @@ struct PoolGradSrc {
 // and a 2-byte store per ELEMENT: 23 us for 13 MB.)
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B,
                                                          int T, int D, int k, int dpad, long long ldo) {
+  pdl_entry();
   const int slots = static_cast<int>((ldo + dpad - 1) / dpad);     // the last slot may be narrower than dpad
   const long long total = static_cast<long long>(B) * T * slots;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -101,6 +102,7 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ col_sum, cons
                                          const float* __restrict__ beta, float* moving_mean, float* moving_var,
                                          float momentum, float eps, int unbiased, float* scale, float* shift,
                                          float* save_mean, float* save_rstd, int C) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float mean_nb = col_sum[c] / count;                       // mean of the bias-free accumulator
@@ -121,6 +123,7 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ col_sum, cons
 __global__ void bn_finalize_infer_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                          const float* __restrict__ mm, const float* __restrict__ mv, float eps,
                                          float* scale, float* shift, int C) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] * rsqrtf(mv[c] + eps);
@@ -132,10 +135,19 @@ __global__ void bn_finalize_infer_kernel(const float* __restrict__ gamma, const 
 // a warp covers 128 channels (4 per lane, one 8-byte vector) and walks rows w, w+8, ... of its chunk two at a time.
 // Every per-channel constant (scale, shift, mean, rstd, dgamma, dbeta, alpha) is loaded ONCE per thread, and four
 // channels per thread keep the kernels under 64-80 registers so that 3-4 blocks (24-32 warps) stay resident per SM.
-constexpr int STREAM_ROWS = 64;
+#ifndef XV_STREAM_ROWS
+#define XV_STREAM_ROWS 64
+#endif
+#ifndef XV_RU
+#define XV_RU 2
+#endif
+#ifndef XV_FU
+#define XV_FU 4
+#endif
+constexpr int STREAM_ROWS = XV_STREAM_ROWS;
 constexpr int SV = 4;                 // channels per thread
 constexpr int SCH = 32 * SV;          // channels per warp / block column
-constexpr int RU = 2;                 // rows a warp keeps in flight per tensor (8 in flight measured SLOWER in the step:
+constexpr int RU = XV_RU;               // rows a warp keeps in flight per tensor (8 in flight measured SLOWER in the step:
                                       // 125 registers -> 2 blocks/SM and no load/compute overlap inside a block)
 
 __device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&f)[4]) {
@@ -167,11 +179,15 @@ struct RowGrid {
   int seg_len, chunks, rows_per_chunk;   // seg_len = rows when the tensor has no segment structure
   int col_groups;                        // channel groups of SCH channels; blockIdx.x = row_chunk * col_groups + group
 };
-static inline RowGrid make_row_grid(long long rows, int seg_len, int C) {
+// Kernels that evaluate the pooling gradient on the fly load 4 x 8 per-(segment, channel) coefficients per thread and
+// block: longer row chunks amortise them (64-row chunks made the coefficient traffic equal to the data traffic).
+constexpr int FUSED_STREAM_ROWS = 128;
+static inline RowGrid make_row_grid(long long rows, int seg_len, int C, int group_channels = SCH,
+                                    int stream_rows = STREAM_ROWS) {
   RowGrid g;
-  g.col_groups = (C + SCH - 1) / SCH;
+  g.col_groups = (C + group_channels - 1) / group_channels;
   g.seg_len = seg_len > 0 ? seg_len : static_cast<int>(rows);
-  g.chunks = (g.seg_len + STREAM_ROWS - 1) / STREAM_ROWS;
+  g.chunks = (g.seg_len + stream_rows - 1) / stream_rows;
   g.rows_per_chunk = (g.seg_len + g.chunks - 1) / g.chunks;
   return g;
 }
@@ -220,40 +236,73 @@ __device__ __forceinline__ void pool_coef_load(PoolCoef& pc, const PoolGradSrc& 
   }
 }
 
+// ---- wide row-streaming kernels (BN apply / backward): 8 channels per thread (16-byte accesses), a block column of
+// WCH = 256 channels, row pointers advanced by adds.  ncu on the first 4-channel versions: ~29 issued instructions per
+// element (64-bit address multiplies and row bookkeeping amortised over 4 elements), issue slots 45 % busy at 35 %
+// occupancy -- the kernels were instruction-bound at ~2.5 TB/s, not memory-bound.
+constexpr int WV = 8;
+constexpr int WCH = 32 * WV;
+// Rows in flight per warp, from the sweep in tools/layers_bench.py on B200 (C = 512 / 1536, HBM-streaming):
+//   plain kernels: 1 row (17 / 25 / 39 / 58 us) beats 2 (26 / 30 / 64 / 76) and 4 -- fewer registers, more resident warps;
+//   fused-pooling kernels: 4 rows (49 us) beat 2 (56) and 1 (68) -- they amortise the per-block coefficient loads.
+#ifndef XV_WROWS
+#define XV_WROWS 1
+#endif
+#ifndef XV_WROWS_FUSED
+#define XV_WROWS_FUSED 4
+#endif
+
+struct WideBlock {
+  int c0, w, lane, cgroup;
+  RowChunk rc;
+};
+__device__ __forceinline__ WideBlock wide_block(const RowGrid& rg, int seg_len, int seg_valid, const int* lengths) {
+  WideBlock b;
+  b.lane = threadIdx.x & 31;
+  b.w = threadIdx.x >> 5;
+  b.cgroup = blockIdx.x % rg.col_groups;
+  b.c0 = b.cgroup * WCH + b.lane * WV;
+  b.rc = row_chunk(blockIdx.x / rg.col_groups, rg, seg_len, seg_valid, lengths);
+  return b;
+}
+
 // a = act(y*scale + shift) on valid rows, 0 on invalid rows.
 template <int ACT>
 __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ alpha, RowGrid rg, int C, long long ld,
                                     int seg_len, int seg_valid, const int* __restrict__ lengths) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int cg_ = blockIdx.x % rg.col_groups, by_ = blockIdx.x / rg.col_groups;
-  const int c0 = cg_ * SCH + lane * SV;
+  pdl_entry();
+  const WideBlock wb = wide_block(rg, seg_len, seg_valid, lengths);
+  const int c0 = wb.c0;
   if (c0 >= C) return;
-  const RowChunk rc = row_chunk(by_, rg, seg_len, seg_valid, lengths);
-  float sc[SV], sh[SV], al[SV];
-  load4f(scale + c0, sc);
-  load4f(shift + c0, sh);
+  const RowChunk rc = wb.rc;
+  float sc[WV], sh[WV], al[WV];
+  load8f(scale + c0, sc);
+  load8f(shift + c0, sh);
 #pragma unroll
-  for (int j = 0; j < SV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
-  constexpr int FU = 4;      // rows in flight per warp
-  for (int t = rc.t0 + w; t < rc.t1; t += 8 * FU) {
-    float v[FU][SV];
-    bool in[FU], valid[FU];
+  for (int j = 0; j < WV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+  const long long step = 8 * ld;
+  const __nv_bfloat16* yp = y + (rc.m_base + rc.t0 + wb.w) * ld + c0;
+  __nv_bfloat16* ap = a + (rc.m_base + rc.t0 + wb.w) * ld + c0;
+  constexpr int WROWS = XV_WROWS;
+  for (int t = rc.t0 + wb.w; t < rc.t1; t += 8 * WROWS, yp += WROWS * step, ap += WROWS * step) {
+    float v[WROWS][WV];
+    bool in[WROWS], valid[WROWS];
 #pragma unroll
-    for (int u = 0; u < FU; ++u) {
+    for (int u = 0; u < WROWS; ++u) {
       const int tt = t + 8 * u;
       in[u] = tt < rc.t1;
       valid[u] = tt < rc.t1 && tt < rc.L;
-      if (valid[u]) load4(y + (rc.m_base + tt) * ld + c0, v[u]);
+      if (valid[u]) load8(yp + u * step, v[u]);
     }
 #pragma unroll
-    for (int u = 0; u < FU; ++u) {
+    for (int u = 0; u < WROWS; ++u) {
       if (!in[u]) continue;
-      float o[SV];
+      float o[WV];
 #pragma unroll
-      for (int j = 0; j < SV; ++j) o[j] = valid[u] ? actf<ACT>(fmaf(v[u][j], sc[j], sh[j]), al[j]) : 0.f;
-      store4(a + (rc.m_base + t + 8 * u) * ld + c0, o);
+      for (int j = 0; j < WV; ++j) o[j] = valid[u] ? actf<ACT>(fmaf(v[u][j], sc[j], sh[j]), al[j]) : 0.f;
+      store8(ap + u * step, o);
     }
   }
 }
@@ -263,6 +312,7 @@ __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
                                                         RowGrid rg, int C, long long ld, int seg_len, int seg_valid,
                                                         const int* __restrict__ lengths, float* col_sum, float* col_sumsq) {
+  pdl_entry();
   __shared__ float red[8][2][SCH];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int cg_ = blockIdx.x % rg.col_groups, by_ = blockIdx.x / rg.col_groups;
@@ -310,6 +360,29 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
   }
 }
 
+// Per-(segment, channel) coefficients of the on-the-fly pooling gradient, 8 channels: da = ca + cb * a.
+struct PoolCoef8 { float ca[WV], cb[WV]; };
+__device__ __forceinline__ void pool_coef_load8(PoolCoef8& pc, const PoolGradSrc& ps, int b, int c0, int L) {
+  const float invl = 1.0f / (static_cast<float>(L) + 1e-16f);
+  float mu[WV], sd[WV], gm[WV], gs[WV];
+  const float* pb = ps.pooled + static_cast<long long>(b) * 2 * ps.cpad;
+  const float* gb = ps.dpooled + static_cast<long long>(b) * 2 * ps.cpad;
+  load8f(pb + c0, mu); load8f(pb + ps.cpad + c0, sd); load8f(gb + c0, gm); load8f(gb + ps.cpad + c0, gs);
+#pragma unroll
+  for (int j = 0; j < WV; ++j) {
+    float ca = 0.f, cb = 0.f;
+    if (c0 + j < ps.c_real) {
+      ca = gm[j] * invl;
+      if (sd[j] * sd[j] > 1.0000001e-12f) {       // variance above the 1e-12 floor: gradient flows through std
+        cb = gs[j] * invl / sd[j];
+        ca -= cb * mu[j];
+      }
+    }
+    pc.ca[j] = ca;
+    pc.cb[j] = cb;
+  }
+}
+
 // Column reductions for the BN backward: dbeta += sum g, dgamma += sum g*yhat, dalpha += sum da*min(z,0).
 template <bool FUSED_POOL, int ACT>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
@@ -317,70 +390,80 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const float* __restrict__ shift, const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
     const float* __restrict__ alpha, RowGrid rg, int C, long long ld, int seg_len, int seg_valid,
     const int* __restrict__ lengths, float* dgamma, float* dbeta, float* dalpha, PoolGradSrc ps) {
-  __shared__ float red[8][3][SCH];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int cg_ = blockIdx.x % rg.col_groups, by_ = blockIdx.x / rg.col_groups;
-  const int c0 = cg_ * SCH + lane * SV;
+  pdl_entry();
+  constexpr int WROWS = FUSED_POOL ? XV_WROWS_FUSED : XV_WROWS;
+  __shared__ float red[8][WCH];
+  const WideBlock wb = wide_block(rg, seg_len, seg_valid, lengths);
+  const int c0 = wb.c0, lane = wb.lane, w = wb.w;
   const bool c_ok = c0 < C;
-  float sg[SV], sgy[SV], sal[SV];
+  float sg[WV], sgy[WV], sal[WV];
 #pragma unroll
-  for (int j = 0; j < SV; ++j) sg[j] = sgy[j] = sal[j] = 0.f;
+  for (int j = 0; j < WV; ++j) sg[j] = sgy[j] = sal[j] = 0.f;
   if (c_ok) {
-    float sc[SV], sh[SV], mu[SV], rs[SV], al[SV];
-    load4f(scale + c0, sc); load4f(shift + c0, sh); load4f(save_mean + c0, mu); load4f(save_rstd + c0, rs);
+    const RowChunk rc = wb.rc;
+    float sc[WV], sh[WV], mu[WV], al[WV];
+    load8f(scale + c0, sc); load8f(shift + c0, sh); load8f(save_mean + c0, mu);
 #pragma unroll
-    for (int j = 0; j < SV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
-    const RowChunk rc = row_chunk(by_, rg, seg_len, seg_valid, lengths);
-    PoolCoef pc;
-    pc.b = -1;
-    if (FUSED_POOL) pool_coef_load(pc, ps, rc.b, c0, seg_valid, lengths);
+    for (int j = 0; j < WV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+    PoolCoef8 pc;
+    if (FUSED_POOL) pool_coef_load8(pc, ps, rc.b, c0, rc.L);
     const int t1 = min(rc.t1, rc.L);
-    for (int t = rc.t0 + w; t < t1; t += 8 * RU) {
-      float v[RU][SV], d[RU][SV];
-      bool ok[RU];
+    const long long step = 8 * ld;
+    const long long off = (rc.m_base + rc.t0 + w) * ld + c0;
+    const __nv_bfloat16* yp = y + off;
+    const __nv_bfloat16* dp = FUSED_POOL ? nullptr : da + off;
+    for (int t = rc.t0 + w; t < t1; t += 8 * WROWS, yp += WROWS * step) {
+      float v[WROWS][WV], d[WROWS][WV];
+      bool ok[WROWS];
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const int tt = t + 8 * u;
-        ok[u] = tt < t1;
+      for (int u = 0; u < WROWS; ++u) {
+        ok[u] = t + 8 * u < t1;
         if (ok[u]) {
-          load4(y + (rc.m_base + tt) * ld + c0, v[u]);
-          if (!FUSED_POOL) load4(da + (rc.m_base + tt) * ld + c0, d[u]);
+          load8(yp + u * step, v[u]);
+          if (!FUSED_POOL) load8(dp + u * step, d[u]);
         }
       }
+      if (!FUSED_POOL) dp += WROWS * step;
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {
+      for (int u = 0; u < WROWS; ++u) {
         if (!ok[u]) continue;
 #pragma unroll
-        for (int j = 0; j < SV; ++j) {
+        for (int j = 0; j < WV; ++j) {
           const float z = fmaf(v[u][j], sc[j], sh[j]);
           const float dd = FUSED_POOL ? fmaf(pc.cb[j], actf<ACT>(z, al[j]), pc.ca[j]) : d[u][j];
           const float g = dd * actg<ACT>(z, al[j]);
           sg[j] += g;
-          sgy[j] += g * (v[u][j] - mu[j]) * rs[j];
-          if (ACT == ACT_PRELU) sal[j] += dd * fminf(z, 0.f);
+          sgy[j] = fmaf(g, v[u][j] - mu[j], sgy[j]);      // * rstd once, below
+          if (ACT == ACT_PRELU) sal[j] = fmaf(dd, fminf(z, 0.f), sal[j]);
         }
       }
     }
-  }
+    float rs[WV];
+    load8f(save_rstd + c0, rs);
 #pragma unroll
-  for (int j = 0; j < SV; ++j) {
-    red[w][0][lane * SV + j] = sg[j];
-    red[w][1][lane * SV + j] = sgy[j];
-    red[w][2][lane * SV + j] = sal[j];
+    for (int j = 0; j < WV; ++j) sgy[j] *= rs[j];
   }
-  __syncthreads();
-  const int c = cg_ * SCH + threadIdx.x;
-  if (threadIdx.x < SCH && c < C) {
-    float a = 0.f, b = 0.f, d = 0.f;
+  // three passes through one [8][WCH] staging tile: dbeta, dgamma, (dalpha)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; b += red[k][1][threadIdx.x]; d += red[k][2][threadIdx.x]; }
-    atomicAdd(dbeta + c, a);
-    atomicAdd(dgamma + c, b);
-    if (ACT == ACT_PRELU && dalpha) atomicAdd(dalpha + c, d);
+  for (int pass = 0; pass < (ACT == ACT_PRELU ? 3 : 2); ++pass) {
+    if (pass) __syncthreads();
+#pragma unroll
+    for (int j = 0; j < WV; ++j) red[w][lane * WV + j] = pass == 0 ? sg[j] : (pass == 1 ? sgy[j] : sal[j]);
+    __syncthreads();
+    const int c = wb.cgroup * WCH + threadIdx.x;
+    if (c < C) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[k][threadIdx.x];
+      if (pass == 0) atomicAdd(dbeta + c, a);
+      else if (pass == 1) atomicAdd(dgamma + c, a);
+      else if (dalpha) atomicAdd(dalpha + c, a);
+    }
   }
 }
 
-// dy = scale * (g - dbeta/n - yhat*dgamma/n) on valid rows, 0 elsewhere (scale = gamma*rstd).
+// dy = scale * (g - dbeta/n - yhat*dgamma/n) on valid rows, 0 elsewhere (scale = gamma*rstd), evaluated as
+// dy = scale*g + A*y + Bc with A = -scale*rstd*dgamma/n and Bc = -scale*dbeta/n - A*mean (per-channel constants).
 template <bool FUSED_POOL, int ACT>
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dy,
@@ -388,54 +471,62 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const float* __restrict__ save_rstd, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
     float inv_count, const float* __restrict__ alpha, RowGrid rg, int C, long long ld, int seg_len,
     int seg_valid, const int* __restrict__ lengths, PoolGradSrc ps) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int cg_ = blockIdx.x % rg.col_groups, by_ = blockIdx.x / rg.col_groups;
-  const int c0 = cg_ * SCH + lane * SV;
+  pdl_entry();
+  constexpr int WROWS = FUSED_POOL ? XV_WROWS_FUSED : XV_WROWS;
+  const WideBlock wb = wide_block(rg, seg_len, seg_valid, lengths);
+  const int c0 = wb.c0;
   if (c0 >= C) return;
-  float sc[SV], sh[SV], mu[SV], rs[SV], dg[SV], db[SV], al[SV];
-  load4f(scale + c0, sc); load4f(shift + c0, sh); load4f(save_mean + c0, mu); load4f(save_rstd + c0, rs);
-  load4f(dgamma + c0, dg); load4f(dbeta + c0, db);
+  const RowChunk rc = wb.rc;
+  float sc[WV], sh[WV], ka[WV], kb[WV], al[WV];
+  load8f(scale + c0, sc); load8f(shift + c0, sh);
+  {
+    float mu[WV], rs[WV], dg[WV], db[WV];
+    load8f(save_mean + c0, mu); load8f(save_rstd + c0, rs); load8f(dgamma + c0, dg); load8f(dbeta + c0, db);
 #pragma unroll
-  for (int j = 0; j < SV; ++j) {
-    al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
-    dg[j] *= inv_count;
-    db[j] *= inv_count;
+    for (int j = 0; j < WV; ++j) {
+      ka[j] = -sc[j] * rs[j] * dg[j] * inv_count;
+      kb[j] = -sc[j] * db[j] * inv_count - ka[j] * mu[j];
+      al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+    }
   }
-  const RowChunk rc = row_chunk(by_, rg, seg_len, seg_valid, lengths);
-  PoolCoef pc;
-  pc.b = -1;
-  if (FUSED_POOL) pool_coef_load(pc, ps, rc.b, c0, seg_valid, lengths);
-  for (int t = rc.t0 + w; t < rc.t1; t += 8 * RU) {
-    float v[RU][SV], d[RU][SV];
-    bool in[RU], valid[RU];
+  PoolCoef8 pc;
+  if (FUSED_POOL) pool_coef_load8(pc, ps, rc.b, c0, rc.L);
+  const long long step = 8 * ld;
+  const long long off = (rc.m_base + rc.t0 + wb.w) * ld + c0;
+  const __nv_bfloat16* yp = y + off;
+  const __nv_bfloat16* dp = FUSED_POOL ? nullptr : da + off;
+  __nv_bfloat16* op = dy + off;
+  for (int t = rc.t0 + wb.w; t < rc.t1; t += 8 * WROWS, yp += WROWS * step, op += WROWS * step) {
+    float v[WROWS][WV], d[WROWS][WV];
+    bool in[WROWS], valid[WROWS];
 #pragma unroll
-    for (int u = 0; u < RU; ++u) {
+    for (int u = 0; u < WROWS; ++u) {
       const int tt = t + 8 * u;
       in[u] = tt < rc.t1;
       valid[u] = tt < rc.t1 && tt < rc.L;
       if (valid[u]) {
-        load4(y + (rc.m_base + tt) * ld + c0, v[u]);
-        if (!FUSED_POOL) load4(da + (rc.m_base + tt) * ld + c0, d[u]);
+        load8(yp + u * step, v[u]);
+        if (!FUSED_POOL) load8(dp + u * step, d[u]);
       }
     }
+    if (!FUSED_POOL) dp += WROWS * step;
 #pragma unroll
-    for (int u = 0; u < RU; ++u) {
+    for (int u = 0; u < WROWS; ++u) {
       if (!in[u]) continue;
-      float o[SV];
+      float o[WV];
       if (valid[u]) {
 #pragma unroll
-        for (int j = 0; j < SV; ++j) {
+        for (int j = 0; j < WV; ++j) {
           const float z = fmaf(v[u][j], sc[j], sh[j]);
           const float dd = FUSED_POOL ? fmaf(pc.cb[j], actf<ACT>(z, al[j]), pc.ca[j]) : d[u][j];
           const float g = dd * actg<ACT>(z, al[j]);
-          const float yh = (v[u][j] - mu[j]) * rs[j];
-          o[j] = sc[j] * (g - db[j] - yh * dg[j]);
+          o[j] = fmaf(sc[j], g, fmaf(ka[j], v[u][j], kb[j]));
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < SV; ++j) o[j] = 0.f;
+        for (int j = 0; j < WV; ++j) o[j] = 0.f;
       }
-      store4(dy + (rc.m_base + t + 8 * u) * ld + c0, o);
+      store8(op + u * step, o);
     }
   }
 }
@@ -451,6 +542,12 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
 //   dgamma = sum_{b,t} da g' yhat     = sum_b ca S3 + cb S4,   S3 = sum_t g' yhat, S4 = sum_t g' a yhat
 // which turns the backward column-reduction pass over the largest activation of the network (78 MB) into a
 // [B, C]-sized kernel (pool_bn_bwd_reduce_kernel).
+#ifndef XV_POOL_ROWS
+#define XV_POOL_ROWS 1
+#endif
+#ifndef XV_POOL_CPT
+#define XV_POOL_CPT 4
+#endif
 template <int N>
 __device__ __forceinline__ void loadN(const __nv_bfloat16* p, float (&f)[N]);
 template <>
@@ -465,17 +562,18 @@ template <>
 __device__ __forceinline__ void loadNf<4>(const float* p, float (&f)[4]) { load4f(p, f); }
 
 // CPT = channels per thread (8: 16-byte loads; 4 when the extra sums would push the kernel past 128 registers).
-template <bool BWD_SUMS, int CPT>
+template <bool BWD_SUMS, int CPT, int ACT>
 __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ out3, int seg_len,
                                                              int seg_valid, const int* __restrict__ lengths,
                                                              int c_real, int cpad, long long ld,
                                                              const float* __restrict__ scale,
                                                              const float* __restrict__ shift,
-                                                             const float* __restrict__ alpha, int act,
+                                                             const float* __restrict__ alpha,
                                                              const float* __restrict__ save_mean,
                                                              const float* __restrict__ save_rstd,
                                                              float* __restrict__ bwd_sums) {
+  pdl_entry();
   // scale != nullptr: x is the PRE-BN tensor and the pooled quantity is act(x*scale + shift) (fused tdnn5 BN+ReLU)
   constexpr int BC = 32 * CPT;     // channels per block
   __shared__ float red[8][2][BC];
@@ -499,37 +597,43 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
     if (scale) {
       loadNf<CPT>(scale + c0, sc);
       loadNf<CPT>(shift + c0, sh);
-      if (act == ACT_PRELU) loadNf<CPT>(alpha + c0, al);
+      if (ACT == ACT_PRELU) loadNf<CPT>(alpha + c0, al);
     }
     if (BWD_SUMS) { loadNf<CPT>(save_mean + c0, mu); loadNf<CPT>(save_rstd + c0, rs); }
     loadN<CPT>(xb + c0, x0);
     if (scale) {
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) x0[j] = act_fwd(act, fmaf(x0[j], sc[j], sh[j]), al[j]);
+      for (int j = 0; j < CPT; ++j) x0[j] = actf<ACT>(fmaf(x0[j], sc[j], sh[j]), al[j]);
     }
-    for (int t = w; t < L; t += 16) {
-      float v[2][CPT];
-      const bool ok1 = (t + 8) < L;
-      loadN<CPT>(xb + static_cast<long long>(t) * ld + c0, v[0]);
-      if (ok1) loadN<CPT>(xb + static_cast<long long>(t + 8) * ld + c0, v[1]);
+    constexpr int PR = XV_POOL_ROWS;       // frames in flight per warp
+    const long long step = 8 * ld;
+    const __nv_bfloat16* xp = xb + static_cast<long long>(w) * ld + c0;
+    for (int t = w; t < L; t += 8 * PR, xp += PR * step) {
+      float v[PR][CPT];
+      bool ok[PR];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && !ok1) continue;
+      for (int u = 0; u < PR; ++u) {
+        ok[u] = t + 8 * u < L;
+        if (ok[u]) loadN<CPT>(xp + u * step, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < PR; ++u) {
+        if (!ok[u]) continue;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
           const float z = fmaf(v[u][j], sc[j], sh[j]);
-          const float a = scale ? act_fwd(act, z, al[j]) : v[u][j];
+          const float a = scale ? actf<ACT>(z, al[j]) : v[u][j];
           const float d = a - x0[j];
           s1[j] += d;
-          s2[j] += d * d;
-          if (BWD_SUMS) {
-            const float gp = act_grad(act, z, al[j]);
-            const float yh = (v[u][j] - mu[j]) * rs[j];
+          s2[j] = fmaf(d, d, s2[j]);
+          if (BWD_SUMS) {       // yhat = (y - mean) * rstd: the rstd factor is applied once, at the end
+            const float gp = actg<ACT>(z, al[j]);
+            const float ym = v[u][j] - mu[j];
             const float ga = gp * a;
             q1[j] += gp;
             q2[j] += ga;
-            q3[j] = fmaf(gp, yh, q3[j]);
-            q4[j] = fmaf(ga, yh, q4[j]);
+            q3[j] = fmaf(gp, ym, q3[j]);
+            q4[j] = fmaf(ga, ym, q4[j]);
           }
         }
       }
@@ -547,7 +651,7 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
     float mean = 0.f, sd = 0.f;
     if (c < c_real && L > 0) {
       float first = __bfloat162float(xb[c]);
-      if (scale) first = act_fwd(act, fmaf(first, scale[c], shift[c]), act == ACT_PRELU ? alpha[c] : 0.f);
+      if (scale) first = actf<ACT>(fmaf(first, scale[c], shift[c]), ACT == ACT_PRELU ? alpha[c] : 0.f);
       const float invl = 1.0f / (static_cast<float>(L) + 1e-16f);
       const float md = a * invl;
       mean = first + md;
@@ -582,8 +686,9 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
         float a = 0.f, q = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; q += red[k][1][threadIdx.x]; }
-        sb[(2 * round) * cpad + c] = (c < c_real) ? a : 0.f;
-        sb[(2 * round + 1) * cpad + c] = (c < c_real) ? q : 0.f;
+        const float f = round ? save_rstd[c] : 1.0f;
+        sb[(2 * round) * cpad + c] = (c < c_real) ? a * f : 0.f;
+        sb[(2 * round + 1) * cpad + c] = (c < c_real) ? q * f : 0.f;
       }
     }
   }
@@ -596,6 +701,7 @@ __global__ void __launch_bounds__(256) pool_bn_bwd_reduce_kernel(const float* __
                                                                  const float* __restrict__ sums, int B, int seg_valid,
                                                                  const int* __restrict__ lengths, int c_real, int cpad,
                                                                  float* dgamma, float* dbeta) {
+  pdl_entry();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= c_real) return;
   const int per = (B + gridDim.y - 1) / gridDim.y;
@@ -624,6 +730,7 @@ __global__ void stats_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const
                                       const float* __restrict__ dpooled, __nv_bfloat16* __restrict__ dx, int B,
                                       int seg_len, int seg_valid, const int* __restrict__ lengths, int c_real, int cpad,
                                       long long ld) {
+  pdl_entry();
   const int cv = cpad / 8;
   const long long total = static_cast<long long>(B) * seg_len * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -683,7 +790,7 @@ extern "C" int xv_pack_input(const float* x, void* out, int B, int T, int D, int
     return set_error(XV_ERR_INVALID, "xv_pack_input: bad arguments (dpad and ldo must be multiples of 8)");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
   const long long total = static_cast<long long>(B) * T * ((ldo + dpad - 1) / dpad);
-  pack_input_kernel<<<grid_for(total, 256, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((pack_input_kernel), grid_for(total, 256, sms), 256, 0, static_cast<cudaStream_t>(stream), 
       x, static_cast<__nv_bfloat16*>(out), B, T, D, k, dpad, ldo);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -695,7 +802,7 @@ extern "C" int xv_bn_finalize_train(const float* col_sum, const float* col_sumsq
                                     float* save_mean, float* save_rstd, int C, void* stream) {
   if (!col_sum || !col_sumsq || !gamma || !beta || !scale || !shift || !save_mean || !save_rstd || C <= 0 || count <= 0)
     return set_error(XV_ERR_INVALID, "xv_bn_finalize_train: bad arguments");
-  bn_finalize_train_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((bn_finalize_train_kernel), ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream), 
       col_sum, col_sumsq, bias, count, gamma, beta, moving_mean, moving_var, momentum, eps, unbiased, scale, shift,
       save_mean, save_rstd, C);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -706,7 +813,7 @@ extern "C" int xv_bn_finalize_infer(const float* gamma, const float* beta, const
                                     const float* moving_var, float eps, float* scale, float* shift, int C, void* stream) {
   if (!gamma || !beta || !moving_mean || !moving_var || !scale || !shift || C <= 0)
     return set_error(XV_ERR_INVALID, "xv_bn_finalize_infer: bad arguments");
-  bn_finalize_infer_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, moving_mean,
+  ::xv::launch_pdl((bn_finalize_infer_kernel), ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream), gamma, beta, moving_mean,
                                                                                             moving_var, eps, scale, shift, C);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -726,9 +833,9 @@ extern "C" int xv_bn_act_apply(const void* y, void* a, const float* scale, const
   int rc = check_act_layout("xv_bn_act_apply", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: rows must fit in int32");
   if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
-  const RowGrid rg = make_row_grid(rows, seg_len, C);
-  const unsigned grid = static_cast<unsigned>(ceil_div(C, SCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
-  XV_ACT_DISPATCH(act, (bn_act_apply_kernel<A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const RowGrid rg = make_row_grid(rows, seg_len, C, WCH);
+  const unsigned grid = static_cast<unsigned>(ceil_div(C, WCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
+  XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_apply_kernel<A_>), grid, 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha,
       rg, C, ld, seg_len, seg_valid, lengths)));
   XV_CUDA_CHECK(cudaGetLastError());
@@ -742,7 +849,7 @@ extern "C" int xv_col_stats(const void* y, const float* bias, int64_t rows, int 
   if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
   const RowGrid rg = make_row_grid(rows, seg_len, C);
   const unsigned grid = static_cast<unsigned>(ceil_div(C, SCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
-  col_stats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((col_stats_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(y), bias, rg, C, ld, seg_len, seg_valid, lengths, col_sum,
       col_sumsq);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -768,15 +875,15 @@ extern "C" int xv_bn_act_bwd_reduce(const void* y, const void* da, const float* 
   int rc = check_act_layout("xv_bn_act_bwd_reduce", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_reduce: rows must fit in int32");
   if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
-  const RowGrid rg = make_row_grid(rows, seg_len, C);
-  const unsigned grid = static_cast<unsigned>(ceil_div(C, SCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
+  const RowGrid rg = make_row_grid(rows, seg_len, C, WCH, pooled ? FUSED_STREAM_ROWS : STREAM_ROWS);
+  const unsigned grid = static_cast<unsigned>(ceil_div(C, WCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
   PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
   if (pooled) {
-    XV_ACT_DISPATCH(act, (bn_act_bwd_reduce_kernel<true, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_bwd_reduce_kernel<true, A_>), grid, 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(y), nullptr, scale, shift, save_mean, save_rstd, alpha,
         rg, C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps)));
   } else {
-    XV_ACT_DISPATCH(act, (bn_act_bwd_reduce_kernel<false, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_bwd_reduce_kernel<false, A_>), grid, 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), scale, shift, save_mean, save_rstd,
         alpha, rg, C, ld, seg_len, seg_valid, lengths, dgamma, dbeta, dalpha, ps)));
   }
@@ -796,14 +903,14 @@ extern "C" int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, cons
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_apply: rows must fit in int32");
   PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
   if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
-  const RowGrid rg = make_row_grid(rows, seg_len, C);
-  const unsigned grid = static_cast<unsigned>(ceil_div(C, SCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
+  const RowGrid rg = make_row_grid(rows, seg_len, C, WCH, pooled ? FUSED_STREAM_ROWS : STREAM_ROWS);
+  const unsigned grid = static_cast<unsigned>(ceil_div(C, WCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
   if (pooled) {
-    XV_ACT_DISPATCH(act, (bn_act_bwd_apply_kernel<true, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_bwd_apply_kernel<true, A_>), grid, 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(y), nullptr, static_cast<__nv_bfloat16*>(dy), scale, shift, save_mean,
         save_rstd, dgamma, dbeta, 1.0f / count, alpha, rg, C, ld, seg_len, seg_valid, lengths, ps)));
   } else {
-    XV_ACT_DISPATCH(act, (bn_act_bwd_apply_kernel<false, A_><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_bwd_apply_kernel<false, A_>), grid, 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dy),
         scale, shift, save_mean, save_rstd, dgamma, dbeta, 1.0f / count, alpha, rg, C, ld,
         seg_len, seg_valid, lengths, ps)));
@@ -821,16 +928,21 @@ extern "C" int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int
     return set_error(XV_ERR_INVALID, "xv_stats_pool_fwd: bad arguments");
   if (bwd_sums && (!scale || !save_mean || !save_rstd || act == ACT_PRELU))
     return set_error(XV_ERR_INVALID, "xv_stats_pool_fwd: backward sums need the fused BN (scale, shift, saved mean / rstd) and a non-prelu activation");
+  if (act < ACT_NONE || act > ACT_TANH) return set_error(XV_ERR_INVALID, "xv_stats_pool_fwd: unknown activation %d", act);
+  const cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* o3 = static_cast<__nv_bfloat16*>(out_split);
   if (bwd_sums) {
-    dim3 grid(ceil_div(cpad, 128), B);
-    stats_pool_fwd_kernel<true, 4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), out, static_cast<__nv_bfloat16*>(out_split), seg_len, seg_valid, lengths,
-        c_real, cpad, ld, scale, shift, alpha, act, save_mean, save_rstd, bwd_sums);
+    dim3 grid(ceil_div(cpad, 32 * XV_POOL_CPT), B);
+    XV_ACT_DISPATCH(act, (::xv::launch_pdl((stats_pool_fwd_kernel<true, XV_POOL_CPT, A_>), grid, 256, 0, s_, xb, out, o3, seg_len,
+                                           seg_valid, lengths, c_real, cpad, ld, scale, shift, alpha, save_mean, save_rstd,
+                                           bwd_sums)));
   } else {
     dim3 grid(ceil_div(cpad, 256), B);
-    stats_pool_fwd_kernel<false, 8><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), out, static_cast<__nv_bfloat16*>(out_split), seg_len, seg_valid, lengths,
-        c_real, cpad, ld, scale, shift, alpha, act, nullptr, nullptr, nullptr);
+    const float* nf = nullptr;
+    float* nfm = nullptr;
+    XV_ACT_DISPATCH(act, (::xv::launch_pdl((stats_pool_fwd_kernel<false, 8, A_>), grid, 256, 0, s_, xb, out, o3, seg_len,
+                                           seg_valid, lengths, c_real, cpad, ld, scale, shift, alpha, nf, nf, nfm)));
   }
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -840,8 +952,8 @@ extern "C" int xv_pool_bn_bwd_reduce(const float* pooled, const float* dpooled, 
                                      const int32_t* lengths, int c_real, int cpad, float* dgamma, float* dbeta, void* stream) {
   if (!pooled || !dpooled || !bwd_sums || !dgamma || !dbeta || B <= 0 || c_real <= 0 || c_real > cpad)
     return set_error(XV_ERR_INVALID, "xv_pool_bn_bwd_reduce: bad arguments");
-  dim3 grid(ceil_div(c_real, 256), B < 16 ? B : 16);
-  pool_bn_bwd_reduce_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, dpooled, bwd_sums, B, seg_valid,
+  dim3 grid(ceil_div(c_real, 256), B < 64 ? B : 64);
+  ::xv::launch_pdl((pool_bn_bwd_reduce_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream), pooled, dpooled, bwd_sums, B, seg_valid,
                                                                                  lengths, c_real, cpad, dgamma, dbeta);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
@@ -853,7 +965,7 @@ extern "C" int xv_stats_pool_bwd(const void* x, const float* pooled, const float
     return set_error(XV_ERR_INVALID, "xv_stats_pool_bwd: bad arguments");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
   const long long total = static_cast<long long>(B) * seg_len * (cpad / 8);
-  stats_pool_bwd_kernel<<<grid_for(total, 256, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((stats_pool_bwd_kernel), grid_for(total, 256, sms), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), pooled, dpooled, static_cast<__nv_bfloat16*>(dx), B, seg_len, seg_valid,
       lengths, c_real, cpad, ld);
   XV_CUDA_CHECK(cudaGetLastError());

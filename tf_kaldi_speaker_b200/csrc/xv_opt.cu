@@ -15,6 +15,7 @@ enum { OPT_SGD = 0, OPT_MOMENTUM = 1, OPT_NESTEROV = 2, OPT_ADAM = 3 };
 // sum over all elements of (g + l2*w)^2  -> out[0] (atomic); blk_l2[b] is the L2 coefficient of block b.
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ params, const float* __restrict__ grads,
                                                          const float* __restrict__ blk_l2, long long n, float* out) {
+  pdl_entry();
   __shared__ float sh[8];
   float acc = 0.f;
   for (long long blk = blockIdx.x; blk * OPT_BLOCK < n; blk += gridDim.x) {
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) opt_step_kernel(float* __restrict__ param
                                                        __nv_bfloat16* __restrict__ shadow, long long n, int opt,
                                                        const float* __restrict__ hyper, const float* __restrict__ gsumsq,
                                                        float* l2_out) {
+  pdl_entry();
   __shared__ float sh[8];
   const float lr = hyper[0];
   float gscale = 1.f;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) shadow_refresh_kernel(const float* __rest
                                                              const long long* __restrict__ blk_shadow,
                                                              const long long* __restrict__ blk_split_stride,
                                                              __nv_bfloat16* __restrict__ shadow, long long n) {
+  pdl_entry();
   for (long long blk = blockIdx.x; blk * OPT_BLOCK < n; blk += gridDim.x) {
     const long long so = blk_shadow[blk];
     const long long base = blk * OPT_BLOCK + threadIdx.x * 4;
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(256) shadow_refresh_kernel(const float* __rest
 // loss += sum over blocks of l2/2 * w^2   (tf.losses.get_regularization_loss, trainer.py:357)
 __global__ void __launch_bounds__(256) l2_loss_kernel(const float* __restrict__ params, const float* __restrict__ blk_l2,
                                                       long long n, float* out) {
+  pdl_entry();
   __shared__ float sh[8];
   float acc = 0.f;
   for (long long blk = blockIdx.x; blk * OPT_BLOCK < n; blk += gridDim.x) {
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(256) l2_loss_kernel(const float* __restrict__ 
 // learning rate / margin schedule change between replays of a captured CUDA graph without any host-buffer race.
 struct Scalars16 { float v[16]; };
 __global__ void set_scalars_kernel(float* dst, Scalars16 s, int n) {
+  pdl_entry();
   if (threadIdx.x < n) dst[threadIdx.x] = s.v[threadIdx.x];
 }
 
@@ -205,7 +210,7 @@ using namespace xv;
 extern "C" int xv_grad_sumsq(const float* params, const float* grads, const float* blk_l2, int64_t n, float* out, void* stream) {
   if (!params || !grads || !blk_l2 || !out || n <= 0 || n % OPT_BLOCK) return set_error(XV_ERR_INVALID, "xv_grad_sumsq: n must be a positive multiple of 1024");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
-  grad_sumsq_kernel<<<opt_grid(n, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, blk_l2, n, out);
+  ::xv::launch_pdl((grad_sumsq_kernel), opt_grid(n, sms), 256, 0, static_cast<cudaStream_t>(stream), params, grads, blk_l2, n, out);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
@@ -219,7 +224,7 @@ extern "C" int xv_opt_step(float* params, const float* grads, float* state1, flo
   if (opt != OPT_SGD && !state1) return set_error(XV_ERR_INVALID, "xv_opt_step: momentum/adam need state1");
   if (opt == OPT_ADAM && !state2) return set_error(XV_ERR_INVALID, "xv_opt_step: adam needs state2");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
-  opt_step_kernel<<<opt_grid((n + OPT_UNROLL - 1) / OPT_UNROLL, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((opt_step_kernel), opt_grid((n + OPT_UNROLL - 1) / OPT_UNROLL, sms), 256, 0, static_cast<cudaStream_t>(stream), 
       params, grads, state1, state2, blk_l2, reinterpret_cast<const long long*>(blk_shadow),
       reinterpret_cast<const long long*>(blk_split_stride), static_cast<__nv_bfloat16*>(shadow), n, opt, hyper, gsumsq,
       l2_loss_out);
@@ -232,7 +237,7 @@ extern "C" int xv_shadow_refresh(const float* params, const int64_t* blk_shadow,
   if (!params || !blk_shadow || !blk_split_stride || !shadow || n <= 0 || n % OPT_BLOCK)
     return set_error(XV_ERR_INVALID, "xv_shadow_refresh: bad arguments");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
-  shadow_refresh_kernel<<<opt_grid(n, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((shadow_refresh_kernel), opt_grid(n, sms), 256, 0, static_cast<cudaStream_t>(stream), 
       params, reinterpret_cast<const long long*>(blk_shadow), reinterpret_cast<const long long*>(blk_split_stride),
       static_cast<__nv_bfloat16*>(shadow), n);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -242,7 +247,7 @@ extern "C" int xv_shadow_refresh(const float* params, const int64_t* blk_shadow,
 extern "C" int xv_l2_loss(const float* params, const float* blk_l2, int64_t n, float* out, void* stream) {
   if (!params || !blk_l2 || !out || n <= 0 || n % OPT_BLOCK) return set_error(XV_ERR_INVALID, "xv_l2_loss: bad arguments");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
-  l2_loss_kernel<<<opt_grid(n, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, blk_l2, n, out);
+  ::xv::launch_pdl((l2_loss_kernel), opt_grid(n, sms), 256, 0, static_cast<cudaStream_t>(stream), params, blk_l2, n, out);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
@@ -251,7 +256,7 @@ extern "C" int xv_set_scalars(float* dst, const float* host_vals, int n, void* s
   if (!dst || !host_vals || n <= 0 || n > 16) return set_error(XV_ERR_INVALID, "xv_set_scalars: n must be in [1, 16]");
   Scalars16 s;
   for (int i = 0; i < 16; ++i) s.v[i] = i < n ? host_vals[i] : 0.f;
-  set_scalars_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(dst, s, n);
+  ::xv::launch_pdl((set_scalars_kernel), 1, 32, 0, static_cast<cudaStream_t>(stream), dst, s, n);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

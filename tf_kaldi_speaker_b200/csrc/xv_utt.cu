@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(32 * UROWG) bn_rows_fwd_kernel(const float* __
                                    float eps, const float* __restrict__ alpha, int act, float* __restrict__ bn_out,
                                    float* __restrict__ a, __nv_bfloat16* __restrict__ a_split, int split_terms,
                                    float* save_mean, float* save_rstd) {
+  pdl_entry();
   __shared__ float red[UROWG][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(32 * UROWG) bn_rows_bwd_kernel(const float* __
                                    const float* __restrict__ alpha, int act, float* __restrict__ dy,
                                    __nv_bfloat16* __restrict__ dy_bf16, float* dgamma, float* dbeta, float* dalpha,
                                    float* dbias) {
+  pdl_entry();
   __shared__ float red[UROWG][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(32 * UROWG) bn_rows_bwd_kernel(const float* __
 // f32 [rows, cols] -> bf16, optionally as the [hi | hi | lo] split (terms = 3).
 __global__ void cast_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int cols,
                                   int terms) {
+  pdl_entry();
   const long long total = rows * cols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -180,7 +183,7 @@ extern "C" int xv_bn_rows_fwd(const float* y, int B, int C, int mode, const floa
   if (mode == 2 && (!moving_mean || !moving_var)) return set_error(XV_ERR_INVALID, "xv_bn_rows_fwd: inference needs moving stats");
   if (act == ACT_PRELU && !alpha) return set_error(XV_ERR_INVALID, "xv_bn_rows_fwd: prelu needs alpha");
   if (a_split && split_terms != 1 && split_terms != 3) return set_error(XV_ERR_INVALID, "xv_bn_rows_fwd: split_terms must be 1 or 3");
-  bn_rows_fwd_kernel<<<ceil_div(C, 32), 32 * UROWG, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((bn_rows_fwd_kernel), ceil_div(C, 32), 32 * UROWG, 0, static_cast<cudaStream_t>(stream), 
       y, B, C, mode, gamma, beta, moving_mean, moving_var, momentum, eps, alpha, act, bn_out, a,
       static_cast<__nv_bfloat16*>(a_split), split_terms, save_mean, save_rstd);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -193,7 +196,7 @@ extern "C" int xv_bn_rows_bwd(const float* y, const float* da, int B, int C, int
                               float* dbias, void* stream) {
   if (!y || !da || B <= 0 || C <= 0 || mode < 0 || mode > 2) return set_error(XV_ERR_INVALID, "xv_bn_rows_bwd: bad arguments");
   if (mode != 0 && (!gamma || !beta || !save_mean || !save_rstd)) return set_error(XV_ERR_INVALID, "xv_bn_rows_bwd: BN needs saved statistics");
-  bn_rows_bwd_kernel<<<ceil_div(C, 32), 32 * UROWG, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((bn_rows_bwd_kernel), ceil_div(C, 32), 32 * UROWG, 0, static_cast<cudaStream_t>(stream), 
       y, da, B, C, mode, gamma, beta, save_mean, save_rstd, alpha, act, dy, static_cast<__nv_bfloat16*>(dy_bf16),
       dgamma, dbeta, dalpha, dbias);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -205,7 +208,7 @@ extern "C" int xv_cast_split(const float* x, void* out, int64_t rows, int cols, 
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
   long long g = (rows * cols + 255) / 256;
   if (g > sms * 8LL) g = sms * 8LL;
-  cast_split_kernel<<<static_cast<int>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::xv::launch_pdl((cast_split_kernel), static_cast<int>(g), 256, 0, static_cast<cudaStream_t>(stream), 
       x, static_cast<__nv_bfloat16*>(out), rows, cols, terms);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;

@@ -1,5 +1,9 @@
-set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_g.json 2> gpurun_out/bench_g.err
-cat gpurun_out/bench_g.json | cut -c1-300; tail -3 gpurun_out/bench_g.err
-python tools/step_kernel_times.py 20 gpurun_out/step_kernels_g.md 2>&1 | grep -v "gemm_kernel<[01]>" | head -32
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/layers_bench.py 2>&1 | grep -E "bn_act|stats_pool|copy|pool_bn"
+for cfg in "-DXV_POOL_ROWS=1" "-DXV_POOL_ROWS=4" "-DXV_POOL_ROWS=1 -DXV_POOL_CPT=8" "-DXV_POOL_ROWS=2 -DXV_POOL_CPT=8"; do
+  echo "=== $cfg"
+  XV_EXTRA_CFLAGS="$cfg" python -m tf_kaldi_speaker_b200.build 2>&1 | grep -i error
+  python tools/layers_bench.py 2>&1 | grep -E "stats_pool"
+done
+python -m tf_kaldi_speaker_b200.build 2>&1 | grep -i error
+python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-260
