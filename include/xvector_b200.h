@@ -153,6 +153,13 @@ XV_API int xv_bn_finalize_train(const float* col_sum, const float* col_sumsq, co
                                 const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                                 float momentum, float eps, int unbiased_moving_var, float* scale, float* shift,
                                 float* save_mean, float* save_rstd, int C, void* stream);
+/* xv_bn_finalize_train + xv_bn_act_apply in one launch: every block derives scale / shift from the batch statistics,
+ * the first row chunk publishes scale / shift / save_mean / save_rstd and updates the moving statistics. */
+XV_API int xv_bn_train_apply(const void* y, void* a, const float* col_sum, const float* col_sumsq, const float* bias,
+                             float count, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                             float momentum, float eps, int unbiased_moving_var, float* scale, float* shift,
+                             float* save_mean, float* save_rstd, const float* alpha, int act, int64_t rows, int C,
+                             int64_t ld, int seg_len, int seg_valid, const int32_t* lengths, void* stream);
 /* Per-channel sum and sum of squares of (y - bias) over the valid rows (+= into col_sum / col_sumsq): the batch
  * statistics of tf.layers.batch_normalization for layers whose GEMM is too short to hide a reduction epilogue. */
 XV_API int xv_col_stats(const void* y, const float* bias, int64_t rows, int C, int64_t ld, int seg_len, int seg_valid,

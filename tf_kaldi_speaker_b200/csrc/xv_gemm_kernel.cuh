@@ -300,6 +300,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       const bool row_ok = m < p.M;
       const int cbase = n0 + hf * EPI_COLS;                       // first global column of this warp
       const int ncols = max(0, min(EPI_COLS, p.N - cbase));
+      if (EPI == XV_EPI_BF16 && p.bnb.y != nullptr && row_ok && ncols > 0) {
+        // The fused BN-backward reductions read this thread's row of y (256 B): pull it into L2 now, while the MMAs of
+        // this tile are still running, so the loads below do not expose HBM latency four times per tile.
+        const char* yb = reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(p.bnb.y) +
+                                                       static_cast<long long>(m) * p.bnb.ldy + cbase);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(yb));
+        if (ncols > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(yb + 128));
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * BLOCK_N + hf * EPI_COLS;

@@ -266,20 +266,71 @@ __device__ __forceinline__ WideBlock wide_block(const RowGrid& rg, int seg_len, 
   return b;
 }
 
+// Training-mode BN finalisation folded into the apply kernel (col_sum != nullptr): every block derives scale / shift of
+// its 8 channels per thread from the batch statistics the GEMM epilogue accumulated; the blocks of the first row
+// chunk also publish scale / shift / saved mean / rstd for the backward pass and update the moving statistics
+// (what xv_bn_finalize_train does as a separate 3 us launch per layer).
+struct BnTrainSrc {
+  const float* col_sum;
+  const float* col_sumsq;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float* moving_mean;
+  float* moving_var;
+  float* scale_out;
+  float* shift_out;
+  float* save_mean;
+  float* save_rstd;
+  float count, momentum, eps;
+  int unbiased;
+};
+
 // a = act(y*scale + shift) on valid rows, 0 on invalid rows.
 template <int ACT>
 __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ alpha, RowGrid rg, int C, long long ld,
-                                    int seg_len, int seg_valid, const int* __restrict__ lengths) {
+                                    int seg_len, int seg_valid, const int* __restrict__ lengths, BnTrainSrc bt) {
   pdl_entry();
+  __shared__ float s_sc[WCH], s_sh[WCH];
   const WideBlock wb = wide_block(rg, seg_len, seg_valid, lengths);
   const int c0 = wb.c0;
+  if (bt.col_sum != nullptr) {      // one channel per thread, shared through smem (not 8 per thread: 2x the kernel time)
+    const int c = wb.cgroup * WCH + threadIdx.x;
+    if (c < C) {
+      const float mean_nb = bt.col_sum[c] / bt.count;                       // mean of the bias-free accumulator
+      const float var = fmaxf(bt.col_sumsq[c] / bt.count - mean_nb * mean_nb, 0.f);
+      const float mean = mean_nb + (bt.bias ? bt.bias[c] : 0.f);
+      const float rstd = rsqrtf(var + bt.eps);
+      const float scv = bt.gamma[c] * rstd;
+      const float shv = bt.beta[c] - mean * scv;
+      s_sc[threadIdx.x] = scv;
+      s_sh[threadIdx.x] = shv;
+      if ((blockIdx.x / rg.col_groups) == 0) {     // first row chunk: publish for the backward pass, update moving stats
+        bt.scale_out[c] = scv;
+        bt.shift_out[c] = shv;
+        bt.save_mean[c] = mean;
+        bt.save_rstd[c] = rstd;
+        if (bt.moving_mean) {
+          const float mv = bt.unbiased ? var * (bt.count / fmaxf(bt.count - 1.f, 1.f)) : var;
+          bt.moving_mean[c] = bt.moving_mean[c] * bt.momentum + mean * (1.f - bt.momentum);
+          bt.moving_var[c] = bt.moving_var[c] * bt.momentum + mv * (1.f - bt.momentum);
+        }
+      }
+    }
+    __syncthreads();
+  }
   if (c0 >= C) return;
   const RowChunk rc = wb.rc;
   float sc[WV], sh[WV], al[WV];
-  load8f(scale + c0, sc);
-  load8f(shift + c0, sh);
+  if (bt.col_sum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < WV; ++j) { sc[j] = s_sc[wb.lane * WV + j]; sh[j] = s_sh[wb.lane * WV + j]; }
+  } else {
+    load8f(scale + c0, sc);
+    load8f(shift + c0, sh);
+  }
 #pragma unroll
   for (int j = 0; j < WV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
   const long long step = 8 * ld;
@@ -826,20 +877,41 @@ static int check_act_layout(const char* who, int C, int64_t ld, int act, const f
   return XV_OK;
 }
 
-extern "C" int xv_bn_act_apply(const void* y, void* a, const float* scale, const float* shift, const float* alpha,
-                               int act, int64_t rows, int C, int64_t ld, int seg_len, int seg_valid,
-                               const int32_t* lengths, void* stream) {
-  if (!y || !a || !scale || !shift || rows <= 0) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: bad arguments");
+static int launch_bn_act_apply(const void* y, void* a, const float* scale, const float* shift, const float* alpha, int act,
+                               int64_t rows, int C, int64_t ld, int seg_len, int seg_valid, const int32_t* lengths,
+                               const BnTrainSrc& bt, void* stream) {
   int rc = check_act_layout("xv_bn_act_apply", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: rows must fit in int32");
   if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
   const RowGrid rg = make_row_grid(rows, seg_len, C, WCH);
   const unsigned grid = static_cast<unsigned>(ceil_div(C, WCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
-  XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_apply_kernel<A_>), grid, 256, 0, static_cast<cudaStream_t>(stream), 
+  XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_apply_kernel<A_>), grid, 256, 0, static_cast<cudaStream_t>(stream),
       static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha,
-      rg, C, ld, seg_len, seg_valid, lengths)));
+      rg, C, ld, seg_len, seg_valid, lengths, bt)));
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
+}
+
+extern "C" int xv_bn_act_apply(const void* y, void* a, const float* scale, const float* shift, const float* alpha,
+                               int act, int64_t rows, int C, int64_t ld, int seg_len, int seg_valid,
+                               const int32_t* lengths, void* stream) {
+  if (!y || !a || !scale || !shift || rows <= 0) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: bad arguments");
+  BnTrainSrc bt;
+  memset(&bt, 0, sizeof(bt));
+  return launch_bn_act_apply(y, a, scale, shift, alpha, act, rows, C, ld, seg_len, seg_valid, lengths, bt, stream);
+}
+
+extern "C" int xv_bn_train_apply(const void* y, void* a, const float* col_sum, const float* col_sumsq, const float* bias,
+                                 float count, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                                 float momentum, float eps, int unbiased_moving_var, float* scale, float* shift,
+                                 float* save_mean, float* save_rstd, const float* alpha, int act, int64_t rows, int C,
+                                 int64_t ld, int seg_len, int seg_valid, const int32_t* lengths, void* stream) {
+  if (!y || !a || !col_sum || !col_sumsq || !gamma || !beta || !scale || !shift || !save_mean || !save_rstd || rows <= 0 ||
+      count <= 0)
+    return set_error(XV_ERR_INVALID, "xv_bn_train_apply: bad arguments");
+  BnTrainSrc bt{col_sum, col_sumsq, bias, gamma, beta, moving_mean, moving_var, scale, shift, save_mean, save_rstd,
+                count, momentum, eps, unbiased_moving_var};
+  return launch_bn_act_apply(y, a, scale, shift, alpha, act, rows, C, ld, seg_len, seg_valid, lengths, bt, stream);
 }
 
 extern "C" int xv_col_stats(const void* y, const float* bias, int64_t rows, int C, int64_t ld, int seg_len, int seg_valid,

@@ -364,7 +364,7 @@ class Engine(object):
 
     def splits_for(self, M, N, K, max_splits=64, min_kb=4):
         """Split-K factor of an f32-output GEMM: the persistent grid runs ceil(tiles*s / SMs) rounds of equal-length
-        work units, so SM occupancy is tiles*s / (rounds * SMs).  Pick the smallest s within 6 % of the best
+        work units, so SM occupancy is tiles*s / (rounds * SMs).  Pick the smallest s within 6 % (relative) of the best
         occupancy (fewer splits = fewer TMA reduce-add epilogues); every split keeps >= ``min_kb`` 64-deep k-blocks."""
         tiles = ((M + 127) // 128) * ((N + 255) // 256)
         kb = (K + 63) // 64
@@ -376,7 +376,7 @@ class Engine(object):
             effs.append(units / float(rounds * self.num_sms))
         best = max(effs)
         for s_, e in enumerate(effs, 1):
-            if e >= best - 0.06:
+            if e >= 0.94 * best:
                 return s_
         return 1
 
@@ -455,10 +455,12 @@ class Engine(object):
             smean.zero_()
             srstd.fill_(1.0)
         elif training:
-            self.call(self.lib.xv_bn_finalize_train, L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(st.view(bias)),
-                      C.c_float(count), L.ptr(st.view(bn[0])), L.ptr(st.view(bn[1])), L.ptr(st.view(bn[2])),
-                      L.ptr(st.view(bn[3])), C.c_float(momentum), C.c_float(BN_EPS), int(unbiased_moving_var),
-                      L.ptr(scale), L.ptr(shift), L.ptr(smean), L.ptr(srstd), cout_pad, L.stream_ptr())
+            fused_finalize = epi_stats and not defer_apply      # finalisation folded into the apply kernel below
+            if not fused_finalize:
+                self.call(self.lib.xv_bn_finalize_train, L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(st.view(bias)),
+                          C.c_float(count), L.ptr(st.view(bn[0])), L.ptr(st.view(bn[1])), L.ptr(st.view(bn[2])),
+                          L.ptr(st.view(bn[3])), C.c_float(momentum), C.c_float(BN_EPS), int(unbiased_moving_var),
+                          L.ptr(scale), L.ptr(shift), L.ptr(smean), L.ptr(srstd), cout_pad, L.stream_ptr())
         else:
             self.call(self.lib.xv_bn_finalize_infer, L.ptr(st.view(bn[0])), L.ptr(st.view(bn[1])), L.ptr(st.view(bn[2])),
                       L.ptr(st.view(bn[3])), C.c_float(BN_EPS), L.ptr(scale), L.ptr(shift), cout_pad, L.stream_ptr())
@@ -470,8 +472,15 @@ class Engine(object):
 
         def apply_now():
             a = self.buf(name + "/a", (R, cout_pad), torch.bfloat16)
-            self.call(self.lib.xv_bn_act_apply, L.ptr(y), L.ptr(a), L.ptr(scale), L.ptr(shift), L.ptr(alpha_t), act,
-                      C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, L.stream_ptr())
+            if bn is not None and training and epi_stats and not defer_apply:
+                self.call(self.lib.xv_bn_train_apply, L.ptr(y), L.ptr(a), L.ptr(stats[0]), L.ptr(stats[1]),
+                          L.ptr(st.view(bias)), C.c_float(count), L.ptr(st.view(bn[0])), L.ptr(st.view(bn[1])),
+                          L.ptr(st.view(bn[2])), L.ptr(st.view(bn[3])), C.c_float(momentum), C.c_float(BN_EPS),
+                          int(unbiased_moving_var), L.ptr(scale), L.ptr(shift), L.ptr(smean), L.ptr(srstd), L.ptr(alpha_t),
+                          act, C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, L.stream_ptr())
+            else:
+                self.call(self.lib.xv_bn_act_apply, L.ptr(y), L.ptr(a), L.ptr(scale), L.ptr(shift), L.ptr(alpha_t), act,
+                          C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, L.stream_ptr())
             aa.data = a
         aa._materialize = apply_now
         if defer_apply:     # the consumer (statistics pooling) applies BN + activation on the fly

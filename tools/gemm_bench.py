@@ -73,6 +73,15 @@ def main():
             lambda: L.gemm(L.operand(dy, False, div=(cout if k > 1 else 0), tap_rows=(-1 if k > 1 else 0)),
                            L.operand(w, False, div=(cout if k > 1 else 0), tap_rows=(cin if k > 1 else 0)), R, cin,
                            k * cout, dx, epilogue=L.EPI_BF16), R, cin, k * cout)
+        if cin == 512:      # the same dgrad with the fused BN-backward reductions of the producer layer in its epilogue
+            yprev = mk(R, cin)
+            cst = [torch.rand(cin, device=dev) + 0.5 for _ in range(4)]
+            acc2 = torch.zeros(2, cin, device=dev)
+            run(name.replace("fwd", "dgrad+bnbwd"),
+                lambda: L.gemm(L.operand(dy, False, div=(cout if k > 1 else 0), tap_rows=(-1 if k > 1 else 0)),
+                               L.operand(w, False, div=(cout if k > 1 else 0), tap_rows=(cin if k > 1 else 0)), R, cin,
+                               k * cout, dx, epilogue=L.EPI_BF16, col_sum=acc2[0], col_sumsq=acc2[1],
+                               bn_bwd=(yprev, cst[0], cst[1], cst[2], cst[3], 0.0)), R, cin, k * cout)
         gw = torch.zeros(k * cin, cout, device=dev)
         tiles = ((k * cin + 127) // 128) * ((cout + 255) // 256)
         splits = max(1, min(32, 148 // tiles))
