@@ -1,3 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-260
-python tools/gemm_bench.py 2>&1 | grep -E "dgrad|fwd"
+timeout 600 python tools/config_bench.py --json gpurun_out/config_bench.json 2>&1 | tail -25
