@@ -43,7 +43,39 @@ def _worker(rank, world, port, out):
     params = torch.full((4,), float(rank))
     comm.broadcast_(params, src=0)
     ok_bcast = bool((params == 0).all())
-    out.put((rank, ok_grad, ok_loss, ok_bcast))
+    # the two-bucket overlapped exchange of DataParallel on a stand-in parameter store: [tdnn6 .. head] first (async),
+    # then [tdnn1 .. pooling]; together they must equal one all-reduce of the flat buffer
+    class _Spec(object):
+        def __init__(self, offset):
+            self.offset = offset
+
+    class _Store(object):
+        def __init__(self):
+            self.specs = {"tdnn/tdnn1_conv/kernel": _Spec(0), "tdnn/tdnn6_dense/kernel": _Spec(2048)}
+            self.params = torch.zeros(4096)
+            self.buffers = torch.zeros(32)
+            self.grads = torch.arange(4096, dtype=torch.float32) * (rank + 1)
+
+        def refresh_shadows(self):
+            pass
+
+    class _Eng(object):
+        pass
+
+    class _Trainer(object):
+        pass
+    tr = _Trainer()
+    tr.engine = _Eng()
+    tr.engine.store = _Store()
+    tr.engine.device = "cpu"
+    dp = parallel.DataParallel(tr, local_batch=4)
+    ok_dp = dp.split == 2048 and abs(tr.engine.inv_global_batch - 1.0 / (world * 4)) < 1e-12
+    dp.allreduce_bucket_async("head")
+    dp.allreduce_bucket_async("trunk")
+    dp.wait_all()
+    expect = torch.arange(4096, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    ok_dp = ok_dp and torch.equal(tr.engine.store.grads, expect)
+    out.put((rank, ok_grad, ok_loss, ok_bcast and ok_dp))
     dist.destroy_process_group()
 
 

@@ -140,6 +140,7 @@ def tdnn(features, params, is_training=None, reuse_variables=None, aux_features=
     else:
         raise NotImplementedError("Not implement %s pooling" % params.pooling_type)
     endpoints["pooling"] = u
+    eng.mark_utterance_level()
 
     # Utterance-level network (tdnn.py:147-189)
     y6, bn6, a6 = eng.utt_affine(u, "tdnn/tdnn6_dense/kernel", "tdnn/tdnn6_dense/bias", "tdnn6", training,

@@ -123,7 +123,7 @@ class Trainer(object):
             labels = labels.to(dev, dtype=torch.int32, non_blocking=True)
         return features, labels
 
-    def _fwd_bwd(self, features, labels, l2_loss=True):
+    def _fwd_bwd(self, features, labels, l2_loss=True, backward_part=None):
         """Forward + backward of one device-resident batch; gradients are left in the flat gradient buffer.
         ``l2_loss=False``: the regularisation loss is left to the optimizer kernel (same pass over the parameters)."""
         eng = self.engine
@@ -134,7 +134,7 @@ class Trainer(object):
         self.endpoints = endpoints
         if l2_loss:
             eng.l2_loss()
-        eng.backward()
+        eng.backward(backward_part)
 
     def forward_backward(self, features, labels, global_step):
         """Eager forward + backward (no optimizer step); used by tests and gradient inspection."""
@@ -179,19 +179,39 @@ class Trainer(object):
                       float(self.params.dict.get("clip_gradient_norm", 0.0)) if clip else 0.0, flush=False)
         eng.set_sched(*margin_schedule(self.loss_type, self.params, global_step))
 
+        # dp_overlap: all-reduce the [tdnn6 .. head] gradient bucket while the frame-level backward runs.  Measured on
+        # 2 x B200: 1.169 ms/step with, 1.160 ms without (the 39 MB exchange costs ~75 us either way and the NCCL CTAs
+        # take SMs from the persistent GEMMs), so it stays opt-in.
+        overlap = self.dp is not None and bool(self.params.dict.get("dp_overlap", False))
+
         def part_a():
-            self._fwd_bwd(st["x"], st["y"], l2_loss=False)
+            self._fwd_bwd(st["x"], st["y"], l2_loss=False, backward_part=("head" if overlap else None))
+
+        def part_a2():
+            eng.backward("trunk")
 
         def part_b():
             eng.optimizer_step(self.opt, clip=clip, with_l2_loss=True)
 
-        if st["graphs"] is not None:
-            ga, gb = st["graphs"]
-            ga.replay()
-            if self.dp is not None:
+        def run(ga, ga2, gb):
+            """forward + head backward | all-reduce(head bucket) overlapping the frame-level backward | all-reduce(trunk
+            bucket) | optimizer.  ga / ga2 / gb are captured graphs or None (eager)."""
+            ga.replay() if ga is not None else part_a()
+            if self.dp is None:
+                if ga is None:
+                    part_b()
+                return
+            if overlap:
+                self.dp.allreduce_bucket_async("head")
+                ga2.replay() if ga2 is not None else part_a2()
+                self.dp.allreduce_bucket_async("trunk")
+                self.dp.wait_all()
+            else:
                 self.dp.allreduce_gradients()
-            if gb is not None:
-                gb.replay()
+            gb.replay() if gb is not None else part_b()
+
+        if st["graphs"] is not None:
+            run(*st["graphs"])
             eng.launches += st["launches"]
         else:
             st["calls"] += 1
@@ -200,28 +220,26 @@ class Trainer(object):
                 eng.capturing = True
                 try:
                     ga = torch.cuda.CUDAGraph()
-                    gb = None
+                    ga2 = gb = None
                     with torch.cuda.graph(ga):
                         part_a()
                         if self.dp is None:
                             part_b()
                     if self.dp is not None:
+                        if overlap:
+                            ga2 = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(ga2):
+                                part_a2()
                         gb = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(gb):
                             part_b()
                 finally:
                     eng.capturing = False
                 st["launches"] = eng.launches - l0
-                st["graphs"] = (ga, gb)
-                ga.replay()
-                if self.dp is not None:
-                    self.dp.allreduce_gradients()
-                    gb.replay()
+                st["graphs"] = (ga, ga2, gb)
+                run(ga, ga2, gb)
             else:
-                part_a()
-                if self.dp is not None:
-                    self.dp.allreduce_gradients()
-                part_b()
+                run(None, None, None)
         self.global_step = int(global_step) + 1
         if fetch_loss:
             vals = eng.scalars[:4].tolist()          # one D2H read

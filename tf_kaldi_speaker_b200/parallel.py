@@ -79,8 +79,26 @@ class DataParallel(object):
         st.refresh_shadows()
         trainer.dp = self
 
+        # Two gradient buckets of the flat buffer: [tdnn6 .. head] is complete once the utterance-level backward has
+        # run (a third of the way into the backward pass), [tdnn1 .. pooling] only at its end.
+        self.split = st.specs["tdnn/tdnn6_dense/kernel"].offset if "tdnn/tdnn6_dense/kernel" in st.specs else 0
+        self._pending = []
+
     def allreduce_gradients(self):
         self.comm.allreduce_(self.trainer.engine.store.grads)
+
+    def allreduce_bucket_async(self, which):
+        """Enqueue the sum all-reduce of one gradient bucket on NCCL's stream (ordered after the work already on the
+        current stream) and return immediately, so later kernels of the current stream overlap it."""
+        g = self.trainer.engine.store.grads
+        t = g[self.split:] if which == "head" else g[:self.split]
+        if self.world > 1 and t.numel() > 0:
+            self._pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.comm.group, async_op=True))
+
+    def wait_all(self):
+        for w in self._pending:
+            w.wait()          # the current stream waits for the collective; the host does not block
+        self._pending = []
 
     def mean_scalar(self, local_mean_scaled):
         # each rank's loss scalar is sum_i CE_i / (N*B): the global mean is their sum

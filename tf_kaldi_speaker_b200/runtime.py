@@ -383,6 +383,7 @@ class Engine(object):
     # ---- step bookkeeping
     def begin_step(self, training):
         self.tape = []
+        self.tape_mark = None
         self.penalties = []
         self.training = training
         sc = self.scalars                   # make sure the scalars exist before the fill
@@ -394,10 +395,23 @@ class Engine(object):
         else:
             st.arena[:max(st.arena_used, 32)].zero_()
 
-    def backward(self):
-        for fn in reversed(self.tape):
+    def mark_utterance_level(self):
+        """Called by the network builder right after the pooling layer: backward closures recorded from here on belong to
+        the utterance-level layers and the head, whose gradients are complete early in the backward pass (the
+        data-parallel wrapper all-reduces them while the frame-level backward is still running)."""
+        self.tape_mark = len(self.tape)
+
+    def backward(self, part=None):
+        """part=None: everything; "head": closures after the pooling mark (head, tdnn7, tdnn6); "trunk": the rest."""
+        mark = self.tape_mark if self.tape_mark is not None else 0
+        if part == "head":
+            fns, self.tape = self.tape[mark:], self.tape[:mark]
+        elif part == "trunk":
+            fns, self.tape = self.tape[:mark], []
+        else:
+            fns, self.tape = self.tape, []
+        for fn in reversed(fns):
             fn()
-        self.tape = []
 
     # ---- frame-level ops ------------------------------------------------------------------------
     def pack_input(self, features, lengths=None, k=5, dpad=32):

@@ -1,1 +1,2 @@
-timeout 600 python tools/config_bench.py --json gpurun_out/config_bench.json 2>&1 | tail -25
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-300
