@@ -42,6 +42,15 @@ def flops_train(t, d, c):
     return 3 * flops_fwd(t, d, c) - 2 * 512 * 5 * d * (t - 4)
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the GEMM launches of one step from the committed `ncu --set full` capture."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_ncu_traffic.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["dram_read_bytes"]) + float(j["dram_write_bytes"]), int(j["launches"])
+    return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -274,7 +283,10 @@ def run_ours(args):
                 "roofline": {"bound": "tensor", "kernel": "xv::gemm_kernel<EPI> (tcgen05 implicit GEMM, all %d launches "
                                                           "of a step: fwd/dgrad/wgrad/head)" % n_gemm,
                              "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                             "frac": (achieved / sustained) if achieved else None, "traffic": None,
+                             "frac": (achieved / sustained) if achieved else None, "traffic": ncu_traffic()[0],
+                             "traffic_note": "sum of dram__bytes_read + dram__bytes_write over the %s GEMM launches of one "
+                                             "step (profiles/r01_gemm_ncu_full.md); outputs mostly stay in the 126 MB L2"
+                                             % ncu_traffic()[1],
                              "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % (how, burst),
                              "gemm_ms_per_step": gemm_ms / 3.0, "gemm_flops_per_step": gemm_flops / 3.0,
                              "step_frac": seg_s * ftrain / (world * sustained * 1e12),

@@ -102,6 +102,44 @@ def case_dgrad(B_=3, T=40, cin=256, cout=512, k=5):
     return {"err": _err(dx.float().reshape(B_, T, cin), ref)}
 
 
+def case_dgrad_bnbwd(B_=4, T=70, cin=512, cout=512, k=5, neg_slope=0.0):
+    """dgrad whose epilogue also accumulates the BN-backward reductions of the producer layer:
+    g = dX * act'(y*scale + shift); dbeta = sum g; dgamma = sum g * (y - mean) * rstd."""
+    import torch
+    from tf_kaldi_speaker_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(5)
+    R = B_ * T
+    valid = T - (k - 1)
+    dy = _mk((R, cout), g)
+    dyv = dy.reshape(B_, T, cout).clone()
+    dyv[:, valid:] = 0
+    dy = dyv.reshape(R, cout).contiguous()
+    w = _mk((k * cin, cout), g, 0.05)
+    y = _mk((R, cin), g)
+    scale = 0.5 + torch.rand(cin, generator=g, device="cuda")
+    scale[::7] *= -1           # negative gamma: the activation mask must follow the sign of z, not of y
+    shift = 0.3 * torch.randn(cin, generator=g, device="cuda")
+    mean = 0.2 * torch.randn(cin, generator=g, device="cuda")
+    rstd = 0.5 + torch.rand(cin, generator=g, device="cuda")
+    dbeta = torch.zeros(cin, device="cuda")
+    dgamma = torch.zeros(cin, device="cuda")
+    dx = torch.zeros(R, cin, device="cuda", dtype=torch.bfloat16)
+    L.gemm(L.operand(dy, False, div=cout, tap_rows=-1), L.operand(w, False, div=cout, tap_rows=cin),
+           R, cin, k * cout, dx, epilogue=L.EPI_BF16, col_sum=dbeta, col_sumsq=dgamma,
+           bn_bwd=(y, scale, shift, mean, rstd, neg_slope))
+    torch.cuda.synchronize()
+    wf = w.float().reshape(k, cin, cout)
+    dyf = dy.float().reshape(B_, T, cout)
+    ref = torch.zeros(B_, T, cin, device="cuda")
+    for j in range(k):
+        ref[:, j:] += dyf[:, :T - j] @ wf[j].t()
+    ref = ref.reshape(R, cin)
+    z = y.float() * scale + shift
+    gg = ref * torch.where(z > 0, torch.ones_like(z), torch.full_like(z, neg_slope))
+    return {"err": _err(dx.float(), ref), "err_dbeta": _err(dbeta, gg.sum(0)),
+            "err_dgamma": _err(dgamma, (gg * (y.float() - mean) * rstd).sum(0))}
+
+
 def case_wgrad(B_=4, T=64, cin=128, cout=512, k=5, splits=3):
     """dW_j = sum_r X[r+j]^T dY[r] : A = X MN-major (div=cin, tap +1), B = dY MN-major, split-K atomics."""
     import torch
@@ -142,6 +180,8 @@ def _cases():
         "conv_fwd": lambda: case_conv_fwd(),
         "conv_fwd_k7": lambda: case_conv_fwd(B_=5, T=100, cin=512, cout=512, k=7),
         "dgrad": lambda: case_dgrad(),
+        "dgrad_bnbwd_relu": lambda: case_dgrad_bnbwd(),
+        "dgrad_bnbwd_lrelu_dense": lambda: case_dgrad_bnbwd(B_=3, T=50, cin=512, cout=1536, k=1, neg_slope=0.2),
         "wgrad": lambda: case_wgrad(),
         "wgrad_nosplit": lambda: case_wgrad(splits=1),
     }

@@ -37,7 +37,21 @@ for k, r in enumerate(data):
             pass
         vals.append(v)
     lines.append("| %d | `%s` | %s |" % (k, name, " | ".join(vals)))
+# per-step DRAM traffic of the captured launches (bench.py reports it as roofline.traffic)
+tot_r = sum(float(r[H["dram__bytes_read.sum"]]) for r in data)
+tot_w = sum(float(r[H["dram__bytes_write.sum"]]) for r in data)
+unit_r = rows[1][H["dram__bytes_read.sum"]]
+lines.append("")
+lines.append("DRAM traffic of these %d launches: read %.1f %s, write %.1f %s" % (len(data), tot_r, unit_r, tot_w,
+                                                                                rows[1][H["dram__bytes_write.sum"]]))
 text = "\n".join(lines)
 print(text)
+for a in sys.argv[2:]:
+    if a.startswith("--traffic-json="):
+        import json
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        json.dump({"launches": len(data), "dram_read_bytes": tot_r * scale.get(unit_r, 1e6),
+                   "dram_write_bytes": tot_w * scale.get(rows[1][H["dram__bytes_write.sum"]], 1e6),
+                   "source": src}, open(a.split("=", 1)[1], "w"), indent=1)
 if out:
     open(out, "w").write(text + "\n")
