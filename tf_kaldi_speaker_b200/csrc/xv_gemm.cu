@@ -1,4 +1,6 @@
 // Host side of the tcgen05 implicit-GEMM: tensor-map encoding, argument checks, dispatch.
+#include <stdlib.h>
+
 #include "xv_gemm_kernel.cuh"
 
 namespace xv {
@@ -74,15 +76,29 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   if ((a->col_sum == nullptr) != (a->col_sumsq == nullptr) && a->epilogue == XV_EPI_BF16)
     return set_error(XV_ERR_INVALID, "col_sum and col_sumsq must be given together");
 
+  // CTA pairs (cta_group::2, 256 x 256 tiles) for the matrix-output epilogues when there are enough tiles to fill
+  // the 74 SM pairs; head epilogues and small problems stay on one CTA per 128 x 256 tile.  XV_GEMM_CG=1|2 forces it.
+  int cg = 1;
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("XV_GEMM_CG");
+      forced = e ? atoi(e) : 0;
+    }
+    const bool can = (a->epilogue == XV_EPI_BF16 || a->epilogue == XV_EPI_F32);
+    const long long pair_tiles = static_cast<long long>((a->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) *
+                                 ((a->N + BLOCK_N - 1) / BLOCK_N) * (a->splits > 0 ? a->splits : 1);
+    if (can && ((forced == 2) || (forced == 0 && pair_tiles >= 64))) cg = 2;
+  }
   GemmKernelParams kp;
   memset(&kp, 0, sizeof(kp));
   int rc = make_tmap(&kp.tma_a, a->a, BLOCK_M);
   if (rc) return rc;
-  rc = make_tmap(&kp.tma_b, a->b, BLOCK_N);
+  rc = make_tmap(&kp.tma_b, a->b, BLOCK_N / cg);
   if (rc) return rc;
   kp.M = a->M; kp.N = a->N; kp.K = a->K;
   kp.a_div = a->a.div; kp.a_tap = a->a.tap_rows; kp.b_div = a->b.div; kp.b_tap = a->b.tap_rows;
-  kp.num_m = (a->M + BLOCK_M - 1) / BLOCK_M;
+  kp.num_m = (a->M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
   kp.num_n = (a->N + BLOCK_N - 1) / BLOCK_N;
   kp.num_kb = (a->K + BLOCK_K - 1) / BLOCK_K;
   int splits = a->splits < kp.num_kb ? a->splits : kp.num_kb;
@@ -118,14 +134,21 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   rc = device_sm_count(&sms);
   if (rc) return rc;
   const long long tiles = static_cast<long long>(kp.num_m) * kp.num_n * kp.splits;
-  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  const int units = sms / cg;                                   // CTAs (cg = 1) or CTA pairs (cg = 2) on the device
+  const int grid = static_cast<int>(tiles < units ? tiles : units) * cg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   kp.a_mn = a->a.mn_major != 0; kp.b_mn = a->b.mn_major != 0;
+  if (cg == 2) {
+    switch (a->epilogue) {
+      case XV_EPI_BF16: return launch_gemm<XV_EPI_BF16, 2>(kp, grid, s);
+      default: return launch_gemm<XV_EPI_F32, 2>(kp, grid, s);
+    }
+  }
   switch (a->epilogue) {
-    case XV_EPI_BF16: return launch_gemm<XV_EPI_BF16>(kp, grid, s);
-    case XV_EPI_F32: return launch_gemm<XV_EPI_F32>(kp, grid, s);
-    case XV_EPI_HEAD_FWD: return launch_gemm<XV_EPI_HEAD_FWD>(kp, grid, s);
-    case XV_EPI_HEAD_BWD: return launch_gemm<XV_EPI_HEAD_BWD>(kp, grid, s);
+    case XV_EPI_BF16: return launch_gemm<XV_EPI_BF16, 1>(kp, grid, s);
+    case XV_EPI_F32: return launch_gemm<XV_EPI_F32, 1>(kp, grid, s);
+    case XV_EPI_HEAD_FWD: return launch_gemm<XV_EPI_HEAD_FWD, 1>(kp, grid, s);
+    case XV_EPI_HEAD_BWD: return launch_gemm<XV_EPI_HEAD_BWD, 1>(kp, grid, s);
     default: return set_error(XV_ERR_INVALID, "unknown epilogue %d", a->epilogue);
   }
 }

@@ -1,5 +1,5 @@
-// Instantiation of the tcgen05 GEMM kernel for epilogue 1 (see xv_gemm_kernel.cuh).
+// Instantiation of the tcgen05 GEMM kernel for epilogue 1, one CTA per tile (see xv_gemm_kernel.cuh).
 #include "xv_gemm_kernel.cuh"
 namespace xv {
-template int launch_gemm<1>(const GemmKernelParams&, int, cudaStream_t);
+template int launch_gemm<1, 1>(const GemmKernelParams&, int, cudaStream_t);
 }

@@ -20,10 +20,21 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+// CG = CTAs cooperating on one output tile.  CG = 1: 128 x 256 tile, 4 stages of (16 KB A + 32 KB B).
+// CG = 2 (tcgen05 cta_group::2, a 2-CTA cluster on one TPC): 256 x 256 tile, each CTA stages its 128 rows of A and
+// HALF of B (the MMA reads the other half from the peer's shared memory), 6 stages of (16 + 16) KB -- a third less
+// L2 -> SM traffic and shared-memory fill per FLOP than CG = 1, which is what bounds the 1-CTA kernel.
+template <int CG>
+struct GemmCfg {
+  static constexpr int B_ROWS = BLOCK_N / CG;                       // B (N) rows staged per CTA
+  static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = CG == 1 ? 4 : 6;
+  static constexpr int TILE_M = BLOCK_M * CG;
+};
+constexpr int MAX_STAGES = 6;
+constexpr int PIPE_BYTES = 4 * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2);   // 192 KB in both configurations
 constexpr int CHUNK_BYTES = 64 * BLOCK_K * 2;          // one MN-major 64x64 box = 8 KB
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;
@@ -33,7 +44,9 @@ constexpr int STAGING_BYTES = 32 * 128;                // per epilogue warp: one
 constexpr int STATS_BYTES = 2 * BLOCK_N * 4;           // [sum|sumsq][col], accumulated with shared-memory atomics
 constexpr int BAR_BYTES = 256;
 // The dynamic shared-memory window is declared 1024-byte aligned (128B-swizzle atom); no slack is reserved.
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + STATS_BYTES + BAR_BYTES;
+constexpr int SMEM_BYTES = PIPE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + STATS_BYTES + BAR_BYTES;
+static_assert(GemmCfg<1>::STAGES * GemmCfg<1>::STAGE_BYTES == PIPE_BYTES && GemmCfg<2>::STAGES * GemmCfg<2>::STAGE_BYTES == PIPE_BYTES,
+              "both pipeline configurations fill the same 192 KB");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 struct alignas(64) GemmKernelParams {
@@ -124,20 +137,44 @@ __device__ __forceinline__ void stage_store16(uint8_t* stg, int row, int chunk, 
   *reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
 }
 
-template <int EPI>
+template <int CG>
+__device__ __forceinline__ void tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  if (CG == 2) tma_load_2d_cg2(dst, map, bar, c0, c1);
+  else tma_load_2d(dst, map, bar, c0, c1);
+}
+template <int CG>
+__device__ __forceinline__ void umma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if (CG == 2) umma_bf16_cg2(d, da, db, idesc, acc);
+  else umma_bf16(d, da, db, idesc, acc);
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_n(uint64_t* bar) {
+  if (CG == 2) umma_commit_cg2(bar);
+  else umma_commit(bar);
+}
+
+template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmKernelParams p) {
+  using Cfg = GemmCfg<CG>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int B_STAGE_BYTES = Cfg::B_STAGE_BYTES;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   const bool A_MN = p.a_mn != 0, B_MN = p.b_mn != 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* smem_stg = smem + STAGES * STAGE_BYTES;
+  uint8_t* smem_stg = smem + PIPE_BYTES;
   float* s_stats = reinterpret_cast<float*>(smem_stg + NUM_EPI_WARPS * STAGING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_stats) + STATS_BYTES);
-  uint64_t* full_bar = bars;                    // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
-  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* full_bar = bars;                            // [MAX_STAGES]  (CG = 2: only the leader's are used)
+  uint64_t* empty_bar = bars + MAX_STAGES;              // [MAX_STAGES]
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;          // [2]
+  uint64_t* tmem_empty = bars + 2 * MAX_STAGES + 2;     // [2]           (CG = 2: the leader's collect both CTAs)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  // CTA pair bookkeeping: rank 0 ("leader") issues the MMAs for both CTAs
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int unit_id = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // tile-walking unit
+  const int num_units = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,35 +196,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS * CG);   // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_ptr, TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_ptr, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < 2 * BLOCK_N; i += NUM_THREADS) s_stats[i] = 0.f;
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();      // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   // Everything above (barrier init, TMEM allocation, tensor-map prefetch) is independent of earlier kernels; global
   // memory is first touched below, after the previous kernel of the stream has completed.
   pdl_wait();
 
-  const int total_tiles = p.num_m * p.num_n * p.splits;
+  const int total_tiles = p.num_m * p.num_n * p.splits;     // num_m counts TILE_M-row blocks
 
   if (warp_idx == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit_id; tile < total_tiles; tile += num_units) {
         const int n_blk = tile % p.num_n;
         const int m_blk = (tile / p.num_n) % p.num_m;
         const int split = tile / (p.num_n * p.num_m);
-        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        const int m0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M;   // this CTA's 128 rows of A
+        const int n0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * Cfg::B_ROWS;   // this CTA's share of B
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         // Tile coordinates are walked incrementally: the only integer divisions happen here, once per tile
@@ -213,27 +257,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
         const int b_wrap = (!B_MN && p.b_div) ? p.b_div : 0x7fffffff;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          // CG = 2: both CTAs' loads complete on the LEADER's barrier, which its producer arms for all the bytes
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES * CG);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
           if (!A_MN) {
-            tma_load_2d(sa, &p.tma_a, &full_bar[stage], a_col, a_row);
+            tma_load<CG>(sa, &p.tma_a, &full_bar[stage], a_col, a_row);
             a_col += BLOCK_K;
             if (a_col >= a_wrap) { a_col = 0; a_row += p.a_tap; }
           } else {
 #pragma unroll
             for (int c = 0; c < BLOCK_M / 64; ++c)
-              tma_load_2d(sa + c * CHUNK_BYTES, &p.tma_a, &full_bar[stage], a_col + 64 * c, a_row);
+              tma_load<CG>(sa + c * CHUNK_BYTES, &p.tma_a, &full_bar[stage], a_col + 64 * c, a_row);
             a_row += BLOCK_K;
           }
           if (!B_MN) {
-            tma_load_2d(sb, &p.tma_b, &full_bar[stage], b_col, b_row);
+            tma_load<CG>(sb, &p.tma_b, &full_bar[stage], b_col, b_row);
             b_col += BLOCK_K;
             if (b_col >= b_wrap) { b_col = 0; b_row += p.b_tap; }
           } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c)
-              tma_load_2d(sb + c * CHUNK_BYTES, &p.tma_b, &full_bar[stage], b_col + 64 * c, b_row);
+            for (int c = 0; c < Cfg::B_ROWS / 64; ++c)
+              tma_load<CG>(sb + c * CHUNK_BYTES, &p.tma_b, &full_bar[stage], b_col + 64 * c, b_row);
             b_row += BLOCK_K;
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -241,9 +286,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       }
     }
   } else if (warp_idx == 1) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ============================== MMA issuer (CG = 2: leader CTA only) ==============================
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(Cfg::TILE_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major SW128: 64-wide MN chunks
       // CHUNK_BYTES apart (LBO), 8-k-row groups 1024 B apart (SBO).
       const uint32_t a_lbo = A_MN ? CHUNK_BYTES : 16, b_lbo = B_MN ? CHUNK_BYTES : 16;
@@ -255,7 +300,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int tile = unit_id; tile < total_tiles; tile += num_units, ++local) {
         const int split = tile / (p.num_n * p.num_m);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
@@ -271,12 +316,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           const uint64_t db = db0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(d_tmem, da + static_cast<uint64_t>((k * a_kstep) >> 4), db + static_cast<uint64_t>((k * b_kstep) >> 4),
-                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+            umma<CG>(d_tmem, da + static_cast<uint64_t>((k * a_kstep) >> 4), db + static_cast<uint64_t>((k * b_kstep) >> 4),
+                     idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit_n<CG>(&empty_bar[stage]);   // frees the smem slot (in both CTAs) once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+        umma_commit_n<CG>(&tmem_full[acc]);       // accumulator complete -> epilogue (of both CTAs)
       }
     }
   } else if (warp_idx >= 4) {
@@ -288,11 +333,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     uint8_t* stg = smem_stg + e * STAGING_BYTES;
     const bool tma_out = p.use_tma_out != 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = unit_id; tile < total_tiles; tile += num_units, ++local) {
       const int n_blk = tile % p.num_n;
       const int m_blk = (tile / p.num_n) % p.num_m;
       const int split = tile / (p.num_n * p.num_m);
-      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+      const int m0 = m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BLOCK_M, n0 = n_blk * BLOCK_N;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int row0 = m0 + qd * 32;
@@ -572,7 +617,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&tmem_empty[acc]);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
 
       if (EPI == XV_EPI_HEAD_FWD && row_ok) {
         p.head.part_max[static_cast<long long>(n_blk * 2 + hf) * p.M + m] = run_max;
@@ -593,30 +641,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();      // neither CTA may exit (or free TMEM) while the peer's MMAs read its smem
+  else __syncthreads();
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int EPI>
+template <int EPI, int CG>
 int launch_gemm(const GemmKernelParams& kp, int grid, cudaStream_t stream) {
-  auto kern = gemm_kernel<EPI>;
+  auto kern = gemm_kernel<EPI, CG>;
   static bool configured = false;
   if (!configured) {
     XV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  launch_pdl(kern, grid, NUM_THREADS, SMEM_BYTES, stream, kp);
+  launch_cluster(kern, grid, NUM_THREADS, SMEM_BYTES, stream, CG, kp);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
 
 // explicit instantiations live in xv_gemm_epi*.cu (one TU per epilogue keeps the parallel build short)
-extern template int launch_gemm<0>(const GemmKernelParams&, int, cudaStream_t);
-extern template int launch_gemm<1>(const GemmKernelParams&, int, cudaStream_t);
-extern template int launch_gemm<2>(const GemmKernelParams&, int, cudaStream_t);
-extern template int launch_gemm<3>(const GemmKernelParams&, int, cudaStream_t);
+extern template int launch_gemm<0, 1>(const GemmKernelParams&, int, cudaStream_t);
+extern template int launch_gemm<1, 1>(const GemmKernelParams&, int, cudaStream_t);
+extern template int launch_gemm<2, 1>(const GemmKernelParams&, int, cudaStream_t);
+extern template int launch_gemm<3, 1>(const GemmKernelParams&, int, cudaStream_t);
+extern template int launch_gemm<0, 2>(const GemmKernelParams&, int, cudaStream_t);
+extern template int launch_gemm<1, 2>(const GemmKernelParams&, int, cudaStream_t);
 
 }  // namespace xv

@@ -1,2 +1,4 @@
-python -m pytest tests -m gpu -x -q --deselect tests/test_gemm_gpu.py 2>&1 | tail -3
-python bench.py --steps 200 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-260
+echo "=== CG auto"; python tools/gemm_bench.py 2>&1 | grep -E "fwd|dgrad|wgrad" | cut -c1-100
+echo "=== CG=1";  XV_GEMM_CG=1 python tools/gemm_bench.py 2>&1 | grep -E "fwd|dgrad|wgrad" | cut -c1-72
+python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-260
+XV_GEMM_CG=1 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-260
