@@ -133,6 +133,8 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   int sms = 0;
   rc = device_sm_count(&sms);
   if (rc) return rc;
+  if (kp.bnb.y != nullptr && !kp.use_tma_out)
+    return set_error(XV_ERR_INVALID, "bn_bwd fusion needs a TMA-storable output (16-byte aligned, no accumulate)");
   const long long tiles = static_cast<long long>(kp.num_m) * kp.num_n * kp.splits;
   const int units = sms / cg;                                   // CTAs (cg = 1) or CTA pairs (cg = 2) on the device
   const int grid = static_cast<int>(tiles < units ? tiles : units) * cg;

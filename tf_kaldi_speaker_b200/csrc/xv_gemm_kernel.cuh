@@ -385,42 +385,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 
         if (EPI == XV_EPI_BF16) {
-          if (do_stats) {
+          if (do_stats && p.bnb.y == nullptr) {
+            // forward BN statistics: per-column sum / sum of squares of the bias-free fp32 accumulator over the valid
+            // rows (warp-shuffle column sums; a column pass over the staged bf16 tile measured 15-20 % slower here)
             float s[32], q[32];
-            if (p.bnb.y == nullptr) {        // forward: per-column sum / sum of squares of the bias-free accumulator
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { s[j] = row_valid ? v[j] : 0.f; q[j] = s[j] * s[j]; }
-            } else {
-              // dgrad: v = dLoss/d act(BN(y)).  g = v * act'(z); dbeta += g, dgamma += g * yhat.  Rows >= M carry a zero
-              // accumulator (TMA zero fill) and invalid rows a zero gradient, so only the y loads need the row guard.
-              uint4 yq[4];
-              const uint4* yrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bnb.y) +
-                                                                 static_cast<long long>(m) * p.bnb.ldy + nc0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) yq[j] = row_ok ? __ldg(yrow + j) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 sc4 = __ldg(reinterpret_cast<const float4*>(p.bnb.scale + nc0) + j4);
-                const float4 sh4 = __ldg(reinterpret_cast<const float4*>(p.bnb.shift + nc0) + j4);
-                const float4 mu4 = __ldg(reinterpret_cast<const float4*>(p.bnb.mean + nc0) + j4);
-                const float4 rs4 = __ldg(reinterpret_cast<const float4*>(p.bnb.rstd + nc0) + j4);
-                const uint4 yy = yq[j4 >> 1];
-                const uint32_t w0 = (j4 & 1) ? yy.z : yy.x, w1 = (j4 & 1) ? yy.w : yy.y;
-                const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0));
-                const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1));
-                const float yv[4] = {y01.x, y01.y, y23.x, y23.y};
-                const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
-                const float muv[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  const int j = 4 * j4 + jj;
-                  const float z = fmaf(yv[jj], scv[jj], shv[jj]);
-                  const float g = v[j] * (z > 0.f ? 1.0f : p.bnb.neg_slope);
-                  s[j] = g;
-                  q[j] = g * (yv[jj] - muv[jj]) * rsv[jj];
-                }
-              }
-            }
+            for (int j = 0; j < 32; ++j) { s[j] = row_valid ? v[j] : 0.f; q[j] = s[j] * s[j]; }
             warp_column_sums(s, lane);
             warp_column_sums(q, lane);
             atomicAdd(&s_stats[hf * EPI_COLS + c * 32 + lane], s[0]);
@@ -456,6 +426,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
               if (lane == 0) {
                 tma_store_2d(&p.tma_out, stg, nc0 - cc * 32, row0);
                 bulk_commit();
+              }
+              if (do_stats && p.bnb.y != nullptr) {
+                // Fused BN backward of the producer layer: column pass over the staged 32-row x 64-column box (while the
+                // TMA store drains it).  Lane l owns columns 2l, 2l+1 -- one conflict-free 4-byte shared-memory word per
+                // row -- so the column sums need no shuffles, y is read with coalesced 128-byte rows and the per-column
+                // constants live in 8 registers.  g uses the STORED (bf16) gradient, like the stand-alone kernel.
+                const int colb = nc0 - cc * 32 + 2 * lane;                 // first of this lane's two columns
+                const bool col_ok = colb < p.N;                            // N is even: both columns or neither
+                const uint32_t vmask = __ballot_sync(0xffffffffu, row_ok);
+                const uint8_t* sbase = stg + ((lane & 3) << 2);
+                const int jc = lane >> 2;
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                if (col_ok) {
+                  // g = dX * act'(y*scale + shift); dbeta += g, dgamma += g * (y - mean) * rstd
+                  const float sc0 = __ldg(p.bnb.scale + colb), sc1 = __ldg(p.bnb.scale + colb + 1);
+                  const float sh0 = __ldg(p.bnb.shift + colb), sh1 = __ldg(p.bnb.shift + colb + 1);
+                  const float mu0 = __ldg(p.bnb.mean + colb), mu1 = __ldg(p.bnb.mean + colb + 1);
+                  const uint32_t* yp = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(p.bnb.y) +
+                                                                         static_cast<long long>(row0) * p.bnb.ldy + colb);
+                  const long long ystep = p.bnb.ldy >> 1;                   // row stride in 4-byte words
+#pragma unroll
+                  for (int half = 0; half < 2; ++half) {
+                    uint32_t yw[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                      yw[r] = ((vmask >> (half * 16 + r)) & 1u) ? __ldg(yp + (half * 16 + r) * ystep) : 0u;
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) {
+                      const int r = half * 16 + rr;
+                      const uint32_t w = *reinterpret_cast<const uint32_t*>(sbase + r * 128 + ((jc ^ (r & 7)) << 4));
+                      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+                      const float2 yv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[rr]));
+                      const bool live = (vmask >> r) & 1u;
+                      const float g0 = live ? f.x * (fmaf(yv.x, sc0, sh0) > 0.f ? 1.0f : p.bnb.neg_slope) : 0.f;
+                      const float g1 = live ? f.y * (fmaf(yv.y, sc1, sh1) > 0.f ? 1.0f : p.bnb.neg_slope) : 0.f;
+                      s0 += g0; s1 += g1;
+                      q0 = fmaf(g0, yv.x - mu0, q0); q1 = fmaf(g1, yv.y - mu1, q1);
+                    }
+                  }
+                  q0 *= __ldg(p.bnb.rstd + colb);
+                  q1 *= __ldg(p.bnb.rstd + colb + 1);
+                }
+                if (col_ok) {
+                  const int sc_ = hf * EPI_COLS + (c - cc) * 32 + 2 * lane;
+                  atomicAdd(&s_stats[sc_], s0);
+                  atomicAdd(&s_stats[sc_ + 1], s1);
+                  atomicAdd(&s_stats[BLOCK_N + sc_], q0);
+                  atomicAdd(&s_stats[BLOCK_N + sc_ + 1], q1);
+                }
               }
             }
           } else if (row_ok) {

@@ -135,7 +135,8 @@ def case_dgrad_bnbwd(B_=4, T=70, cin=512, cout=512, k=5, neg_slope=0.0):
         ref[:, j:] += dyf[:, :T - j] @ wf[j].t()
     ref = ref.reshape(R, cin)
     z = y.float() * scale + shift
-    gg = ref * torch.where(z > 0, torch.ones_like(z), torch.full_like(z, neg_slope))
+    # the reductions use the gradient as it is STORED (bf16), like the stand-alone xv_bn_act_bwd_reduce kernel
+    gg = ref.to(torch.bfloat16).float() * torch.where(z > 0, torch.ones_like(z), torch.full_like(z, neg_slope))
     return {"err": _err(dx.float(), ref), "err_dbeta": _err(dbeta, gg.sum(0)),
             "err_dgamma": _err(dgamma, (gg * (y.float() - mean) * rstd).sum(0))}
 
