@@ -272,6 +272,18 @@ XV_API int xv_head_combine(const float* part_max, const float* part_sum, const f
 XV_API int xv_head_finish_dx(const float* dx_gemm, const float* gnorm, const float* x, const float* xnorm, const float* u,
                              const float* u_rinv, float scaling, float* du, int B, int E, void* stream);
 XV_API int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, int E, int C, void* stream);
+/* Class-sharded head (north_star "Data parallelism": the speaker matrix split by columns over the ranks; the reference
+ * has no multi-device path, README.md:1,82,115).  Each rank runs the XV_EPI_HEAD_* epilogues on its own columns for
+ * the all-gathered rows:
+ *   xv_head_local_labels    labels[R] (global class ids) -> out[R] = label - lo inside [0, n_local), else -1 (no target);
+ *   xv_head_shard_partials  per-tile partials -> out f32 [3, R] = this shard's per-row (max, sum exp(z'-max), target|0);
+ *   xv_head_combine_shards  gathered parts f32 [S, 3, R] -> lse[R] (the all-reduce(max) / all-reduce(sum) pair of a
+ *                           sharded softmax evaluated on the gathered pairs) and loss += sum_i (lse_i - target_i)*inv_batch. */
+XV_API int xv_head_local_labels(const int32_t* labels, int lo, int n_local, int32_t* out, int R, void* stream);
+XV_API int xv_head_shard_partials(const float* part_max, const float* part_sum, const float* target_logit, int nblk, int R,
+                                  float* out, void* stream);
+XV_API int xv_head_combine_shards(const float* parts, int S, int R, float inv_batch, float* lse, float* loss_rows,
+                                  float* loss, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer over one flat f32 parameter buffer whose tensors start at multiples of 1024 elements

@@ -197,6 +197,70 @@ __global__ void __launch_bounds__(32 * HROWG) head_finish_dw_kernel(float* __res
   }
 }
 
+
+// ---- class-sharded head (the speaker matrix split by columns over the data-parallel ranks) --------------------------
+// Global labels -> labels local to the shard that owns columns [lo, lo + n_local): out-of-shard rows get -1, which no
+// column of the fused GEMM epilogues matches (no margin, no target logit, no ||x|| gradient from this shard).
+__global__ void head_local_labels_kernel(const int* __restrict__ labels, int lo, int n_local, int* __restrict__ out, int R) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  const int l = labels[i] - lo;
+  out[i] = (l >= 0 && l < n_local) ? l : -1;
+}
+
+// This shard's per-row (max, sum exp(z' - max), target logit or 0) from the per-tile partials of the head-forward GEMM:
+// out f32 [3, R].  One warp per row, as head_combine_kernel.
+__global__ void __launch_bounds__(128) head_shard_partials_kernel(const float* __restrict__ part_max,
+                                                                  const float* __restrict__ part_sum,
+                                                                  const float* __restrict__ target_logit, int nblk, int R,
+                                                                  float* __restrict__ out) {
+  pdl_entry();
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= R) return;
+  float gmax = -INFINITY;
+  for (int k = lane; k < nblk; k += 32) gmax = fmaxf(gmax, part_max[static_cast<long long>(k) * R + i]);
+  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  float s = 0.f;
+  for (int k = lane; k < nblk; k += 32)
+    s += part_sum[static_cast<long long>(k) * R + i] * expf(part_max[static_cast<long long>(k) * R + i] - gmax);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    out[i] = gmax;
+    out[R + i] = s;
+    out[2 * R + i] = target_logit[i];     // zero unless this shard owns the row's label
+  }
+}
+
+// The all-gathered shard partials [S, 3, R] -> lse_i = log sum_s sum_s exp(max_s - gmax) + gmax (the all-reduce(max) /
+// all-reduce(sum) pair of a class-sharded softmax, done locally on the gathered (max, sum) pairs), target logit =
+// sum over shards (one owner), loss += sum_i (lse_i - target_i) * inv_batch.  One thread per row.
+__global__ void __launch_bounds__(128) head_combine_shards_kernel(const float* __restrict__ parts, int S, int R,
+                                                                  float inv_batch, float* __restrict__ lse,
+                                                                  float* __restrict__ loss_rows, float* loss) {
+  pdl_entry();
+  __shared__ float sh[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float li = 0.f;
+  if (i < R) {
+    float gmax = -INFINITY;
+    for (int s = 0; s < S; ++s) gmax = fmaxf(gmax, parts[(static_cast<long long>(s) * 3) * R + i]);
+    float acc = 0.f, tgt = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float* ps = parts + (static_cast<long long>(s) * 3) * R;
+      acc += ps[R + i] * expf(ps[i] - gmax);
+      tgt += ps[2 * R + i];
+    }
+    const float l = logf(acc) + gmax;
+    lse[i] = l;
+    li = l - tgt;
+    if (loss_rows) loss_rows[i] = li;
+  }
+  const float tot = block_sum(li, sh);
+  if (threadIdx.x == 0) atomicAdd(loss, tot * inv_batch);
+}
+
 }  // namespace xv
 
 using namespace xv;
@@ -243,6 +307,32 @@ extern "C" int xv_head_finish_dx(const float* dx_gemm, const float* gnorm, const
 extern "C" int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, int E, int C, void* stream) {
   if (!dw || !w || !inv_norm || E <= 0 || C <= 0 || (C & 1)) return set_error(XV_ERR_INVALID, "xv_head_finish_dw: bad arguments (C must be even)");
   ::xv::launch_pdl((head_finish_dw_kernel), ceil_div(C, 64), 32 * HROWG, 0, static_cast<cudaStream_t>(stream), dw, w, inv_norm, E, C);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_head_local_labels(const int32_t* labels, int lo, int n_local, int32_t* out, int R, void* stream) {
+  if (!labels || !out || R <= 0 || n_local <= 0 || lo < 0) return set_error(XV_ERR_INVALID, "xv_head_local_labels: bad arguments");
+  ::xv::launch_pdl((head_local_labels_kernel), ceil_div(R, 128), 128, 0, static_cast<cudaStream_t>(stream), labels, lo, n_local, out, R);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_head_shard_partials(const float* part_max, const float* part_sum, const float* target_logit, int nblk,
+                                      int R, float* out, void* stream) {
+  if (!part_max || !part_sum || !target_logit || !out || nblk <= 0 || R <= 0)
+    return set_error(XV_ERR_INVALID, "xv_head_shard_partials: bad arguments");
+  ::xv::launch_pdl((head_shard_partials_kernel), ceil_div(R, 4), 128, 0, static_cast<cudaStream_t>(stream), part_max, part_sum,
+                   target_logit, nblk, R, out);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_head_combine_shards(const float* parts, int S, int R, float inv_batch, float* lse, float* loss_rows,
+                                      float* loss, void* stream) {
+  if (!parts || !lse || !loss || S <= 0 || R <= 0) return set_error(XV_ERR_INVALID, "xv_head_combine_shards: bad arguments");
+  ::xv::launch_pdl((head_combine_shards_kernel), ceil_div(R, 128), 128, 0, static_cast<cudaStream_t>(stream), parts, S, R, inv_batch,
+                   lse, loss_rows, loss);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

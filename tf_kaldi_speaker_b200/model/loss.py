@@ -21,8 +21,21 @@ def declare_head_variables(engine, embedding_dim, num_outputs, params, loss_type
     l2 = float(params.weight_l2_regularizer)
     if "output_weight_l2_regularizer" in params.dict:
         l2 = float(params.output_weight_l2_regularizer)
-    cpad = _pad_to(num_outputs, 8)
     st = engine.store
+    sh = engine.head_shard
+    if sh is not None:
+        # class-sharded head: this rank declares only its columns [lo, hi); initialisation draws the full [E, C] matrix
+        # from the shared seed and slices it, so the sharded and the replicated model start from the same weights
+        assert sh.num_outputs == num_outputs
+        n_loc, cpad = sh.n_local, _pad_to(sh.n_local, 8)
+        st.declare(VarSpec(name + "/output/kernel", (embedding_dim, n_loc), (embedding_dim, cpad), l2=l2, init="glorot",
+                           fans=(embedding_dim, num_outputs), full_shape=(embedding_dim, num_outputs),
+                           col_range=(sh.lo, sh.hi)))
+        if loss_type == "softmax":
+            st.declare(VarSpec(name + "/output/bias", (n_loc,), (cpad,), full_shape=(num_outputs,),
+                               col_range=(sh.lo, sh.hi)))
+        return
+    cpad = _pad_to(num_outputs, 8)
     st.declare(VarSpec(name + "/output/kernel", (embedding_dim, num_outputs), (embedding_dim, cpad), l2=l2,
                        init="glorot", fans=(embedding_dim, num_outputs)))
     if loss_type == "softmax":
@@ -57,9 +70,15 @@ def _run_head(features, labels, num_outputs, params, is_training, name, head_typ
     scaling = float(getattr(features, "scaling", 0.0) or 0.0)
     bias = (name + "/output/bias") if head_type == L.HEAD_SOFTMAX and (name + "/output/bias") in eng.store else None
     want_logits = bool(params.dict.get("debug_logits", False))
-    loss, logits, x = eng.margin_head(features, labels, name + "/output/kernel", bias, head_type, num_outputs,
-                                      bool(is_training), margin=margin, asoftmax_m=asoftmax_m, scaling=scaling,
-                                      want_logits=want_logits)
+    if eng.head_shard is not None:
+        if want_logits:
+            raise NotImplementedError("debug_logits is not available with the class-sharded head")
+        loss, logits, x = eng.margin_head_sharded(features, labels, name + "/output/kernel", bias, head_type, num_outputs,
+                                                  bool(is_training), margin=margin, asoftmax_m=asoftmax_m, scaling=scaling)
+    else:
+        loss, logits, x = eng.margin_head(features, labels, name + "/output/kernel", bias, head_type, num_outputs,
+                                          bool(is_training), margin=margin, asoftmax_m=asoftmax_m, scaling=scaling,
+                                          want_logits=want_logits)
     params.dict["softmax_w"] = eng.store.view(name + "/output/kernel")      # loss.py:103,211,297
     endpoints = OrderedDict()
     endpoints["logits"] = None if logits is None else logits[:, :num_outputs]

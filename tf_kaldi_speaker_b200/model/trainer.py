@@ -6,6 +6,7 @@ on one CUDA stream.  Host control flow (epochs, logging, checkpoints, LR bookkee
 feature pipeline (dataset/data_loader.py) stays on the host: ``train``/``valid`` take any object with the
 ``start()/fetch()/stop()`` queue protocol of KaldiDataRandomQueue (data_loader.py:310-414).
 """
+import ctypes as C
 import glob
 import os
 import re
@@ -98,6 +99,15 @@ class Trainer(object):
                 self.opt = L.OPT_ADAM
             else:
                 sys.exit("Optimizer %s is not supported." % self.params.optimizer)
+        if (mode != "predict" and not eng.store.finalized and bool(self.params.dict.get("head_class_shard", False))):
+            # north_star "Data parallelism": optionally split the speaker matrix by columns over the ranks
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                from ..parallel import HeadShard
+                eng.head_shard = HeadShard(num_speakers)
+                if bool(self.params.dict.get("clip_gradient", False)):
+                    raise NotImplementedError("clip_gradient needs the global gradient norm: not available with "
+                                              "head_class_shard")
         if not eng.store.finalized:
             tdnn_mod.declare_variables(eng, dim, self.params)
             if mode != "predict":
@@ -191,7 +201,46 @@ class Trainer(object):
             eng.backward("trunk")
 
         def part_b():
+            if eng.head_shard is not None:       # regularisation loss of this rank's head columns, for the logged total
+                hs = eng.store.specs["softmax/output/kernel"]
+                nb = (hs.numel + 1023) // 1024 * 1024
+                eng.call(eng.lib.xv_l2_loss, L.ptr(eng.store.params[hs.offset:]), L.ptr(eng.store.blk_l2[hs.offset // 1024:]),
+                         C.c_int64(nb), L.ptr(eng.scalars[4:5]), L.stream_ptr())
             eng.optimizer_step(self.opt, clip=clip, with_l2_loss=True)
+
+        if self.dp is not None and eng.head_shard is not None:
+            # class-sharded head: the step contains collectives (row all-gather, partial exchange, dx reduce-scatter,
+            # trunk-gradient all-reduce); it is captured as consecutive CUDA graphs with the exchanges between them
+            def body():
+                part_a()
+                eng.collective(self.dp.allreduce_gradients)
+                part_b()
+
+            if st["graphs"] is not None:
+                st["graphs"].replay()
+                eng.launches += st["launches"]
+            else:
+                st["calls"] += 1
+                if self.use_cuda_graph and st["calls"] > 2:
+                    from ..parallel import SegmentedGraph
+                    seg = SegmentedGraph()
+                    l0 = eng.launches
+                    eng.capturing, eng.segmenter = True, seg
+                    try:
+                        seg.begin()
+                        body()
+                        seg.end()
+                    except Exception:
+                        seg.abort()
+                        raise
+                    finally:
+                        eng.capturing, eng.segmenter = False, None
+                    st["launches"] = eng.launches - l0
+                    st["graphs"] = seg
+                    seg.replay()
+                else:
+                    body()
+            return self._finish_step(global_step, fetch_loss)
 
         def run(ga, ga2, gb):
             """forward + head backward | all-reduce(head bucket) overlapping the frame-level backward | all-reduce(trunk
@@ -240,13 +289,20 @@ class Trainer(object):
                 run(ga, ga2, gb)
             else:
                 run(None, None, None)
+        return self._finish_step(global_step, fetch_loss)
+
+    def _finish_step(self, global_step, fetch_loss):
+        eng = self.engine
         self.global_step = int(global_step) + 1
         if fetch_loss:
-            vals = eng.scalars[:4].tolist()          # one D2H read
+            vals = eng.scalars[:5].tolist()          # one D2H read
             raw = vals[0]
+            l2 = vals[1]
             if self.dp is not None:
                 raw = self.dp.mean_scalar(raw)
-            self.train_ops = {"raw_loss": raw, "loss": raw + vals[1] + vals[3]}
+                if eng.head_shard is not None:       # add the regularisation loss of the other ranks' head columns
+                    l2 += self.dp.sum_scalar(vals[4]) - vals[4]
+            self.train_ops = {"raw_loss": raw, "loss": raw + l2 + vals[3]}
             return dict(self.train_ops)
         return None
 
@@ -356,6 +412,15 @@ class Trainer(object):
         os.makedirs(self.model, exist_ok=True)
         st = self.engine.store
         vals = st.export_tf()
+        sh = self.engine.head_shard
+        if sh is not None:          # every rank calls save(); the sharded variables are written in their full TF shape
+            for name, spec in st.specs.items():
+                if spec.col_range is not None:
+                    loc = torch.from_numpy(vals[name]).to(self.engine.device)
+                    full = sh.gather_columns(loc.reshape(-1, loc.shape[-1]))
+                    vals[name] = full.reshape(spec.full_shape).cpu().numpy()
+            if sh.rank != 0:
+                return
         path = os.path.join(self.model, "model-%d.npz" % step)
         extra = {}
         if st.state1 is not None:

@@ -64,6 +64,123 @@ class FlatAllReduce(object):
         return float(t.item())
 
 
+class HeadShard(object):
+    """Column partition of the speaker matrix [E, C] over the ranks, and the exchanges of a class-sharded head step.
+
+    Shard r owns classes [r*per, min((r+1)*per, C)) with per = ceil(C / N) rounded up to a multiple of 8 (aligned column
+    offsets for the 16-byte tensor-map rows).  Exchanges (NCCL over NVLink on GPUs, gloo in the CPU tests):
+      forward   all-gather of the embeddings [B, E] and labels [B]; all-gather of the per-row (max, sum, target) triples
+      backward  sum reduce-scatter of dLoss/dx [N*B, E] and of the target-column ||x|| gradients [N*B]."""
+
+    def __init__(self, num_outputs, rank=None, world=None, group=None):
+        self.group = group
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rank, self.world, self.num_outputs = int(rank), int(world), int(num_outputs)
+        per = -(-self.num_outputs // self.world)
+        self.per = (per + 7) // 8 * 8
+        if (self.world - 1) * self.per >= self.num_outputs:
+            raise ValueError("%d classes cannot be split over %d ranks in multiples of 8 columns"
+                             % (self.num_outputs, self.world))
+        self.lo, self.hi = self.range_of(self.rank)
+        self.n_local = self.hi - self.lo
+
+    def range_of(self, r):
+        lo = min(r * self.per, self.num_outputs)
+        return lo, min(lo + self.per, self.num_outputs)
+
+    def local_labels(self, labels):
+        """Host-side statement of xv_head_local_labels (tests)."""
+        l = labels - self.lo
+        return torch.where((l >= 0) & (l < self.n_local), l, torch.full_like(l, -1))
+
+    def all_gather(self, out, local):
+        if self.world == 1:
+            out.view(-1).copy_(local.reshape(-1))
+        else:
+            dist.all_gather_into_tensor(out.view(-1), local.reshape(-1), group=self.group)
+        return out
+
+    def reduce_scatter_sum(self, out, full):
+        """out [n] <- rows [rank*n, (rank+1)*n) of the sum over ranks of full [world*n]."""
+        n = out.numel()
+        if self.world == 1:
+            out.view(-1).copy_(full.reshape(-1))
+        elif dist.get_backend(self.group) == "gloo":       # gloo has no reduce-scatter: all-reduce a copy, keep our rows
+            tmp = full.reshape(-1).clone()
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
+            out.view(-1).copy_(tmp[self.rank * n:(self.rank + 1) * n])
+        else:
+            dist.reduce_scatter_tensor(out.view(-1), full.reshape(-1), op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def gather_columns(self, local, pad_value=0.0):
+        """[E, n_local] shards -> the full [E, C] matrix on every rank (checkpoint export)."""
+        E = local.shape[0]
+        buf = torch.full((E, self.per), pad_value, dtype=local.dtype, device=local.device)
+        buf[:, :self.n_local] = local[:, :self.n_local]
+        allb = torch.empty((self.world, E, self.per), dtype=local.dtype, device=local.device)
+        self.all_gather(allb, buf)
+        return torch.cat([allb[r, :, :(self.range_of(r)[1] - self.range_of(r)[0])] for r in range(self.world)], 1)
+
+
+class SegmentedGraph(object):
+    """A step that contains host-side collectives, captured as consecutive CUDA graphs with the collectives replayed
+    eagerly between them (all on the current stream, so stream order carries every dependency).  Engine.collective()
+    calls cut() while the step is being captured."""
+
+    def __init__(self):
+        self.items = []
+        self.pool = None
+        self.stream = torch.cuda.Stream()
+        self._g = None
+        self._ctx = None
+
+    def _open(self):
+        self._g = torch.cuda.CUDAGraph()
+        self._ctx = torch.cuda.graph(self._g, pool=self.pool, stream=self.stream)
+        self._ctx.__enter__()
+
+    def _close(self):
+        self._ctx.__exit__(None, None, None)
+        if self.pool is None:
+            self.pool = self._g.pool()
+        self.items.append(self._g)
+        self._g = self._ctx = None
+
+    def begin(self):
+        self._open()
+
+    def cut(self, fn):
+        self._close()
+        self.items.append(fn)       # not executed during capture: no kernel has run, and every rank skips it alike
+        self._open()
+
+    def end(self):
+        self._close()
+
+    def abort(self):
+        if self._ctx is not None:
+            try:
+                self._ctx.__exit__(None, None, None)
+            except Exception:
+                pass
+            self._g = self._ctx = None
+
+    def replay(self):
+        for it in self.items:
+            if isinstance(it, torch.cuda.CUDAGraph):
+                it.replay()
+            else:
+                it()
+
+    @property
+    def num_graphs(self):
+        return sum(isinstance(it, torch.cuda.CUDAGraph) for it in self.items)
+
+
 class DataParallel(object):
     """Attach to a Trainer: per-rank batches of size B, loss scaled by 1/(N*B), one all-reduce per step."""
 
@@ -74,7 +191,15 @@ class DataParallel(object):
         eng = trainer.engine
         eng.inv_global_batch = 1.0 / float(self.world * local_batch)
         st = eng.store
-        self.comm.broadcast_(st.params)
+        # class-sharded head: its kernel (declared last) differs per rank and its gradient is complete locally, so
+        # broadcast / all-reduce cover only the replicated prefix of the flat buffers
+        self.head_shard = eng.head_shard
+        self.dp_numel = st.n
+        if self.head_shard is not None:
+            self.dp_numel = min(s.offset for s in st.specs.values() if s.col_range is not None)
+            assert all(s.offset < self.dp_numel for s in st.specs.values() if s.trainable and s.col_range is None), \
+                "sharded variables must be declared last"
+        self.comm.broadcast_(st.params[:self.dp_numel])
         self.comm.broadcast_(st.buffers)
         st.refresh_shadows()
         trainer.dp = self
@@ -85,12 +210,12 @@ class DataParallel(object):
         self._pending = []
 
     def allreduce_gradients(self):
-        self.comm.allreduce_(self.trainer.engine.store.grads)
+        self.comm.allreduce_(self.trainer.engine.store.grads[:self.dp_numel])
 
     def allreduce_bucket_async(self, which):
         """Enqueue the sum all-reduce of one gradient bucket on NCCL's stream (ordered after the work already on the
         current stream) and return immediately, so later kernels of the current stream overlap it."""
-        g = self.trainer.engine.store.grads
+        g = self.trainer.engine.store.grads[:self.dp_numel]
         t = g[self.split:] if which == "head" else g[:self.split]
         if self.world > 1 and t.numel() > 0:
             self._pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.comm.group, async_op=True))
@@ -102,4 +227,9 @@ class DataParallel(object):
 
     def mean_scalar(self, local_mean_scaled):
         # each rank's loss scalar is sum_i CE_i / (N*B): the global mean is their sum
+        if self.head_shard is not None:
+            return float(local_mean_scaled)      # the sharded head already sums the rows of every rank
         return self.comm.mean_scalar(local_mean_scaled, device=self.trainer.engine.device)
+
+    def sum_scalar(self, value):
+        return self.comm.mean_scalar(value, device=self.trainer.engine.device)

@@ -35,8 +35,11 @@ def _pad_to(n, m):
 
 class VarSpec(object):
     def __init__(self, name, tf_shape, ishape, row_map=None, l2=0.0, shadow="none", init="zeros", trainable=True,
-                 fans=None, pad_value=0.0):
+                 fans=None, pad_value=0.0, full_shape=None, col_range=None):
         self.name, self.tf_shape, self.ishape = name, tuple(tf_shape), tuple(ishape)
+        # class-sharded head: this rank holds columns [col_range) of a variable whose unsharded TF shape is full_shape
+        self.full_shape = None if full_shape is None else tuple(full_shape)
+        self.col_range = col_range
         self.row_map, self.l2, self.shadow, self.init = row_map, float(l2), shadow, init
         self.trainable, self.fans, self.pad_value = trainable, fans, pad_value
         self.numel = int(np.prod(self.ishape))
@@ -173,6 +176,8 @@ class ParamStore(object):
             if isinstance(arr, torch.Tensor):
                 arr = arr.detach().cpu().double().numpy()
             s = self.specs[name]
+            if s.col_range is not None and tuple(np.shape(arr)) == s.full_shape and s.full_shape != s.tf_shape:
+                arr = np.asarray(arr)[..., s.col_range[0]:s.col_range[1]]      # unsharded checkpoint -> this rank's columns
             self.view(name).copy_(torch.from_numpy(s.to_internal(arr)).to(self.device))
         self.refresh_shadows()
 
@@ -189,7 +194,7 @@ class ParamStore(object):
         gen = torch.Generator().manual_seed(seed)
         vals = {}
         for name, s in self.specs.items():
-            shp = s.tf_shape
+            shp = s.full_shape if s.full_shape is not None else s.tf_shape   # shards draw the full tensor: same stream
             if s.init == "glorot":
                 fan_in, fan_out = s.fans
                 lim = math.sqrt(6.0 / (fan_in + fan_out))
@@ -204,7 +209,7 @@ class ParamStore(object):
             else:
                 v = torch.zeros(shp, dtype=torch.float64)
             vals[name] = v.numpy()
-        self.load_tf(vals)
+        self.load_tf(vals)          # column-sharded variables are sliced there
 
     def refresh_shadows(self):
         L.check(L.load().xv_shadow_refresh(L.ptr(self.params), L.ptr(self.blk_shadow), L.ptr(self.blk_stride),
@@ -316,6 +321,19 @@ class Engine(object):
         self.side_wgrad = False          # frame-level wgrad GEMMs on a second stream: measured 1.067 vs 1.056 ms (no gain)
         self._side = None
         self._side_used = False
+        self.head_shard = None           # parallel.HeadShard: the speaker matrix is split by columns over the ranks
+        self.segmenter = None            # SegmentedGraph while a step containing collectives is being captured
+
+    def collective(self, fn):
+        """Run a host-side exchange (torch.distributed call on named workspace buffers) between kernels.  While a step is
+        being captured the exchange cuts the CUDA graph: kernels before / after it land in consecutive graph segments
+        and the exchange itself is replayed eagerly between them (SegmentedGraph)."""
+        if self.capturing:
+            if self.segmenter is None:
+                raise L.XvError("a collective inside a captured step needs a SegmentedGraph")
+            self.segmenter.cut(fn)
+        else:
+            fn()
 
     # ---- memory
     @property
@@ -827,6 +845,100 @@ class Engine(object):
                 u.grad = du
             self.tape.append(bwd)
         return self.scalars[0], logits, x
+
+    def margin_head_sharded(self, u, labels, kernel, bias, head_type, num_outputs, training, margin=0.0, asoftmax_m=1,
+                            scaling=0.0):
+        """Class-sharded variant of margin_head (north_star "Data parallelism"; SURVEY 8e 2'): this rank holds columns
+        [lo, hi) of the speaker matrix.  Embeddings and labels of ALL ranks are all-gathered (R = N*B rows), every rank runs
+        the fused cosine-GEMM / margin / online-LSE epilogue on its own columns, the per-row (max, sum, target) triples are
+        exchanged once (the all-reduce(max) + all-reduce(sum) of a sharded softmax, evaluated on the gathered pairs), and the
+        backward reduce-scatters dLoss/dx; dLoss/dW of a shard is complete locally, so the 512 x C gradient never crosses
+        NVLink.  The loss scalar is the global-batch mean on every rank."""
+        sh = self.head_shard
+        st = self.store
+        Wm = st.view(kernel)                           # fp32 [E, cpad_local]
+        E, cpad = Wm.shape
+        Cn = sh.n_local
+        N, rk = sh.world, sh.rank
+        B = u.data.shape[0]
+        R = N * B
+        normalize = 0 if head_type == L.HEAD_SOFTMAX else 1
+        s = L.stream_ptr
+        wn3 = self.buf("head/wn3", (3 * E, cpad), torch.bfloat16)
+        inv_norm = self.buf("head/inv_norm", (cpad,), torch.float32)
+        self.call(self.lib.xv_head_prep_weights, L.ptr(Wm), L.ptr(wn3), L.ptr(inv_norm), E, cpad, C.c_int64(cpad),
+                  normalize, s())
+        labels = labels.to(device=self.device, dtype=torch.int32).contiguous()
+        u_loc, l_loc = u.data, labels                  # persistent buffers (named workspace / the step's static batch)
+        assert u_loc.is_contiguous() and tuple(u_loc.shape) == (B, E)
+        u_all = self.buf("head/u_all", (R, E), torch.float32)
+        l_all = self.buf("head/labels_all", (R,), torch.int32)
+
+        def gather_rows():
+            sh.all_gather(u_all, u_loc)
+            sh.all_gather(l_all, l_loc)
+        self.collective(gather_rows)
+        x = self.buf("head/x", (R, E), torch.float32)
+        x3 = self.buf("head/x3", (R, 3 * E), torch.bfloat16)
+        xnorm = self.buf("head/xnorm", (R,), torch.float32)
+        urinv = self.buf("head/urinv", (R,), torch.float32)
+        self.call(self.lib.xv_head_prep_features, L.ptr(u_all), C.c_float(scaling), L.ptr(x), L.ptr(x3), L.ptr(xnorm),
+                  L.ptr(urinv), R, E, s())
+        lab = self.buf("head/labels_shard", (R,), torch.int32)
+        self.call(self.lib.xv_head_local_labels, L.ptr(l_all), sh.lo, Cn, L.ptr(lab), R, s())
+        nblk = 2 * ((Cn + 255) // 256)
+        pmax = self.buf("head/pmax", (nblk, R), torch.float32)
+        psum = self.buf("head/psum", (nblk, R), torch.float32)
+        tgt = self.buf("head/target", (R,), torch.float32, zero=True)       # written by the owning shard only
+        lse = self.buf("head/lse", (R,), torch.float32)
+        gnorm = self.buf("head/gnorm", (R,), torch.float32, zero=True)
+        inv_batch = self.inv_global_batch if self.inv_global_batch is not None else 1.0 / R
+        h = L.HeadArgs()
+        h.type, h.asoftmax_m, h.margin = head_type, asoftmax_m, margin
+        h.cos_m, h.sin_m, h.threshold = math.cos(margin), math.sin(margin), math.cos(math.pi - margin)
+        h.sched = self.sched.data_ptr()
+        h.labels, h.xnorm = lab.data_ptr(), xnorm.data_ptr()
+        h.part_max, h.part_sum, h.target_logit = pmax.data_ptr(), psum.data_ptr(), tgt.data_ptr()
+        h.logits_out = 0
+        h.lse, h.inv_batch, h.gnorm = lse.data_ptr(), inv_batch, gnorm.data_ptr()
+        bias_t = None if bias is None else st.view(bias)
+        dummy = self.buf("head/dummy", (8,), torch.float32)
+        self.gemm(L.operand(x3, False), L.operand(wn3, True, cols=Cn), R, Cn, 3 * E, dummy, epilogue=L.EPI_HEAD_FWD,
+                  bias=bias_t, head=h, ldc=cpad)
+        part = self.buf("head/shard_part", (3, R), torch.float32)
+        parts = self.buf("head/shard_parts", (N, 3, R), torch.float32)
+        self.call(self.lib.xv_head_shard_partials, L.ptr(pmax), L.ptr(psum), L.ptr(tgt), nblk, R, L.ptr(part), s())
+        self.collective(lambda: sh.all_gather(parts, part))
+        self.call(self.lib.xv_head_combine_shards, L.ptr(parts), N, R, C.c_float(inv_batch), L.ptr(lse), L.ptr(None),
+                  L.ptr(self.scalars[0:1]), s())
+        if training:
+            def bwd():
+                d = self.buf("head/d", (R, cpad), torch.bfloat16)
+                self.gemm(L.operand(x3, False), L.operand(wn3, True, cols=Cn), R, Cn, 3 * E, d, epilogue=L.EPI_HEAD_BWD,
+                          bias=bias_t, head=h, col_sum=(st.grad(bias) if bias is not None else None))
+                gw = st.grad(kernel)                     # complete for this shard: all R rows are here
+                self.gemm(L.operand(x3, True, cols=E), L.operand(d, True, cols=Cn), E, Cn, R, gw, epilogue=L.EPI_F32)
+                if normalize:
+                    self.call(self.lib.xv_head_finish_dw, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), E, cpad, s())
+                dx_all = self.buf("head/dxg_all", (R, E), torch.float32, zero=True)      # partial: this shard's columns
+                sp = self.splits_for(R, E, Cn)
+                self.gemm(L.operand(d, False, cols=Cn), L.operand(wn3, False, rows=E, cols=Cn), R, E, Cn, dx_all,
+                          epilogue=L.EPI_F32, splits=sp)
+                dxg = self.buf("head/dxg", (B, E), torch.float32)
+                gn = self.buf("head/gnorm_local", (B,), torch.float32)
+
+                def scatter_dx():
+                    sh.reduce_scatter_sum(dxg, dx_all)
+                    sh.reduce_scatter_sum(gn, gnorm)
+                self.collective(scatter_dx)
+                du = self.buf(u.name + "/grad", (B, E), torch.float32)
+                use_margin = head_type != L.HEAD_SOFTMAX
+                r0, r1 = rk * B, (rk + 1) * B
+                self.call(self.lib.xv_head_finish_dx, L.ptr(dxg), L.ptr(gn if use_margin else None), L.ptr(x[r0:r1]),
+                          L.ptr(xnorm[r0:r1]), L.ptr(u_loc), L.ptr(urinv[r0:r1]), C.c_float(scaling), L.ptr(du), B, E, s())
+                u.grad = du
+            self.tape.append(bwd)
+        return self.scalars[0], None, x[rk * B:(rk + 1) * B]
 
     # ---- regulariser + optimizer ---------------------------------------------------------------------
     def l2_loss(self):

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""N-GPU NCCL check of the class-sharded head (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
+        tools/dist_check_sharded.py [--steps 5] [--loss additive_angular_margin_softmax]
+
+Trainer A: data parallel with the replicated head (one flat gradient all-reduce).  Trainer B: same seed, same per-rank
+batches, ``head_class_shard=True`` (row all-gather, (max, sum, target) exchange, dx reduce-scatter, trunk-only
+all-reduce; the step captured as consecutive CUDA graphs from the third call on).  Both compute the same global-batch
+step, so losses and parameter UPDATES must agree to rounding.  Prints one JSON line on rank 0 and exits non-zero on
+a mismatch."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import bench
+from tf_kaldi_speaker_b200 import parallel
+from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
+from tf_kaldi_speaker_b200.model.trainer import Trainer
+from tf_kaldi_speaker_b200.runtime import set_engine
+
+
+def run(shard, args, rank, world, x, y):
+    pd = dict(bench.PD)
+    pd["loss_func"] = args.loss
+    pd.update(asoftmax_m=4, asoftmax_lambda_min=10, asoftmax_lambda_base=1000, asoftmax_lambda_gamma=1e-5,
+              asoftmax_lambda_power=5, amsoftmax_m=0.2, amsoftmax_lambda_min=0, amsoftmax_lambda_base=1000,
+              amsoftmax_lambda_gamma=1e-5, amsoftmax_lambda_power=5)
+    if args.loss == "softmax":
+        pd["feature_norm"] = False
+    pd["head_class_shard"] = bool(shard)
+    tr = Trainer(ParamsPlain(**pd), "/tmp/xv_shardcheck_%d_%d" % (int(shard), rank))
+    tr.build("train", bench.D, args.loss, args.speakers)
+    dp = parallel.DataParallel(tr, args.batch)
+    set_engine(tr.engine)
+    st = tr.engine.store
+    p0 = {k: v.copy() for k, v in st.export_tf().items()}
+    losses = []
+    for i in range(args.steps):
+        r = tr.train_step(x, y, 0.01, 20000 + i, fetch_loss=True)
+        losses.append((r["raw_loss"], r["loss"]))
+    torch.cuda.synchronize()
+    p1 = st.export_tf()
+    if shard:
+        sh = tr.engine.head_shard
+        assert sh is not None and sh.world == world
+        for name, spec in st.specs.items():
+            if spec.col_range is not None:
+                for d in (p0, p1):
+                    loc = torch.from_numpy(d[name]).cuda()
+                    d[name] = sh.gather_columns(loc.reshape(-1, loc.shape[-1])).reshape(spec.full_shape).cpu().numpy()
+    info = {"graphs": (tr._static[tuple(x.shape)]["graphs"].num_graphs if shard else None)}
+    return losses, p0, p1, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--speakers", type=int, default=1003)
+    ap.add_argument("--loss", default="additive_angular_margin_softmax")
+    args = ap.parse_args()
+    rank, world = parallel.init_from_env("nccl")
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    g = torch.Generator().manual_seed(100 + rank)
+    m = torch.randn(args.batch, 1, bench.D, generator=g)
+    s = 0.5 + torch.rand(args.batch, 1, bench.D, generator=g)
+    x = (m + s * torch.randn(args.batch, 120, bench.D, generator=g)).cuda()
+    y = torch.randint(0, args.speakers, (args.batch,), generator=g, dtype=torch.int32).cuda()
+    la, a0, a1, _ = run(False, args, rank, world, x, y)
+    lb, b0, b1, info = run(True, args, rank, world, x, y)
+    ok = True
+    worst = {}
+    for k in a0:
+        if not np.array_equal(a0[k], b0[k]):
+            ok = False
+            worst[k] = "initial values differ"
+            continue
+        da, db = (a1[k] - a0[k]).astype(np.float64), (b1[k] - b0[k]).astype(np.float64)
+        na = np.linalg.norm(da)
+        if na == 0:
+            continue
+        e = float(np.linalg.norm(da - db) / na)
+        if e > 3e-2:
+            ok = False
+        if e > 1e-3:
+            worst[k] = e
+    lerr = max(abs(p[0] - q[0]) / max(abs(p[0]), 1e-6) for p, q in zip(la, lb))
+    terr = max(abs(p[1] - q[1]) / max(abs(p[1]), 1e-6) for p, q in zip(la, lb))
+    ok = ok and lerr < 2e-3 and terr < 2e-3
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({"check": "class-sharded head == replicated head (NCCL, %d ranks)" % world, "ok": bool(flag.item() > 0),
+                          "loss": args.loss, "steps": args.steps, "raw_loss_replicated": [p[0] for p in la],
+                          "raw_loss_sharded": [p[0] for p in lb], "max_rel_raw_loss": lerr, "max_rel_total_loss": terr,
+                          "update_rel_fro_above_1e-3": worst, "graph_segments": info["graphs"]}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() > 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
