@@ -193,8 +193,8 @@ class DataParallel(object):
         st = eng.store
         # class-sharded head: its kernel (declared last) differs per rank and its gradient is complete locally, so
         # broadcast / all-reduce cover only the replicated prefix of the flat buffers
-        self.head_shard = eng.head_shard
-        self.dp_numel = st.n
+        self.head_shard = getattr(eng, "head_shard", None)
+        self.dp_numel = st.params.numel()
         if self.head_shard is not None:
             self.dp_numel = min(s.offset for s in st.specs.values() if s.col_range is not None)
             assert all(s.offset < self.dp_numel for s in st.specs.values() if s.trainable and s.col_range is None), \
