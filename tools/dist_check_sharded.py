@@ -7,8 +7,11 @@
 Trainer A: data parallel with the replicated head (one flat gradient all-reduce).  Trainer B: same seed, same per-rank
 batches, ``head_class_shard=True`` (row all-gather, (max, sum, target) exchange, dx reduce-scatter, trunk-only
 all-reduce; the step captured as consecutive CUDA graphs from the third call on).  Both compute the same global-batch
-step, so losses and parameter UPDATES must agree to rounding.  Prints one JSON line on rank 0 and exits non-zero on
-a mismatch."""
+step, so the loss and the parameter UPDATE of ONE step from identical parameters must agree to rounding (multi-step
+trajectories diverge chaotically in any bf16 pipeline: a 1e-7 difference flips ReLU masks a step later, and the
+split-K / atomic reductions are not order-deterministic -- the eager-vs-replay difference of the SAME trainer is
+reported as that noise floor).  Checked twice per trainer: the first (eager) call, and a CUDA-graph replay after the
+parameters have been reset.  Prints one JSON line on rank 0 and exits non-zero on a mismatch."""
 import argparse
 import json
 import os
@@ -41,23 +44,35 @@ def run(shard, args, rank, world, x, y):
     dp = parallel.DataParallel(tr, args.batch)
     set_engine(tr.engine)
     st = tr.engine.store
-    p0 = {k: v.copy() for k, v in st.export_tf().items()}
-    losses = []
-    for i in range(args.steps):
-        r = tr.train_step(x, y, 0.01, 20000 + i, fetch_loss=True)
-        losses.append((r["raw_loss"], r["loss"]))
-    torch.cuda.synchronize()
-    p1 = st.export_tf()
-    if shard:
-        sh = tr.engine.head_shard
-        assert sh is not None and sh.world == world
-        for name, spec in st.specs.items():
-            if spec.col_range is not None:
-                for d in (p0, p1):
+
+    def export():
+        torch.cuda.synchronize()
+        d = {k: v.copy() for k, v in st.export_tf().items()}
+        if shard:
+            sh = tr.engine.head_shard
+            assert sh is not None and sh.world == world
+            for name, spec in st.specs.items():
+                if spec.col_range is not None:
                     loc = torch.from_numpy(d[name]).cuda()
                     d[name] = sh.gather_columns(loc.reshape(-1, loc.shape[-1])).reshape(spec.full_shape).cpu().numpy()
-    info = {"graphs": (tr._static[tuple(x.shape)]["graphs"].num_graphs if shard else None)}
-    return losses, p0, p1, info
+        return d
+
+    local0 = {k: v.copy() for k, v in st.export_tf().items()}      # this rank's own (possibly sharded) values
+    p0 = export()
+    losses = []
+    r = tr.train_step(x, y, 0.01, 20000, fetch_loss=True)           # call 1: eager
+    losses.append((r["raw_loss"], r["loss"]))
+    p_eager = export()
+    for i in range(max(args.steps - 2, 2)):                         # calls 2..: the third one captures the graphs
+        tr.train_step(x, y, 0.01, 20000, fetch_loss=False)
+    st.load_tf(local0)
+    r = tr.train_step(x, y, 0.01, 20000, fetch_loss=True)           # pure replay from the initial parameters
+    losses.append((r["raw_loss"], r["loss"]))
+    p_graph = export()
+    g = tr._static[tuple(x.shape)]["graphs"]
+    assert g is not None, "the step was not captured"
+    info = {"graphs": (g.num_graphs if shard else None)}
+    return losses, p0, (p_eager, p_graph), info
 
 
 def main():
@@ -78,20 +93,31 @@ def main():
     lb, b0, b1, info = run(True, args, rank, world, x, y)
     ok = True
     worst = {}
+    noise = 0.0
+
+    def upd_err(pa, pb, k):
+        da, db = (pa[k] - a0[k]).astype(np.float64), (pb[k] - b0[k]).astype(np.float64)
+        na = np.linalg.norm(da)
+        return 0.0 if na == 0 else float(np.linalg.norm(da - db) / na)
+
+    ratio = 0.0
     for k in a0:
         if not np.array_equal(a0[k], b0[k]):
             ok = False
             worst[k] = "initial values differ"
             continue
-        da, db = (a1[k] - a0[k]).astype(np.float64), (b1[k] - b0[k]).astype(np.float64)
-        na = np.linalg.norm(da)
-        if na == 0:
-            continue
-        e = float(np.linalg.norm(da - db) / na)
-        if e > 3e-2:
-            ok = False
-        if e > 1e-3:
-            worst[k] = e
+        # noise floor of this parameter: the SAME (replicated) trainer, eager call vs graph replay from the same parameters
+        nk = upd_err(a1[0], a1[1], k)
+        if nk > 0.5:
+            continue            # zero true gradient (a bias in front of a batch-norm): the update is rounding noise only
+        noise = max(noise, nk)
+        for which in (0, 1):
+            e = upd_err(a1[which], b1[which], k)
+            tol = max(3.0 * nk, 5e-3)
+            ratio = max(ratio, e / tol)
+            if e > tol:
+                ok = False
+                worst["%s[%s]" % (k, "eager" if which == 0 else "graph")] = (e, nk)
     lerr = max(abs(p[0] - q[0]) / max(abs(p[0]), 1e-6) for p, q in zip(la, lb))
     terr = max(abs(p[1] - q[1]) / max(abs(p[1]), 1e-6) for p, q in zip(la, lb))
     ok = ok and lerr < 2e-3 and terr < 2e-3
@@ -101,7 +127,10 @@ def main():
         print(json.dumps({"check": "class-sharded head == replicated head (NCCL, %d ranks)" % world, "ok": bool(flag.item() > 0),
                           "loss": args.loss, "steps": args.steps, "raw_loss_replicated": [p[0] for p in la],
                           "raw_loss_sharded": [p[0] for p in lb], "max_rel_raw_loss": lerr, "max_rel_total_loss": terr,
-                          "update_rel_fro_above_1e-3": worst, "graph_segments": info["graphs"]}), flush=True)
+                          "criterion": "per parameter: one-step update rel-Frobenius error sharded vs replicated <= max(3 x the "
+                                       "replicated trainer's own eager-vs-replay error, 5e-3)",
+                          "violations": worst, "max_error_over_tolerance": ratio,
+                          "max_noise_floor_same_trainer_eager_vs_replay": noise, "graph_segments": info["graphs"]}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() > 0 else 1)
