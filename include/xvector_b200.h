@@ -286,6 +286,17 @@ XV_API int xv_head_combine_shards(const float* parts, int S, int R, float inv_ba
                                   float* loss, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Host feeder: dequantise + transpose Kaldi compressed-matrix ('CM ', format 1) segment crops on the device.
+ * Replaces the NumPy maps of dataset/kaldi_io.py:780-797 (uint16 percentile -> float, three-piece uint8 -> float) and
+ * the column-major -> row-major transpose of :811/:868 that the reference's loader processes run per segment
+ * (dataset/data_loader.py:229-307).  Bit-exact with that reader.
+ *   data u8 [B, D, ld_t] (column d of segment b: T frames), headers u16 [B, D, 4], glob f32 [B, 2] = (min, range),
+ *   out f32 [B, T, ldo].
+ * ------------------------------------------------------------------------------------------ */
+XV_API int xv_cm_decode(const void* data, const void* headers, const float* glob, float* out, int B, int T, int D,
+                        int64_t ld_t, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimizer over one flat f32 parameter buffer whose tensors start at multiples of 1024 elements
  * (tf.train.GradientDescent/Momentum/AdamOptimizer + l2_regularizer + clip_by_global_norm,
  * model/trainer.py:328-347, 357-358, 403-436).  opt: 0 sgd, 1 momentum, 2 nesterov, 3 adam.

@@ -164,11 +164,16 @@ class Trainer(object):
             st = {"x": torch.empty(key, dtype=torch.float32, device=dev),
                   "y": torch.empty((key[0],), dtype=torch.int32, device=dev), "calls": 0, "graphs": None, "launches": 0}
             self._static[key] = st
-        if not torch.is_tensor(features):
-            features = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
         if not torch.is_tensor(labels):
             labels = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
-        st["x"].copy_(features, non_blocking=True)           # H2D (or D2D) of this step's batch
+        if hasattr(features, "decode_into"):
+            # dataset.feeder.CompressedSegmentBatch: H2D of the raw uint8 crops + on-device dequantise / transpose
+            features.decode_into(st["x"])
+            self.engine.launches += 1
+        else:
+            if not torch.is_tensor(features):
+                features = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+            st["x"].copy_(features, non_blocking=True)       # H2D (or D2D) of this step's batch
         st["y"].copy_(labels.to(torch.int32), non_blocking=True)
         return st
 
