@@ -65,7 +65,7 @@ def test_train_step_accepts_compressed_batch(golden_dir):
     from tf_kaldi_speaker_b200.dataset.feeder import CompressedSegmentBatch
     from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
     from tf_kaldi_speaker_b200.model.trainer import Trainer
-    from xv_testlib import base_params
+    from tests.xv_testlib import base_params
     gd, ark, offs = _golden(golden_dir)
     B, T, D, C = 8, 60, 30, 50
     batch = CompressedSegmentBatch(B, T, D)
