@@ -165,6 +165,8 @@ def run_ours(args):
     from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
     from tf_kaldi_speaker_b200.model.trainer import Trainer
 
+    if args.dp_overlap:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(args.overlap_sms))     # NCCL stays inside the SMs the GEMMs leave free
     rank, world = parallel.init_from_env("nccl")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -173,6 +175,8 @@ def run_ours(args):
     pd = dict(PD)
     shard = bool(args.head_shard) and world > 1
     pd["head_class_shard"] = shard
+    pd["dp_overlap"] = bool(args.dp_overlap) and world > 1 and not shard
+    pd["dp_overlap_reserve_sms"] = int(args.overlap_sms)
     tr = Trainer(ParamsPlain(**pd), "/tmp/xv_bench_model_%d" % rank)
     tr.build("train", D, LOSS, C)
     if world > 1:
@@ -341,7 +345,9 @@ def run_ours(args):
                            "speakers": C, "parallelism": ("dp%d (batch-sharded replicas, per-replica BN, class-sharded head: "
                                             "row all-gather + (max,sum) exchange + dx reduce-scatter, trunk-only NCCL "
                                             "all-reduce)" % world) if shard else
-                                           ("dp%d (batch-sharded replicas, per-replica BN, one flat NCCL all-reduce)" % world),
+                                           ("dp%d (batch-sharded replicas, per-replica BN, %s)"
+                                            % (world, "two-bucket NCCL all-reduce, head bucket overlapped with the frame-level "
+                                                      "backward" if pd["dp_overlap"] else "one flat NCCL all-reduce")),
                            "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2 (no flush needed)"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": seg_s_e2e, "unit": "segments/s",
@@ -384,6 +390,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head-shard", action="store_true", help="N>1: split the speaker matrix by columns over the ranks")
+    ap.add_argument("--dp-overlap", action="store_true",
+                    help="N>1: all-reduce the [tdnn6 .. head] gradient bucket while the frame-level backward runs")
+    ap.add_argument("--overlap-sms", type=int, default=16, help="SMs left to NCCL during the overlap (GEMM grid cap)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

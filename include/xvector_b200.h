@@ -134,6 +134,9 @@ typedef struct {
 } xv_gemm_args;
 
 XV_API int xv_gemm_bf16(const xv_gemm_args* args, void* stream);
+/* Cap the persistent GEMM grid at max_ctas CTAs (0 = all SMs) for subsequently enqueued launches: the data-parallel
+ * step reserves SMs for the NCCL kernels of an overlapped gradient all-reduce (process-wide setting, host side only). */
+XV_API int xv_gemm_set_cta_limit(int max_ctas);
 
 /* ------------------------------------------------------------------------------------------
  * Frame-level elementwise / reduction kernels (bf16 activations [rows, ld], channels-last).

@@ -396,3 +396,20 @@ def test_optimizer_kernels(opt, clip):
     hi = wb.to(torch.bfloat16)
     assert torch.equal(sv[:512], hi) and torch.equal(sv[1024:], hi)
     assert torch.equal(sv[512:1024], (wb - hi.float()).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,T,D", [(128, 200, 30), (3, 37, 23), (2, 5, 32), (1, 9, 1)])
+def test_pack_input_bit_exact(B, T, D):
+    """tdnn1's im2col operand (model/tdnn.py:35-44 input side): out[b*T+t, j*32+c] = bf16(x[b, t+j, c]), zero elsewhere."""
+    from tf_kaldi_speaker_b200.runtime import Engine
+    eng = Engine()
+    g = torch.Generator().manual_seed(B + T + D)
+    x = torch.randn(B, T, D, generator=g).cuda()
+    fa = eng.pack_input(x)
+    torch.cuda.synchronize()
+    k, dpad = 5, 32
+    want = torch.zeros(B, T, 192, dtype=torch.bfloat16, device="cuda")
+    for j in range(k):
+        if T - j > 0:
+            want[:, :T - j, j * dpad:j * dpad + D] = x[:, j:, :].to(torch.bfloat16)
+    assert torch.equal(fa.data.view(B, T, 192), want)

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxvector_b200.so")
+# XV_LIB_PATH: load a differently-built library (compile-time tuning sweeps, tools/layers_bench.py); default = in-tree build
+LIB_PATH = os.environ.get("XV_LIB_PATH") or os.path.join(_HERE, "libxvector_b200.so")
 
 XV_OK, XV_ERR_INVALID, XV_ERR_UNSUPPORTED, XV_ERR_CUDA = 0, -1, -2, -3
 EPI_BF16, EPI_F32, EPI_HEAD_FWD, EPI_HEAD_BWD = 0, 1, 2, 3

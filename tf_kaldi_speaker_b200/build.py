@@ -11,8 +11,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(ROOT, "build", "xvector_b200")
-LIB = os.path.join(HERE, "libxvector_b200.so")
+# XV_LIB_VARIANT=name: build libxvector_b200.<name>.so in its own object directory (tuning sweeps with XV_EXTRA_CFLAGS)
+_VARIANT = os.environ.get("XV_LIB_VARIANT", "")
+BUILD = os.path.join(ROOT, "build", "xvector_b200" + ("." + _VARIANT if _VARIANT else ""))
+LIB = os.path.join(HERE, "libxvector_b200%s.so" % ("." + _VARIANT if _VARIANT else ""))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -55,6 +55,17 @@ static int make_out_tmap(CUtensorMap* map, void* out, int M, int N, long long ld
 
 }  // namespace xv
 
+// Persistent GEMM grids normally take every SM (one 227 KB CTA each).  While a collective runs concurrently (the
+// overlapped gradient all-reduce of the data-parallel step) its CTAs hold some SMs; a GEMM CTA that cannot be placed
+// starts late and, because tiles are strided statically over the grid, delays the whole GEMM.  The host therefore caps
+// the grid at (SMs - reserve) for the kernels it enqueues during the overlap.  0 = no cap.
+static int g_cta_limit = 0;
+extern "C" int xv_gemm_set_cta_limit(int max_ctas) {
+  if (max_ctas < 0) return ::xv::set_error(XV_ERR_INVALID, "xv_gemm_set_cta_limit: max_ctas must be >= 0");
+  g_cta_limit = max_ctas;
+  return XV_OK;
+}
+
 extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   using namespace xv;
   if (!a) return set_error(XV_ERR_INVALID, "null args");
@@ -136,6 +147,7 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   if (kp.bnb.y != nullptr && !kp.use_tma_out)
     return set_error(XV_ERR_INVALID, "bn_bwd fusion needs a TMA-storable output (16-byte aligned, no accumulate)");
   const long long tiles = static_cast<long long>(kp.num_m) * kp.num_n * kp.splits;
+  if (g_cta_limit > 0 && g_cta_limit < sms) sms = g_cta_limit < 2 ? 2 : g_cta_limit;   // leave SMs to a concurrent collective
   const int units = sms / cg;                                   // CTAs (cg = 1) or CTA pairs (cg = 2) on the device
   const int grid = static_cast<int>(tiles < units ? tiles : units) * cg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

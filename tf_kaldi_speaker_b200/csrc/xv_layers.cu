@@ -69,29 +69,27 @@ struct PoolGradSrc {
 };
 // ------------------------------------------------------------------------------------------------
 // Input packing: features f32 [B, T, D] -> bf16 im2col rows [B*T, ldo], out[m, j*dpad + c] = x[b, t+j, c].
-// One thread per (row m, tap slot j): it converts one feature frame (D floats) into one dpad-wide bf16 slot with
-// 16-byte stores; slots j >= k and channels c >= D are zero padding.  (The first version did four integer divisions
-// and a 2-byte store per ELEMENT: 23 us for 13 MB.)
+// One thread per (row m, 8-channel group): eight feature loads (L1/L2 hits: the 3 MB input is read k times) and one
+// 16-byte store, so a warp writes 512 contiguous bytes; slots j >= k and channels c >= D are zero padding.
+// (v1: four integer divisions and a 2-byte store per ELEMENT, 23 us for 13 MB; v2: one thread per 64-byte tap slot with
+// 30 strided scalar loads each, 13.5 us.)
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B,
                                                          int T, int D, int k, int dpad, long long ldo) {
   pdl_entry();
-  const int slots = static_cast<int>((ldo + dpad - 1) / dpad);     // the last slot may be narrower than dpad
-  const long long total = static_cast<long long>(B) * T * slots;
+  const int groups = static_cast<int>(ldo >> 3);
+  const long long total = static_cast<long long>(B) * T * groups;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / slots;
-    const int j = static_cast<int>(i - m * slots);
+    const long long m = i / groups;
+    const int col = static_cast<int>(i - m * groups) << 3;
+    const int j = col / dpad, c0 = col - j * dpad;
     const int t = static_cast<int>(m % T);
     const bool live = j < k && t + j < T;
-    const float* src = x + (m + j) * D;          // frame (b, t + j): rows of one segment are contiguous
-    __nv_bfloat16* dst = out + m * ldo + static_cast<long long>(j) * dpad;
-    const int width = min(dpad, static_cast<int>(ldo - static_cast<long long>(j) * dpad));
-    for (int c0 = 0; c0 < width; c0 += 8) {
-      float f[8];
+    const float* src = x + (m + j) * D + c0;     // frame (b, t + j): rows of one segment are contiguous
+    float f[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) f[q] = (live && c0 + q < D) ? __ldg(src + c0 + q) : 0.f;
-      store8(dst + c0, f);
-    }
+    for (int q = 0; q < 8; ++q) f[q] = (live && c0 + q < D) ? __ldg(src + q) : 0.f;
+    store8(out + m * ldo + col, f);
   }
 }
 
@@ -596,6 +594,12 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
 #ifndef XV_POOL_ROWS
 #define XV_POOL_ROWS 1
 #endif
+// frames in flight per warp of the training variant (backward sums): 4 -> 36.4 us, 1 -> 47.8 us, 2 -> 51.6 us isolated at
+// config 2 (the kernel is issue-bound: deeper unrolling amortises the loop / predicate overhead); the plain variant is the
+// other way round (27.0 us at 1, 50.5 us at 4)
+#ifndef XV_POOL_ROWS_BWD
+#define XV_POOL_ROWS_BWD 4
+#endif
 #ifndef XV_POOL_CPT
 #define XV_POOL_CPT 4
 #endif
@@ -656,7 +660,7 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
 #pragma unroll
       for (int j = 0; j < CPT; ++j) x0[j] = actf<ACT>(fmaf(x0[j], sc[j], sh[j]), al[j]);
     }
-    constexpr int PR = XV_POOL_ROWS;       // frames in flight per warp
+    constexpr int PR = BWD_SUMS ? XV_POOL_ROWS_BWD : XV_POOL_ROWS;       // frames in flight per warp
     const long long step = 8 * ld;
     const __nv_bfloat16* xp = xb + static_cast<long long>(w) * ld + c0;
     for (int t = w; t < L; t += 8 * PR, xp += PR * step) {
@@ -680,11 +684,15 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
           if (BWD_SUMS) {       // yhat = (y - mean) * rstd: the rstd factor is applied once, at the end
             const float gp = actg<ACT>(z, al[j]);
             const float ym = v[u][j] - mu[j];
-            const float ga = gp * a;
             q1[j] += gp;
-            q2[j] += ga;
             q3[j] = fmaf(gp, ym, q3[j]);
-            q4[j] = fmaf(ga, ym, q4[j]);
+            if (ACT == ACT_RELU) {       // g' a = a for relu: S2 = sum_t a comes from the pooling sum itself (below)
+              q4[j] = fmaf(a, ym, q4[j]);
+            } else {
+              const float ga = gp * a;
+              q2[j] += ga;
+              q4[j] = fmaf(ga, ym, q4[j]);
+            }
           }
         }
       }
@@ -695,6 +703,7 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
   __syncthreads();
   const int c = blockIdx.x * BC + threadIdx.x;
   const bool c_own = threadIdx.x < BC && c < cpad;
+  float sum_a = 0.f;        // sum over the valid frames of the pooled activation (= S2 of the backward sums for relu)
   if (c_own) {
     float a = 0.f, q = 0.f;
 #pragma unroll
@@ -703,6 +712,7 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
     if (c < c_real && L > 0) {
       float first = __bfloat162float(xb[c]);
       if (scale) first = actf<ACT>(fmaf(first, scale[c], shift[c]), ACT == ACT_PRELU ? alpha[c] : 0.f);
+      sum_a = fmaf(static_cast<float>(L), first, a);
       const float invl = 1.0f / (static_cast<float>(L) + 1e-16f);
       const float md = a * invl;
       mean = first + md;
@@ -737,6 +747,7 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
         float a = 0.f, q = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a += red[k][0][threadIdx.x]; q += red[k][1][threadIdx.x]; }
+        if (ACT == ACT_RELU && round == 0) q = sum_a;
         const float f = round ? save_rstd[c] : 1.0f;
         sb[(2 * round) * cpad + c] = (c < c_real) ? a * f : 0.f;
         sb[(2 * round + 1) * cpad + c] = (c < c_real) ? q * f : 0.f;
@@ -832,6 +843,237 @@ static inline int grid_for(long long work_items, int block, int sms) {
   return static_cast<int>(g);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// "Flat" one-wave variants of the BN apply / BN backward-apply kernels.  The chunked kernels above launch
+// (channel groups x segments x row chunks) blocks -- 1024 blocks of bn_act_apply at C = 512 against ~740 resident
+// (5 per SM): 1.38 waves, the second one 38 % full -- and every block re-loads its per-channel constants for 6-8 rows
+// per thread.  Here the grid is exactly the resident capacity (occupancy query x SM count): block j owns the
+// contiguous row range [j * rows_per_block, ...) of the flat-time matrix for one 256-channel group, every block has the
+// same number of rows (+-8), constants are loaded once, and the (segment, frame) position of a row is walked
+// incrementally (one integer division per warp).
+struct FlatWalk {
+  int b, t, L;
+};
+__device__ __forceinline__ FlatWalk flat_start(int m, int seg_len, int seg_valid, const int* lengths, int rows) {
+  FlatWalk f;
+  if (seg_len <= 0) { f.b = 0; f.t = m; f.L = rows; return f; }
+  f.b = m / seg_len;
+  f.t = m - f.b * seg_len;
+  f.L = lengths ? lengths[f.b] : seg_valid;
+  return f;
+}
+__device__ __forceinline__ void flat_advance(FlatWalk& f, int step, int seg_len, int seg_valid, const int* lengths) {
+  f.t += step;
+  if (seg_len > 0) {
+    while (f.t >= seg_len) {
+      f.t -= seg_len;
+      ++f.b;
+      f.L = lengths ? lengths[f.b] : seg_valid;      // rows beyond the matrix are never touched (m < m1 checked first)
+    }
+  }
+}
+
+template <int ACT, int NR>
+__global__ void __launch_bounds__(256) bn_act_apply_flat_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ alpha, int rows, int rows_per_block, int col_groups, int C,
+                                    long long ld, int seg_len, int seg_valid, const int* __restrict__ lengths, BnTrainSrc bt) {
+  pdl_entry();
+  __shared__ float s_sc[WCH], s_sh[WCH];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cgroup = blockIdx.x % col_groups, rb = blockIdx.x / col_groups;
+  const int c0 = cgroup * WCH + lane * WV;
+  if (bt.col_sum != nullptr) {      // training-mode finalisation folded in (see bn_act_apply_kernel)
+    const int c = cgroup * WCH + threadIdx.x;
+    if (c < C) {
+      const float mean_nb = bt.col_sum[c] / bt.count;
+      const float var = fmaxf(bt.col_sumsq[c] / bt.count - mean_nb * mean_nb, 0.f);
+      const float mean = mean_nb + (bt.bias ? bt.bias[c] : 0.f);
+      const float rstd = rsqrtf(var + bt.eps);
+      const float scv = bt.gamma[c] * rstd;
+      const float shv = bt.beta[c] - mean * scv;
+      s_sc[threadIdx.x] = scv;
+      s_sh[threadIdx.x] = shv;
+      if (rb == 0) {
+        bt.scale_out[c] = scv;
+        bt.shift_out[c] = shv;
+        bt.save_mean[c] = mean;
+        bt.save_rstd[c] = rstd;
+        if (bt.moving_mean) {
+          const float mv = bt.unbiased ? var * (bt.count / fmaxf(bt.count - 1.f, 1.f)) : var;
+          bt.moving_mean[c] = bt.moving_mean[c] * bt.momentum + mean * (1.f - bt.momentum);
+          bt.moving_var[c] = bt.moving_var[c] * bt.momentum + mv * (1.f - bt.momentum);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (c0 >= C) return;
+  float sc[WV], sh[WV], al[WV];
+  if (bt.col_sum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < WV; ++j) { sc[j] = s_sc[lane * WV + j]; sh[j] = s_sh[lane * WV + j]; }
+  } else {
+    load8f(scale + c0, sc);
+    load8f(shift + c0, sh);
+  }
+#pragma unroll
+  for (int j = 0; j < WV; ++j) al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+  const int m0 = rb * rows_per_block, m1 = min(m0 + rows_per_block, rows);
+  FlatWalk fw[NR];
+#pragma unroll
+  for (int u = 0; u < NR; ++u) fw[u] = flat_start(min(m0 + w + 8 * u, rows - 1), seg_len, seg_valid, lengths, rows);
+  const long long step = 8 * ld;
+  const __nv_bfloat16* yp = y + static_cast<long long>(m0 + w) * ld + c0;
+  __nv_bfloat16* ap = a + static_cast<long long>(m0 + w) * ld + c0;
+  for (int m = m0 + w; m < m1; m += 8 * NR, yp += NR * step, ap += NR * step) {
+    float v[NR][WV];
+    bool in[NR], valid[NR];
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      in[u] = m + 8 * u < m1;
+      valid[u] = in[u] && fw[u].t < fw[u].L;
+      if (valid[u]) load8(yp + u * step, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      if (in[u]) {
+        float o[WV];
+#pragma unroll
+        for (int j = 0; j < WV; ++j) o[j] = valid[u] ? actf<ACT>(fmaf(v[u][j], sc[j], sh[j]), al[j]) : 0.f;
+        store8(ap + u * step, o);
+      }
+      if (m + 8 * (u + NR) < m1) flat_advance(fw[u], 8 * NR, seg_len, seg_valid, lengths);
+    }
+  }
+}
+
+template <bool FUSED_POOL, int ACT, int NR>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_flat_kernel(
+    const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dy,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ save_mean,
+    const float* __restrict__ save_rstd, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+    float inv_count, const float* __restrict__ alpha, int rows, int rows_per_block, int col_groups, int C, long long ld,
+    int seg_len, int seg_valid, const int* __restrict__ lengths, PoolGradSrc ps) {
+  pdl_entry();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cgroup = blockIdx.x % col_groups, rb = blockIdx.x / col_groups;
+  const int c0 = cgroup * WCH + lane * WV;
+  if (c0 >= C) return;
+  float sc[WV], sh[WV], ka[WV], kb[WV], al[WV];
+  load8f(scale + c0, sc); load8f(shift + c0, sh);
+  {
+    float mu[WV], rs[WV], dg[WV], db[WV];
+    load8f(save_mean + c0, mu); load8f(save_rstd + c0, rs); load8f(dgamma + c0, dg); load8f(dbeta + c0, db);
+#pragma unroll
+    for (int j = 0; j < WV; ++j) {
+      ka[j] = -sc[j] * rs[j] * dg[j] * inv_count;
+      kb[j] = -sc[j] * db[j] * inv_count - ka[j] * mu[j];
+      al[j] = (ACT == ACT_PRELU) ? alpha[c0 + j] : 0.f;
+    }
+  }
+  const int m0 = rb * rows_per_block, m1 = min(m0 + rows_per_block, rows);
+  FlatWalk fw[NR];
+#pragma unroll
+  for (int u = 0; u < NR; ++u) fw[u] = flat_start(min(m0 + w + 8 * u, rows - 1), seg_len, seg_valid, lengths, rows);
+  PoolCoef8 pc;
+  int pc_b = -1;
+  const long long step = 8 * ld;
+  const long long off = static_cast<long long>(m0 + w) * ld + c0;
+  const __nv_bfloat16* yp = y + off;
+  const __nv_bfloat16* dp = FUSED_POOL ? nullptr : da + off;
+  __nv_bfloat16* op = dy + off;
+  for (int m = m0 + w; m < m1; m += 8 * NR, yp += NR * step, op += NR * step) {
+    float v[NR][WV], d[NR][WV];
+    bool in[NR], valid[NR];
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      in[u] = m + 8 * u < m1;
+      valid[u] = in[u] && fw[u].t < fw[u].L;
+      if (valid[u]) {
+        load8(yp + u * step, v[u]);
+        if (!FUSED_POOL) load8(dp + u * step, d[u]);
+      }
+    }
+    if (!FUSED_POOL) dp += NR * step;
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      if (in[u]) {
+        float o[WV];
+        if (valid[u]) {
+          if (FUSED_POOL && fw[u].b != pc_b) {       // warp-uniform: a warp's rows cross a segment boundary rarely
+            pc_b = fw[u].b;
+            pool_coef_load8(pc, ps, pc_b, c0, fw[u].L);
+          }
+#pragma unroll
+          for (int j = 0; j < WV; ++j) {
+            const float z = fmaf(v[u][j], sc[j], sh[j]);
+            const float dd = FUSED_POOL ? fmaf(pc.cb[j], actf<ACT>(z, al[j]), pc.ca[j]) : d[u][j];
+            const float g = dd * actg<ACT>(z, al[j]);
+            o[j] = fmaf(sc[j], g, fmaf(ka[j], v[u][j], kb[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < WV; ++j) o[j] = 0.f;
+        }
+        store8(op + u * step, o);
+      }
+      if (m + 8 * (u + NR) < m1) flat_advance(fw[u], 8 * NR, seg_len, seg_valid, lengths);
+    }
+  }
+}
+
+// Launch geometry of the flat kernels: grid = resident capacity (a multiple of the channel groups), equal row ranges.
+#ifndef XV_FLAT_APPLY_DEFAULT
+#define XV_FLAT_APPLY_DEFAULT 1
+#endif
+#ifndef XV_FLAT_BWD_DEFAULT
+#define XV_FLAT_BWD_DEFAULT 1
+#endif
+#ifndef XV_FLAT_FUSED_DEFAULT
+#define XV_FLAT_FUSED_DEFAULT 0       // 59.8 us flat (1 row) vs 49.6 us chunked with 4 rows in flight: coefficient reloads dominate
+#endif
+struct FlatGrid {
+  int grid, rows_per_block, col_groups;
+};
+template <typename K>
+static int flat_grid(K kernel, int* cache, long long rows, int C, int nr, FlatGrid* g) {
+  int sms; int rc = device_sm_count(&sms); if (rc) return rc;
+  if (*cache <= 0) {
+    int per_sm = 0;
+    XV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
+    *cache = per_sm > 0 ? per_sm : 1;
+  }
+  g->col_groups = ceil_div(C, WCH);
+  int row_blocks = (*cache * sms) / g->col_groups;
+  if (row_blocks < 1) row_blocks = 1;
+  const int quantum = 8 * nr;
+  long long rpb = (rows + row_blocks - 1) / row_blocks;
+  rpb = (rpb + quantum - 1) / quantum * quantum;
+  row_blocks = static_cast<int>((rows + rpb - 1) / rpb);
+  g->rows_per_block = static_cast<int>(rpb);
+  g->grid = row_blocks * g->col_groups;
+  return XV_OK;
+}
+// 0: chunked kernels; 1 / 2: flat kernels with 1 / 2 rows in flight per warp.  Per kernel family: XV_FLAT_APPLY (BN apply),
+// XV_FLAT_BWD (BN backward apply), XV_FLAT_FUSED (tdnn5 backward apply with the on-the-fly pooling gradient); XV_FLAT
+// sets all three.  Defaults from the on-box sweep (tools/layers_bench.py, profiles/).
+enum { FLAT_APPLY = 0, FLAT_BWD = 1, FLAT_FUSED = 2 };
+static int flat_mode(int which) {
+  static int mode[3] = {-1, -1, -1};
+  if (mode[which] < 0) {
+    static const char* names[3] = {"XV_FLAT_APPLY", "XV_FLAT_BWD", "XV_FLAT_FUSED"};
+    static const int defaults[3] = {XV_FLAT_APPLY_DEFAULT, XV_FLAT_BWD_DEFAULT, XV_FLAT_FUSED_DEFAULT};
+    const char* e = getenv(names[which]);
+    if (!e) e = getenv("XV_FLAT");
+    int m = e ? atoi(e) : defaults[which];
+    if (m < 0 || m > 2) m = defaults[which];
+    mode[which] = m;
+  }
+  return mode[which];
+}
+
 }  // namespace xv
 
 using namespace xv;
@@ -840,7 +1082,7 @@ extern "C" int xv_pack_input(const float* x, void* out, int B, int T, int D, int
   if (!x || !out || B <= 0 || T <= 0 || D <= 0 || D > dpad || k * dpad > ldo || dpad % 8 || ldo % 8)
     return set_error(XV_ERR_INVALID, "xv_pack_input: bad arguments (dpad and ldo must be multiples of 8)");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
-  const long long total = static_cast<long long>(B) * T * ((ldo + dpad - 1) / dpad);
+  const long long total = static_cast<long long>(B) * T * (ldo / 8);
   ::xv::launch_pdl((pack_input_kernel), grid_for(total, 256, sms), 256, 0, static_cast<cudaStream_t>(stream), 
       x, static_cast<__nv_bfloat16*>(out), B, T, D, k, dpad, ldo);
   XV_CUDA_CHECK(cudaGetLastError());
@@ -883,6 +1125,26 @@ static int launch_bn_act_apply(const void* y, void* a, const float* scale, const
   int rc = check_act_layout("xv_bn_act_apply", C, ld, act, alpha); if (rc) return rc;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_apply: rows must fit in int32");
   if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
+  if (flat_mode(FLAT_APPLY) > 0) {
+    static int occ[2][8];
+    const int nr = flat_mode(FLAT_APPLY);
+    FlatGrid fg;
+    if (nr == 1) {
+      XV_ACT_DISPATCH(act, {
+        rc = flat_grid(bn_act_apply_flat_kernel<A_, 1>, &occ[0][A_], rows, C, 1, &fg); if (rc) return rc;
+        ::xv::launch_pdl((bn_act_apply_flat_kernel<A_, 1>), fg.grid, 256, 0, static_cast<cudaStream_t>(stream),
+            static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha,
+            static_cast<int>(rows), fg.rows_per_block, fg.col_groups, C, ld, seg_len, seg_valid, lengths, bt); });
+    } else {
+      XV_ACT_DISPATCH(act, {
+        rc = flat_grid(bn_act_apply_flat_kernel<A_, 2>, &occ[1][A_], rows, C, 2, &fg); if (rc) return rc;
+        ::xv::launch_pdl((bn_act_apply_flat_kernel<A_, 2>), fg.grid, 256, 0, static_cast<cudaStream_t>(stream),
+            static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(a), scale, shift, alpha,
+            static_cast<int>(rows), fg.rows_per_block, fg.col_groups, C, ld, seg_len, seg_valid, lengths, bt); });
+    }
+    XV_CUDA_CHECK(cudaGetLastError());
+    return XV_OK;
+  }
   const RowGrid rg = make_row_grid(rows, seg_len, C, WCH);
   const unsigned grid = static_cast<unsigned>(ceil_div(C, WCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
   XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_apply_kernel<A_>), grid, 256, 0, static_cast<cudaStream_t>(stream),
@@ -975,6 +1237,29 @@ extern "C" int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, cons
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_bn_act_bwd_apply: rows must fit in int32");
   PoolGradSrc ps{pooled, dpooled, pool_cpad, pool_c_real};
   if (seg_len > 0 && rows % seg_len) return set_error(XV_ERR_INVALID, "rows must be a multiple of seg_len");
+  if (flat_mode(pooled ? FLAT_FUSED : FLAT_BWD) > 0) {
+    static int occ[2][2][8];
+    const int nr = flat_mode(pooled ? FLAT_FUSED : FLAT_BWD);
+    const cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* yb = static_cast<const __nv_bfloat16*>(y);
+    const __nv_bfloat16* dab = static_cast<const __nv_bfloat16*>(da);
+    __nv_bfloat16* dyb = static_cast<__nv_bfloat16*>(dy);
+    const int rows_i = static_cast<int>(rows);
+    const float invc = 1.0f / count;
+    FlatGrid fg;
+#define XV_FLAT_BWD(FUSED, NRV)                                                                                          \
+    XV_ACT_DISPATCH(act, {                                                                                               \
+      rc = flat_grid(bn_act_bwd_apply_flat_kernel<FUSED, A_, NRV>, &occ[FUSED ? 1 : 0][NRV - 1][A_], rows, C, NRV, &fg); \
+      if (rc) return rc;                                                                                                 \
+      ::xv::launch_pdl((bn_act_bwd_apply_flat_kernel<FUSED, A_, NRV>), fg.grid, 256, 0, s_, yb, FUSED ? nullptr : dab, dyb,  \
+                       scale, shift, save_mean, save_rstd, dgamma, dbeta, invc, alpha, rows_i, fg.rows_per_block,        \
+                       fg.col_groups, C, ld, seg_len, seg_valid, lengths, ps); })
+    if (pooled) { if (nr == 1) { XV_FLAT_BWD(true, 1); } else { XV_FLAT_BWD(true, 2); } }
+    else { if (nr == 1) { XV_FLAT_BWD(false, 1); } else { XV_FLAT_BWD(false, 2); } }
+#undef XV_FLAT_BWD
+    XV_CUDA_CHECK(cudaGetLastError());
+    return XV_OK;
+  }
   const RowGrid rg = make_row_grid(rows, seg_len, C, WCH, pooled ? FUSED_STREAM_ROWS : STREAM_ROWS);
   const unsigned grid = static_cast<unsigned>(ceil_div(C, WCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
   if (pooled) {

@@ -203,7 +203,14 @@ class Trainer(object):
             self._fwd_bwd(st["x"], st["y"], l2_loss=False, backward_part=("head" if overlap else None))
 
         def part_a2():
-            eng.backward("trunk")
+            # the head-bucket all-reduce is in flight: cap the persistent GEMM grids so that NCCL's CTAs do not strand
+            # GEMM CTAs behind them (xv_gemm_set_cta_limit); the cap is baked into the captured launches
+            reserve = int(self.params.dict.get("dp_overlap_reserve_sms", 16))
+            L.check(eng.lib.xv_gemm_set_cta_limit(max(eng.num_sms - reserve, 2)))
+            try:
+                eng.backward("trunk")
+            finally:
+                L.check(eng.lib.xv_gemm_set_cta_limit(0))
 
         def part_b():
             if eng.head_shard is not None:       # regularisation loss of this rank's head columns, for the logged total
