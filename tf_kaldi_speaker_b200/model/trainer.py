@@ -138,6 +138,7 @@ class Trainer(object):
         ``l2_loss=False``: the regularisation loss is left to the optimizer kernel (same pass over the parameters)."""
         eng = self.engine
         eng.begin_step(True)
+        eng.prefetch_head_weights("softmax/output/kernel", normalize=(self.loss_type != "softmax"))
         out, endpoints = self.entire_network(features, self.params, True, True)
         loss, endpoints_loss = self.loss_network(out, labels, self.num_speakers, self.params, True, True)
         endpoints.update(endpoints_loss)

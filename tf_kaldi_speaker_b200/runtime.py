@@ -319,8 +319,13 @@ class Engine(object):
         self.epilogue_stats = True       # False: BN batch statistics from the separate xv_col_stats pass (tests)
         self.fuse_bn_bwd = True          # dgrad epilogues accumulate the producer layer's BN dgamma / dbeta
         self.side_wgrad = False          # frame-level wgrad GEMMs on a second stream: measured 1.067 vs 1.056 ms (no gain)
+        # utterance-level weight-gradient work (tdnn6 / tdnn7 / head dW GEMMs, head_finish_dw) and the head's weight
+        # normalisation run on a second stream: the utterance-level chain is ~20 dependent, latency-bound launches that
+        # leave most SMs idle, and nothing but the optimizer consumes these results
+        self.side_utt = True
         self._side = None
         self._side_used = False
+        self._head_prefetch = None       # (kernel name, normalize) whose bf16 operand the side stream is preparing
         self.head_shard = None           # parallel.HeadShard: the speaker matrix is split by columns over the ranks
         self.segmenter = None            # SegmentedGraph while a step containing collectives is being captured
 
@@ -422,11 +427,11 @@ class Engine(object):
         data-parallel wrapper all-reduces them while the frame-level backward is still running)."""
         self.tape_mark = len(self.tape)
 
-    def on_side_stream(self):
+    def on_side_stream(self, enabled=None):
         """Context manager: work enqueued inside runs on the side stream, ordered after everything already enqueued on
         the current stream (fork); join_side_stream() makes the current stream wait for it."""
         import contextlib
-        if not self.side_wgrad:
+        if not (self.side_wgrad if enabled is None else enabled):
             return contextlib.nullcontext()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -768,8 +773,9 @@ class Engine(object):
                           L.ptr(srstd), L.ptr(alpha_t), act, L.ptr(dy), L.ptr(dyb), gg(0), gg(1),
                           L.ptr(None if alpha is None else st.grad(alpha)), L.ptr(st.grad(bias)), L.stream_ptr())
                 # wgrad: dW[kk, n] = sum_i u[i, kk] dy[i, n]   (A = bf16(u) MN-major window of the split copy)
-                self.gemm(L.operand(u.split, True, cols=K), L.operand(dyb, True), K, cout, B, st.grad(kernel),
-                          epilogue=L.EPI_F32)
+                with self.on_side_stream(self.side_utt):
+                    self.gemm(L.operand(u.split, True, cols=K), L.operand(dyb, True), K, cout, B, st.grad(kernel),
+                              epilogue=L.EPI_F32)
                 if u.needs_grad:
                     du = self.buf(u.name + "/grad", (B, K), torch.float32)
                     self.gemm(L.operand(dyb, False), L.operand(W3, False, rows=K), B, K, cout, du, epilogue=L.EPI_F32)
@@ -780,6 +786,22 @@ class Engine(object):
         return yu, bn_out, au
 
     # ---- head -------------------------------------------------------------------------------------
+    def prefetch_head_weights(self, kernel, normalize):
+        """Start the head's weight preparation (column normalisation + bf16 [hi; lo; hi] split, 37 MB of traffic at 7200
+        speakers) on the side stream at the beginning of the step: it depends on the parameters only, so it overlaps the
+        trunk forward instead of sitting in the latency-bound utterance-level chain.  margin_head() joins it."""
+        if not self.side_utt or self.head_shard is not None or kernel not in self.store:
+            return
+        st = self.store
+        Wm = st.view(kernel)
+        E, cpad = Wm.shape
+        wn3 = self.buf("head/wn3", (3 * E, cpad), torch.bfloat16)
+        inv_norm = self.buf("head/inv_norm", (cpad,), torch.float32)
+        with self.on_side_stream(True):
+            self.call(self.lib.xv_head_prep_weights, L.ptr(Wm), L.ptr(wn3), L.ptr(inv_norm), E, cpad, C.c_int64(cpad),
+                      int(normalize), L.stream_ptr())
+        self._head_prefetch = (kernel, int(normalize))
+
     def margin_head(self, u, labels, kernel, bias, head_type, num_outputs, training, margin=0.0, asoftmax_m=1,
                     scaling=0.0, want_logits=False):
         """Fused normalise -> cosine GEMM -> margin -> online log-sum-exp (model/loss.py heads + l2_scaling).
@@ -792,8 +814,12 @@ class Engine(object):
         normalize = 0 if head_type == L.HEAD_SOFTMAX else 1
         wn3 = self.buf("head/wn3", (3 * E, cpad), torch.bfloat16)
         inv_norm = self.buf("head/inv_norm", (cpad,), torch.float32)
-        self.call(self.lib.xv_head_prep_weights, L.ptr(Wm), L.ptr(wn3), L.ptr(inv_norm), E, cpad, C.c_int64(cpad),
-                  normalize, L.stream_ptr())
+        if self._head_prefetch == (kernel, normalize):
+            self.join_side_stream()          # prepared on the side stream while the trunk forward was running
+            self._head_prefetch = None
+        else:
+            self.call(self.lib.xv_head_prep_weights, L.ptr(Wm), L.ptr(wn3), L.ptr(inv_norm), E, cpad, C.c_int64(cpad),
+                      normalize, L.stream_ptr())
         x = self.buf("head/x", (B, E), torch.float32)
         x3 = self.buf("head/x3", (B, 3 * E), torch.bfloat16)
         xnorm = self.buf("head/xnorm", (B,), torch.float32)
@@ -830,9 +856,10 @@ class Engine(object):
                           bias=bias_t, head=h, col_sum=(st.grad(bias) if bias is not None else None))
                 # dWn[e, c] = sum_i x[i, e] d[i, c]
                 gw = st.grad(kernel)
-                self.gemm(L.operand(x3, True, cols=E), L.operand(d, True, cols=Cn), E, Cn, B, gw, epilogue=L.EPI_F32)
-                if normalize:
-                    self.call(self.lib.xv_head_finish_dw, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), E, cpad, L.stream_ptr())
+                with self.on_side_stream(self.side_utt):
+                    self.gemm(L.operand(x3, True, cols=E), L.operand(d, True, cols=Cn), E, Cn, B, gw, epilogue=L.EPI_F32)
+                    if normalize:
+                        self.call(self.lib.xv_head_finish_dw, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), E, cpad, L.stream_ptr())
                 # dx[i, e] = sum_c d[i, c] wn[e, c]
                 dxg = self.buf("head/dxg", (B, E), torch.float32, zero=True)
                 sp = self.splits_for(B, E, Cn)
