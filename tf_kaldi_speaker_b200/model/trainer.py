@@ -221,9 +221,10 @@ class Trainer(object):
                          C.c_int64(nb), L.ptr(eng.scalars[4:5]), L.stream_ptr())
             eng.optimizer_step(self.opt, clip=clip, with_l2_loss=True)
 
-        if self.dp is not None and eng.head_shard is not None:
-            # class-sharded head: the step contains collectives (row all-gather, partial exchange, dx reduce-scatter,
-            # trunk-gradient all-reduce); it is captured as consecutive CUDA graphs with the exchanges between them
+        if self.dp is not None and (eng.head_shard is not None or eng.sync_bn is not None):
+            # class-sharded head / SyncBN: the step contains collectives (row all-gather, partial exchange, dx
+            # reduce-scatter, BN statistics, trunk-gradient all-reduce); it is captured as consecutive CUDA graphs with
+            # the exchanges between them
             def body():
                 part_a()
                 eng.collective(self.dp.allreduce_gradients)

@@ -126,6 +126,30 @@ class HeadShard(object):
         return torch.cat([allb[r, :, :(self.range_of(r)[1] - self.range_of(r)[0])] for r in range(self.world)], 1)
 
 
+class SyncBN(object):
+    """Exchanges of synchronised batch normalisation: with ``params.sync_bn`` every BN layer normalises
+    with the statistics of the GLOBAL batch, so an N-GPU step equals the 1-GPU step on the concatenated batch.
+    Frame-level layers all-reduce their per-channel (sum, sum of squares) forward and (dgamma, dbeta) backward;
+    utterance-level layers all-gather their [B, C] rows (runtime.Engine.frame_affine / utt_affine)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def all_reduce_sum_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather(self, out, local):
+        if self.world == 1:
+            out.view(-1).copy_(local.reshape(-1))
+        else:
+            dist.all_gather_into_tensor(out.view(-1), local.reshape(-1), group=self.group)
+        return out
+
+
 class SegmentedGraph(object):
     """A step that contains host-side collectives, captured as consecutive CUDA graphs with the collectives replayed
     eagerly between them (all on the current stream, so stream order carries every dependency).  Engine.collective()
@@ -201,6 +225,9 @@ class DataParallel(object):
                 "sharded variables must be declared last"
         self.comm.broadcast_(st.params[:self.dp_numel])
         self.comm.broadcast_(st.buffers)
+        params = getattr(trainer, "params", None)
+        if params is not None and bool(params.dict.get("sync_bn", False)) and self.world > 1:
+            eng.sync_bn = SyncBN()
         st.refresh_shadows()
         trainer.dp = self
 

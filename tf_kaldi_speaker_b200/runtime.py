@@ -327,6 +327,7 @@ class Engine(object):
         self._side_used = False
         self._head_prefetch = None       # (kernel name, normalize) whose bf16 operand the side stream is preparing
         self.head_shard = None           # parallel.HeadShard: the speaker matrix is split by columns over the ranks
+        self.sync_bn = None              # parallel.SyncBN: batch-norm statistics over the GLOBAL batch (all ranks)
         self.segmenter = None            # SegmentedGraph while a step containing collectives is being captured
 
     def collective(self, fn):
@@ -502,11 +503,14 @@ class Engine(object):
                       x.T, valid, L.ptr(lengths), L.ptr(stats[0]), L.ptr(stats[1]), L.stream_ptr())
         if use_stats and lengths is not None:
             raise NotImplementedError("training-mode BN needs one valid length per batch (data_loader.py:273)")
+        sync = self.sync_bn if (use_stats and self.sync_bn is not None and self.sync_bn.world > 1) else None
+        if sync is not None:      # SyncBN: per-channel (sum, sum of squares) over every rank's rows
+            self.collective(lambda: sync.all_reduce_sum_(stats))
         scale = self.buf(name + "/scale", (cout_pad,), torch.float32)
         shift = self.buf(name + "/shift", (cout_pad,), torch.float32)
         smean = self.buf(name + "/save_mean", (cout_pad,), torch.float32)
         srstd = self.buf(name + "/save_rstd", (cout_pad,), torch.float32)
-        count = float(x.B * valid)
+        count = float(x.B * valid) * (sync.world if sync is not None else 1)
         if bn is None:
             scale.fill_(1.0)
             shift.zero_()
@@ -572,6 +576,10 @@ class Engine(object):
                               L.ptr(smean), L.ptr(srstd), L.ptr(alpha_t), act, C.c_int64(R), cout_pad, C.c_int64(cout_pad),
                               x.T, valid, lp, L.ptr(dgamma), L.ptr(dbeta), L.ptr(dalpha), *pool_args, L.stream_ptr())
                 dy = self.buf(name + "/dy", (R, cout_pad), torch.bfloat16)
+                if sync is not None:
+                    # SyncBN backward: dgamma / dbeta over the global batch enter dy; they live in the flat gradient buffer,
+                    # whose final all-reduce would sum them a second time -> pre-scaled by 1/N after use (below)
+                    self.collective(lambda: (sync.all_reduce_sum_(dgamma), sync.all_reduce_sum_(dbeta)))
                 if bn is not None:
                     dg_used, db_used = dgamma, dbeta
                 else:       # no BN: dy = g; the reductions above were the bias gradient
@@ -579,6 +587,9 @@ class Engine(object):
                 self.call(self.lib.xv_bn_act_bwd_apply, L.ptr(y), L.ptr(aa.grad), L.ptr(dy), L.ptr(scale), L.ptr(shift),
                           L.ptr(smean), L.ptr(srstd), L.ptr(dg_used), L.ptr(db_used), C.c_float(count), L.ptr(alpha_t),
                           act, C.c_int64(R), cout_pad, C.c_int64(cout_pad), x.T, valid, lp, *pool_args, L.stream_ptr())
+                if sync is not None:
+                    dgamma.mul_(1.0 / sync.world)
+                    dbeta.mul_(1.0 / sync.world)
                 # wgrad: dW[(j,c), n] = sum_r X[r+j, c] dY[r, n].  Nothing downstream of it until the optimizer, so it runs
                 # on a side stream: its CTAs fill the SMs that the dgrad's last (partial) wave leaves idle and overlap the
                 # memory-bound BN kernels of the next layer.
@@ -706,6 +717,8 @@ class Engine(object):
         st = self.store
         B, Cn = u.data.shape
         mode = 1 if training else 2
+        if training and self.sync_bn is not None and self.sync_bn.world > 1:
+            raise NotImplementedError("sync_bn does not cover att_apply_nonlinear's post-pooling batch-norm")
         a = self.buf(name + "/a", (B, Cn), torch.float32)
         a3 = self.buf(name + "/a3", (B, 3 * Cn), torch.bfloat16)
         bn_out = self.buf(name + "/bn", (B, Cn), torch.float32)
@@ -747,16 +760,27 @@ class Engine(object):
         self.gemm(L.operand(u.split, False), L.operand(W3, True), B, cout, 3 * K, y, epilogue=L.EPI_F32, splits=splits,
                   bias=st.view(bias))
         mode = 0 if bn is None else (1 if training else 2)
-        a = self.buf(name + "/a", (B, cout), torch.float32)
-        a3 = self.buf(name + "/a3", (B, 3 * cout), torch.bfloat16)
-        bn_out = self.buf(name + "/bn", (B, cout), torch.float32) if bn is not None else None
+        sync = self.sync_bn if (mode == 1 and self.sync_bn is not None and self.sync_bn.world > 1) else None
+        # SyncBN on [B, C] tensors: the rows of every rank are all-gathered (a few hundred KB) and every rank normalises
+        # all N*B rows, so the batch statistics -- and later dgamma / dbeta -- are the global ones without a reduction
+        Bn = B * sync.world if sync is not None else B
+        r0 = sync.rank * B if sync is not None else 0
+        y_bn = y
+        if sync is not None:
+            y_bn = self.buf(name + "/y_all", (Bn, cout), torch.float32)
+            self.collective(lambda: sync.all_gather(y_bn, y))
+        a_f = self.buf(name + "/a", (Bn, cout), torch.float32)
+        a3_f = self.buf(name + "/a3", (Bn, 3 * cout), torch.bfloat16)
+        bn_f = self.buf(name + "/bn", (Bn, cout), torch.float32) if bn is not None else None
         smean = self.buf(name + "/save_mean", (cout,), torch.float32)
         srstd = self.buf(name + "/save_rstd", (cout,), torch.float32)
         g = lambda i: (L.ptr(st.view(bn[i])) if bn is not None else L.ptr(None))
         alpha_t = None if alpha is None else st.view(alpha)
-        self.call(self.lib.xv_bn_rows_fwd, L.ptr(y), B, cout, mode, g(0), g(1), g(2), g(3), C.c_float(momentum),
-                  C.c_float(BN_EPS), L.ptr(alpha_t), act, L.ptr(bn_out), L.ptr(a), L.ptr(a3), 3, L.ptr(smean),
+        self.call(self.lib.xv_bn_rows_fwd, L.ptr(y_bn), Bn, cout, mode, g(0), g(1), g(2), g(3), C.c_float(momentum),
+                  C.c_float(BN_EPS), L.ptr(alpha_t), act, L.ptr(bn_f), L.ptr(a_f), L.ptr(a3_f), 3, L.ptr(smean),
                   L.ptr(srstd), L.stream_ptr())
+        a, a3 = a_f[r0:r0 + B], a3_f[r0:r0 + B]
+        bn_out = None if bn_f is None else bn_f[r0:r0 + B]
         yu = UttAct(y, None, name + "/y")
         au = UttAct(a, a3, name + "/a")
         if bn_out is not None:
@@ -766,12 +790,22 @@ class Engine(object):
                 if au.grad is None and yu.grad is None:
                     return
                 da = au.grad if au.grad is not None else self.buf(name + "/da0", (B, cout), torch.float32, zero=True)
-                dy = self.buf(name + "/dy", (B, cout), torch.float32)
-                dyb = self.buf(name + "/dyb", (B, cout), torch.bfloat16)
+                da_bn = da
+                if sync is not None:
+                    da_bn = self.buf(name + "/da_all", (Bn, cout), torch.float32)
+                    da_c = da.contiguous()
+                    self.collective(lambda: sync.all_gather(da_bn, da_c))
+                dy_f = self.buf(name + "/dy", (Bn, cout), torch.float32)
+                dyb_f = self.buf(name + "/dyb", (Bn, cout), torch.bfloat16)
                 gg = lambda i: (L.ptr(st.grad(bn[i])) if bn is not None else L.ptr(None))
-                self.call(self.lib.xv_bn_rows_bwd, L.ptr(y), L.ptr(da), B, cout, mode, g(0), g(1), L.ptr(smean),
-                          L.ptr(srstd), L.ptr(alpha_t), act, L.ptr(dy), L.ptr(dyb), gg(0), gg(1),
+                self.call(self.lib.xv_bn_rows_bwd, L.ptr(y_bn), L.ptr(da_bn), Bn, cout, mode, g(0), g(1), L.ptr(smean),
+                          L.ptr(srstd), L.ptr(alpha_t), act, L.ptr(dy_f), L.ptr(dyb_f), gg(0), gg(1),
                           L.ptr(None if alpha is None else st.grad(alpha)), L.ptr(st.grad(bias)), L.stream_ptr())
+                dy, dyb = dy_f[r0:r0 + B], dyb_f[r0:r0 + B]
+                if sync is not None:     # every rank holds the GLOBAL dgamma / dbeta / dbias: undo the final all-reduce's sum
+                    for t_ in ([st.grad(bn[0]), st.grad(bn[1])] if bn is not None else []) + [st.grad(bias)] + \
+                              ([st.grad(alpha)] if alpha is not None else []):
+                        t_.mul_(1.0 / sync.world)
                 # wgrad: dW[kk, n] = sum_i u[i, kk] dy[i, n]   (A = bf16(u) MN-major window of the split copy)
                 with self.on_side_stream(self.side_utt):
                     self.gemm(L.operand(u.split, True, cols=K), L.operand(dyb, True), K, cout, B, st.grad(kernel),
