@@ -315,6 +315,10 @@ XV_API int xv_opt_step(float* params, const float* grads, float* state1, float* 
                        const float* hyper, const float* gsumsq, float* l2_loss_out, void* stream);
 XV_API int xv_shadow_refresh(const float* params, const int64_t* blk_shadow, const int64_t* blk_split_stride,
                              void* shadow, int64_t n, void* stream);
+/* Optional bf16 gradient exchange of the data-parallel step: round the flat f32 gradient buffer to bf16 before the
+ * all-reduce (half the NVLink bytes) and widen the reduced values again for xv_opt_step.  n % 8 == 0. */
+XV_API int xv_grad_pack_bf16(const float* grads, void* out_bf16, int64_t n, void* stream);
+XV_API int xv_grad_unpack_bf16(const void* in_bf16, float* grads, int64_t n, void* stream);
 XV_API int xv_l2_loss(const float* params, const float* blk_l2, int64_t n, float* out, void* stream);
 /* dst[0..n) = host_vals[0..n) (n <= 16), passed as kernel arguments: the learning_rate / global_step placeholders of
  * model/trainer.py:229-231,326 fed per step without a host-buffer race under CUDA-graph replay. */

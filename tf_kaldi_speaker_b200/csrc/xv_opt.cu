@@ -203,6 +203,29 @@ static int opt_grid(long long n, int sms) {
   return static_cast<int>(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
+
+// Gradient exchange in bf16 (optional, parallel.DataParallel grad_dtype="bf16"): the flat fp32 gradient buffer is rounded
+// to bf16 for the all-reduce (half the NVLink bytes) and widened again for the optimizer.  8 elements per thread.
+__global__ void __launch_bounds__(256) grad_pack_bf16_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_entry();
+  for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 8; i + 7 < n; i += gridDim.x * 2048LL) {
+    const float4 a = *reinterpret_cast<const float4*>(g + i), b = *reinterpret_cast<const float4*>(g + i + 4);
+    __nv_bfloat162 h[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                           __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<uint4*>(h);
+  }
+}
+__global__ void __launch_bounds__(256) grad_unpack_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ g, long long n) {
+  pdl_entry();
+  for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 8; i + 7 < n; i += gridDim.x * 2048LL) {
+    const uint4 r = *reinterpret_cast<const uint4*>(in + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+    const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+    *reinterpret_cast<float4*>(g + i) = make_float4(f0.x, f0.y, f1.x, f1.y);
+    *reinterpret_cast<float4*>(g + i + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+  }
+}
+
 }  // namespace xv
 
 using namespace xv;
@@ -257,6 +280,26 @@ extern "C" int xv_set_scalars(float* dst, const float* host_vals, int n, void* s
   Scalars16 s;
   for (int i = 0; i < 16; ++i) s.v[i] = i < n ? host_vals[i] : 0.f;
   ::xv::launch_pdl((set_scalars_kernel), 1, 32, 0, static_cast<cudaStream_t>(stream), dst, s, n);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_grad_pack_bf16(const float* grads, void* out, int64_t n, void* stream) {
+  if (!grads || !out || n <= 0 || n % 8) return set_error(XV_ERR_INVALID, "xv_grad_pack_bf16: n must be a positive multiple of 8");
+  int sms; int rc = device_sm_count(&sms); if (rc) return rc;
+  long long g = (n / 8 + 255) / 256; if (g > sms * 8LL) g = sms * 8LL;
+  ::xv::launch_pdl((grad_pack_bf16_kernel), static_cast<int>(g), 256, 0, static_cast<cudaStream_t>(stream), grads,
+                   static_cast<__nv_bfloat16*>(out), static_cast<long long>(n));
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_grad_unpack_bf16(const void* in, float* grads, int64_t n, void* stream) {
+  if (!grads || !in || n <= 0 || n % 8) return set_error(XV_ERR_INVALID, "xv_grad_unpack_bf16: n must be a positive multiple of 8");
+  int sms; int rc = device_sm_count(&sms); if (rc) return rc;
+  long long g = (n / 8 + 255) / 256; if (g > sms * 8LL) g = sms * 8LL;
+  ::xv::launch_pdl((grad_unpack_bf16_kernel), static_cast<int>(g), 256, 0, static_cast<cudaStream_t>(stream),
+                   static_cast<const __nv_bfloat16*>(in), grads, static_cast<long long>(n));
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

@@ -217,6 +217,8 @@ class DataParallel(object):
         st = eng.store
         # class-sharded head: its kernel (declared last) differs per rank and its gradient is complete locally, so
         # broadcast / all-reduce cover only the replicated prefix of the flat buffers
+        self.grad_dtype = str(getattr(getattr(trainer, "params", None), "dict", {}).get("dp_grad_dtype", "fp32"))
+        self._g16 = None
         self.head_shard = getattr(eng, "head_shard", None)
         self.dp_numel = st.params.numel()
         if self.head_shard is not None:
@@ -237,7 +239,19 @@ class DataParallel(object):
         self._pending = []
 
     def allreduce_gradients(self):
-        self.comm.allreduce_(self.trainer.engine.store.grads[:self.dp_numel])
+        g = self.trainer.engine.store.grads[:self.dp_numel]
+        if self.grad_dtype == "bf16" and self.world > 1:
+            # opt-in: exchange the gradients in bf16 (39 -> 19.5 MB at config 2); every activation gradient of the
+            # frame-level path is already stored in bf16, so this adds one more rounding of the same size per element
+            import ctypes as C
+            from . import _lib as L
+            if self._g16 is None or self._g16.numel() != g.numel():
+                self._g16 = torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
+            L.check(L.load().xv_grad_pack_bf16(L.ptr(g), L.ptr(self._g16), C.c_int64(g.numel()), L.stream_ptr()))
+            self.comm.allreduce_(self._g16)
+            L.check(L.load().xv_grad_unpack_bf16(L.ptr(self._g16), L.ptr(g), C.c_int64(g.numel()), L.stream_ptr()))
+            return
+        self.comm.allreduce_(g)
 
     def allreduce_bucket_async(self, which):
         """Enqueue the sum all-reduce of one gradient bucket on NCCL's stream (ordered after the work already on the

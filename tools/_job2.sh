@@ -1,13 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 400 $TR --master-port 29611 tools/dist_check_sharded.py > gpurun_out/n2_check_aam.json 2> gpurun_out/n2_check_aam.err
-echo "check aam rc=$?"
-timeout 400 $TR --master-port 29612 tools/dist_check_sharded.py --loss softmax > gpurun_out/n2_check_softmax.json 2> gpurun_out/n2_check_softmax.err
-echo "check softmax rc=$?"
-timeout 400 $TR --master-port 29613 bench.py --gpus 2 --no-cpu-baseline > gpurun_out/n2b_bench.json 2> gpurun_out/n2b_bench.err
-timeout 400 $TR --master-port 29614 bench.py --gpus 2 --no-cpu-baseline --dp-overlap --overlap-sms 16 > gpurun_out/n2b_bench_ov16.json 2> gpurun_out/n2b_bench_ov16.err
-timeout 400 $TR --master-port 29615 bench.py --gpus 2 --no-cpu-baseline --dp-overlap --overlap-sms 8 > gpurun_out/n2b_bench_ov8.json 2> gpurun_out/n2b_bench_ov8.err
-timeout 400 $TR --master-port 29616 bench.py --gpus 2 --no-cpu-baseline --dp-overlap --overlap-sms 32 > gpurun_out/n2b_bench_ov32.json 2> gpurun_out/n2b_bench_ov32.err
-for f in n2_check_aam n2_check_softmax; do echo "== $f"; grep '"check"' gpurun_out/$f.json | cut -c1-1500; tail -2 gpurun_out/$f.err; done
-for f in n2b_bench n2b_bench_ov16 n2b_bench_ov8 n2b_bench_ov32; do python -c "import json;d=json.load(open('gpurun_out/$f.json'));print('$f',d['value'],d['ms_per_step'])" || tail -5 gpurun_out/$f.err; done
+timeout 400 $TR --master-port 29621 tools/dist_check_syncbn.py > gpurun_out/n2_check_syncbn.json 2> gpurun_out/n2_check_syncbn.err
+echo "check syncbn rc=$?"
+timeout 400 $TR --master-port 29622 tools/dist_check_sharded.py --variant bf16 > gpurun_out/n2_check_bf16.json 2> gpurun_out/n2_check_bf16.err
+echo "check bf16 rc=$?"
+timeout 400 $TR --master-port 29623 bench.py --gpus 2 --no-cpu-baseline --grad-dtype bf16 > gpurun_out/n2c_bench_bf16.json 2> gpurun_out/n2c_bench_bf16.err
+for f in n2_check_syncbn n2_check_bf16; do echo "== $f"; grep '"check"' gpurun_out/$f.json | cut -c1-1500; tail -4 gpurun_out/$f.err | cut -c1-300; done
+for f in n2c_bench_bf16; do grep '"metric"' gpurun_out/$f.json | python -c "import json,sys;d=json.loads(sys.stdin.read());print('$f',d['value'],d['ms_per_step'])" || tail -12 gpurun_out/$f.err | cut -c1-250; done

@@ -38,7 +38,8 @@ def run(shard, args, rank, world, x, y):
               amsoftmax_lambda_gamma=1e-5, amsoftmax_lambda_power=5)
     if args.loss == "softmax":
         pd["feature_norm"] = False
-    pd["head_class_shard"] = bool(shard)
+    pd["head_class_shard"] = bool(shard) and args.variant == "shard"
+    pd["dp_grad_dtype"] = "bf16" if (shard and args.variant == "bf16") else "fp32"
     tr = Trainer(ParamsPlain(**pd), "/tmp/xv_shardcheck_%d_%d" % (int(shard), rank))
     tr.build("train", bench.D, args.loss, args.speakers)
     dp = parallel.DataParallel(tr, args.batch)
@@ -48,7 +49,7 @@ def run(shard, args, rank, world, x, y):
     def export():
         torch.cuda.synchronize()
         d = {k: v.copy() for k, v in st.export_tf().items()}
-        if shard:
+        if shard and args.variant == "shard":
             sh = tr.engine.head_shard
             assert sh is not None and sh.world == world
             for name, spec in st.specs.items():
@@ -71,7 +72,7 @@ def run(shard, args, rank, world, x, y):
     p_graph = export()
     g = tr._static[tuple(x.shape)]["graphs"]
     assert g is not None, "the step was not captured"
-    info = {"graphs": (g.num_graphs if shard else None)}
+    info = {"graphs": (g.num_graphs if (shard and args.variant == "shard") else None)}
     return losses, p0, (p_eager, p_graph), info
 
 
@@ -81,6 +82,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--speakers", type=int, default=1003)
     ap.add_argument("--loss", default="additive_angular_margin_softmax")
+    ap.add_argument("--variant", default="shard", choices=["shard", "bf16"],
+                    help="trainer B: class-sharded head, or the replicated head with the bf16 gradient all-reduce")
     args = ap.parse_args()
     rank, world = parallel.init_from_env("nccl")
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -124,7 +127,8 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"check": "class-sharded head == replicated head (NCCL, %d ranks)" % world, "ok": bool(flag.item() > 0),
+        print(json.dumps({"check": ("class-sharded head == replicated head (NCCL, %d ranks)" if args.variant == "shard" else
+                                    "bf16 gradient all-reduce vs fp32 all-reduce (NCCL, %d ranks)") % world, "ok": bool(flag.item() > 0),
                           "loss": args.loss, "steps": args.steps, "raw_loss_replicated": [p[0] for p in la],
                           "raw_loss_sharded": [p[0] for p in lb], "max_rel_raw_loss": lerr, "max_rel_total_loss": terr,
                           "criterion": "per parameter: one-step update rel-Frobenius error sharded vs replicated <= max(3 x the "
