@@ -334,6 +334,7 @@ class Engine(object):
         """Run a host-side exchange (torch.distributed call on named workspace buffers) between kernels.  While a step is
         being captured the exchange cuts the CUDA graph: kernels before / after it land in consecutive graph segments
         and the exchange itself is replayed eagerly between them (SegmentedGraph)."""
+        self.join_side_stream()          # a graph segment may not end with forked work in flight; the exchange follows both
         if self.capturing:
             if self.segmenter is None:
                 raise L.XvError("a collective inside a captured step needs a SegmentedGraph")
