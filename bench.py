@@ -178,6 +178,7 @@ def run_ours(args):
     pd["dp_overlap"] = bool(args.dp_overlap) and world > 1 and not shard
     pd["dp_overlap_reserve_sms"] = int(args.overlap_sms)
     pd["dp_grad_dtype"] = args.grad_dtype
+    pd["dp_allreduce"] = args.allreduce
     tr = Trainer(ParamsPlain(**pd), "/tmp/xv_bench_model_%d" % rank)
     tr.build("train", D, LOSS, C)
     if world > 1:
@@ -349,7 +350,7 @@ def run_ours(args):
                                            ("dp%d (batch-sharded replicas, per-replica BN, %s)"
                                             % (world, "two-bucket NCCL all-reduce, head bucket overlapped with the frame-level "
                                                       "backward" if pd["dp_overlap"] else
-                                               ("one flat NCCL all-reduce in %s" % args.grad_dtype))),
+                                               ("one flat all-reduce in %s via %s" % (args.grad_dtype, tr.dp.allreduce_impl if tr.dp else "-")))),
                            "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2 (no flush needed)"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": seg_s_e2e, "unit": "segments/s",
@@ -392,6 +393,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head-shard", action="store_true", help="N>1: split the speaker matrix by columns over the ranks")
+    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "symm", "auto"],
+                    help="N>1: gradient all-reduce through NCCL or through symmetric-memory multimem / two-shot kernels")
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"],
                     help="N>1: dtype of the gradient all-reduce (bf16 halves the NVLink bytes; opt-in)")
     ap.add_argument("--dp-overlap", action="store_true",

@@ -40,6 +40,7 @@ def run(shard, args, rank, world, x, y):
         pd["feature_norm"] = False
     pd["head_class_shard"] = bool(shard) and args.variant == "shard"
     pd["dp_grad_dtype"] = "bf16" if (shard and args.variant == "bf16") else "fp32"
+    pd["dp_allreduce"] = "symm" if (shard and args.variant == "symm") else "nccl"
     tr = Trainer(ParamsPlain(**pd), "/tmp/xv_shardcheck_%d_%d" % (int(shard), rank))
     tr.build("train", bench.D, args.loss, args.speakers)
     dp = parallel.DataParallel(tr, args.batch)
@@ -72,7 +73,7 @@ def run(shard, args, rank, world, x, y):
     p_graph = export()
     g = tr._static[tuple(x.shape)]["graphs"]
     assert g is not None, "the step was not captured"
-    info = {"graphs": (g.num_graphs if (shard and args.variant == "shard") else None)}
+    info = {"graphs": (g.num_graphs if (shard and args.variant == "shard") else None), "allreduce": dp.allreduce_impl}
     return losses, p0, (p_eager, p_graph), info
 
 
@@ -82,7 +83,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--speakers", type=int, default=1003)
     ap.add_argument("--loss", default="additive_angular_margin_softmax")
-    ap.add_argument("--variant", default="shard", choices=["shard", "bf16"],
+    ap.add_argument("--variant", default="shard", choices=["shard", "bf16", "symm"],
                     help="trainer B: class-sharded head, or the replicated head with the bf16 gradient all-reduce")
     args = ap.parse_args()
     rank, world = parallel.init_from_env("nccl")
@@ -127,8 +128,10 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"check": ("class-sharded head == replicated head (NCCL, %d ranks)" if args.variant == "shard" else
-                                    "bf16 gradient all-reduce vs fp32 all-reduce (NCCL, %d ranks)") % world, "ok": bool(flag.item() > 0),
+        print(json.dumps({"check": {"shard": "class-sharded head == replicated head (NCCL, %d ranks)",
+                                    "bf16": "bf16 gradient all-reduce vs fp32 all-reduce (NCCL, %d ranks)",
+                                    "symm": "symmetric-memory all-reduce vs NCCL all-reduce (%d ranks)"}[args.variant] % world,
+                          "allreduce_impl": info.get("allreduce"), "ok": bool(flag.item() > 0),
                           "loss": args.loss, "steps": args.steps, "raw_loss_replicated": [p[0] for p in la],
                           "raw_loss_sharded": [p[0] for p in lb], "max_rel_raw_loss": lerr, "max_rel_total_loss": terr,
                           "criterion": "per parameter: one-step update rel-Frobenius error sharded vs replicated <= max(3 x the "
