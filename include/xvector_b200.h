@@ -315,6 +315,14 @@ XV_API int xv_opt_step(float* params, const float* grads, float* state1, float* 
                        const float* hyper, const float* gsumsq, float* l2_loss_out, void* stream);
 XV_API int xv_shadow_refresh(const float* params, const int64_t* blk_shadow, const int64_t* blk_split_stride,
                              void* shadow, int64_t n, void* stream);
+/* Data-parallel gradient all-reduce as one kernel over NVSwitch multicast memory (no reference counterpart: the
+ * reference is single-device).  multicast_ptr: multicast (NVLS) mapping of the flat f32 gradient buffers of all ranks
+ * (CUDA symmetric memory, same offset on every rank); rank r reduces slice r with multimem.ld_reduce.add.f32 and
+ * broadcasts it with multimem.st.  flag_ptrs_dev: device array of `world` pointers to each rank's u32 flag buffer
+ * (>= grid * world entries, zero-initialised once); block_epoch: local u32[grid] launch counters (zero-initialised).
+ * Every rank must call it the same number of times with the same grid (<= SM count); in place, sum. */
+XV_API int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_ptrs_dev, void* block_epoch, int rank, int world,
+                                    int64_t n, int grid, void* stream);
 /* Optional bf16 gradient exchange of the data-parallel step: round the flat f32 gradient buffer to bf16 before the
  * all-reduce (half the NVLink bytes) and widen the reduced values again for xv_opt_step.  n % 8 == 0. */
 XV_API int xv_grad_pack_bf16(const float* grads, void* out_bf16, int64_t n, void* stream);

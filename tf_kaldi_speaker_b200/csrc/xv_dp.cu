@@ -1,0 +1,96 @@
+// Data-parallel gradient exchange as ONE hand-written kernel over NVSwitch multicast (NVLS) memory.
+//
+// The flat fp32 gradient buffer of every rank lives in CUDA symmetric memory that is also mapped through a multicast
+// address (allocated and rendezvous'd by the host layer, tf_kaldi_speaker_b200/parallel.py).  Rank r owns the r-th
+// slice of the buffer: `multimem.ld_reduce.add.v4.f32` returns the sum over all ranks of 16 bytes, reduced inside the
+// switch, and `multimem.st.v4.f32` writes the result back to every rank's copy -- a two-shot all-reduce in which each
+// gradient byte crosses each GPU's NVLink once per direction, with no ring / tree pipeline, no staging buffers and no
+// host involvement: the kernel sits inside the captured CUDA graph of the step, between the backward pass and the
+// optimizer.  Ranks synchronise through per-block flags in a second small symmetric buffer (system-scope
+// release / acquire), so every rank must launch this kernel the same number of times with the same grid.
+#include <cstdint>
+
+#include "xv_internal.h"
+
+namespace xv {
+
+constexpr int AR_THREADS = 512;
+constexpr int AR_UNROLL = 4;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// Block-level barrier across all ranks: block b of rank r writes `epoch` into slot [b][r] of every peer's flag buffer
+// and waits until its own slots [b][*] have reached `epoch` (flags only grow, so nothing is ever reset).
+__device__ __forceinline__ void rank_barrier(uint32_t* const* flags, int rank, int world, uint32_t epoch) {
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const int peer = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(flags[peer] + blockIdx.x * world + rank, epoch);
+    const uint32_t* mine = flags[rank] + blockIdx.x * world + peer;
+    while (ld_acquire_sys(mine) < epoch) {
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(AR_THREADS) dp_allreduce_multimem_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ flags,
+                                                                           uint32_t* __restrict__ block_epoch, int rank, int world,
+                                                                           long long n_vec) {
+  // per-block launch counter (local memory): the same on every rank because every rank launches the same sequence
+  const uint32_t epoch0 = block_epoch[blockIdx.x];
+  rank_barrier(flags, rank, world, epoch0 + 1);          // every rank has finished writing its gradients
+  const long long per = (n_vec + world - 1) / world;
+  const long long lo = per * rank, hi = (lo + per < n_vec) ? lo + per : n_vec;
+  const long long stride = static_cast<long long>(gridDim.x) * AR_THREADS;
+  for (long long i = lo + static_cast<long long>(blockIdx.x) * AR_THREADS + threadIdx.x; i < hi; i += stride * AR_UNROLL) {
+    float4 v[AR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u)
+      if (i + u * stride < hi) v[u] = multimem_ld_reduce_add(mc + 4 * (i + u * stride));
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u)
+      if (i + u * stride < hi) multimem_st(mc + 4 * (i + u * stride), v[u]);
+  }
+  rank_barrier(flags, rank, world, epoch0 + 2);          // every slice has been written back everywhere
+  if (threadIdx.x == 0) block_epoch[blockIdx.x] = epoch0 + 2;
+}
+
+}  // namespace xv
+
+using namespace xv;
+
+extern "C" int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_ptrs_dev, void* block_epoch, int rank, int world,
+                                        int64_t n, int grid, void* stream) {
+  if (!multicast_ptr || !flag_ptrs_dev || !block_epoch || world < 1 || world > 32 || rank < 0 || rank >= world || n <= 0 || (n & 3) ||
+      grid < 1 || grid > 1024 || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15))
+    return set_error(XV_ERR_INVALID, "xv_dp_allreduce_multimem: bad arguments (n %% 4 == 0, 16-byte aligned multicast pointer, "
+                                     "world <= 32, grid <= 1024)");
+  int sms; int rc = device_sm_count(&sms); if (rc) return rc;
+  if (grid > sms) return set_error(XV_ERR_INVALID, "xv_dp_allreduce_multimem: the grid must be co-resident (grid <= SM count)");
+  dp_allreduce_multimem_kernel<<<grid, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<float*>(multicast_ptr), reinterpret_cast<uint32_t* const*>(flag_ptrs_dev), static_cast<uint32_t*>(block_epoch),
+      rank, world, static_cast<long long>(n / 4));
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}

@@ -256,12 +256,18 @@ class Trainer(object):
                     body()
             return self._finish_step(global_step, fetch_loss)
 
+        # the multimem all-reduce is a plain kernel with in-kernel rank barriers: the whole data-parallel step (forward,
+        # backward, gradient exchange, optimizer) is then ONE captured graph, like the single-GPU step
+        in_graph_exchange = self.dp is not None and bool(getattr(self.dp, "graph_safe", False)) and not overlap
+
         def run(ga, ga2, gb):
             """forward + head backward | all-reduce(head bucket) overlapping the frame-level backward | all-reduce(trunk
             bucket) | optimizer.  ga / ga2 / gb are captured graphs or None (eager)."""
             ga.replay() if ga is not None else part_a()
-            if self.dp is None:
+            if self.dp is None or in_graph_exchange:
                 if ga is None:
+                    if in_graph_exchange:
+                        self.dp.allreduce_gradients()
                     part_b()
                 return
             if overlap:
@@ -288,7 +294,10 @@ class Trainer(object):
                         part_a()
                         if self.dp is None:
                             part_b()
-                    if self.dp is not None:
+                        elif in_graph_exchange:
+                            self.dp.allreduce_gradients()
+                            part_b()
+                    if self.dp is not None and not in_graph_exchange:
                         if overlap:
                             ga2 = torch.cuda.CUDAGraph()
                             with torch.cuda.graph(ga2):

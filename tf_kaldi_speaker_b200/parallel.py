@@ -232,9 +232,11 @@ class DataParallel(object):
         # two-shot peer-memory all-reduce kernels -- one launch, no ring/tree pipeline latency for a 39 MB message
         self._symm = None
         self.allreduce_impl = "nccl"
+        self._mm = None
+        self.graph_safe = False          # True: the exchange is a plain kernel launch and may sit inside the captured step
         want = str(getattr(getattr(trainer, "params", None), "dict", {}).get("dp_allreduce", "nccl"))
-        if want in ("symm", "auto") and self.world > 1 and st.params.is_cuda:
-            self._try_symmetric_memory(eng, st, strict=(want == "symm"))
+        if want in ("symm", "multimem", "auto") and self.world > 1 and st.params.is_cuda:
+            self._try_symmetric_memory(eng, st, strict=(want != "auto"), own_kernel=(want != "symm"))
         params = getattr(trainer, "params", None)
         if params is not None and bool(params.dict.get("sync_bn", False)) and self.world > 1:
             eng.sync_bn = SyncBN()
@@ -246,7 +248,7 @@ class DataParallel(object):
         self.split = st.specs["tdnn/tdnn6_dense/kernel"].offset if "tdnn/tdnn6_dense/kernel" in st.specs else 0
         self._pending = []
 
-    def _try_symmetric_memory(self, eng, st, strict):
+    def _try_symmetric_memory(self, eng, st, strict, own_kernel=True):
         try:
             import torch.distributed._symmetric_memory as symm_mem
             if st.arena_used != 0 or eng.ws:
@@ -267,14 +269,38 @@ class DataParallel(object):
             multicast = int(getattr(hdl, "multicast_ptr", 0) or 0) != 0
             self._symm_op = (torch.ops.symm_mem.multimem_all_reduce_ if multicast else torch.ops.symm_mem.two_shot_all_reduce_)
             self.allreduce_impl = "symm_mem multimem (NVLS)" if multicast else "symm_mem two-shot (peer memory)"
+            if own_kernel:
+                if not multicast:
+                    raise RuntimeError("no multicast (NVLS) mapping for the symmetric gradient buffer")
+                # xv_dp_allreduce_multimem: rank flags in a second symmetric buffer, per-block launch counters locally
+                flags = symm_mem.empty(8192, dtype=torch.int32, device=buf.device)
+                hdl_f = symm_mem.rendezvous(flags, group_name)
+                flags.zero_()
+                torch.cuda.synchronize()
+                dist.barrier()               # nobody signals before every rank has zeroed its flags
+                self._mm = {"mc": int(hdl.multicast_ptr), "flags": int(hdl_f.buffer_ptrs_dev), "flags_t": flags, "hdl_f": hdl_f,
+                            "epoch": torch.zeros(1024, dtype=torch.int32, device=buf.device),
+                            "grid": int(min(eng.num_sms, 8192 // max(self.world, 1)))}
+                self.graph_safe = True
+                self.allreduce_impl = "xv_dp_allreduce_multimem (multimem.ld_reduce / multimem.st over NVSwitch, in the captured step)"
         except Exception as ex:
             self._symm = None
+            self._mm = None
+            self.graph_safe = False
             self.allreduce_impl = "nccl (symmetric memory unavailable: %s)" % (str(ex).splitlines()[0][:120] if str(ex) else type(ex).__name__)
             if strict:
                 raise
 
     def allreduce_gradients(self):
         g = self.trainer.engine.store.grads[:self.dp_numel]
+        if self._mm is not None and self.grad_dtype != "bf16":
+            import ctypes as C
+            from . import _lib as L
+            m = self._mm
+            L.check(L.load().xv_dp_allreduce_multimem(C.c_void_p(m["mc"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
+                                                      self.world, C.c_int64(g.numel()), m["grid"], L.stream_ptr()))
+            self.trainer.engine.launches += 1
+            return
         if self._symm is not None and self.grad_dtype != "bf16":
             self._symm_op(g, "sum", self._symm_group)
             return
