@@ -9,13 +9,20 @@
 // optimizer.  Ranks synchronise through per-block flags in a second small symmetric buffer (system-scope
 // release / acquire), so every rank must launch this kernel the same number of times with the same grid.
 #include <cstdint>
+#include <cstdlib>
 
 #include "xv_internal.h"
 
+#ifndef XV_AR_CFG_DEFAULT
+#define XV_AR_CFG_DEFAULT 3
+#endif
+
 namespace xv {
 
-constexpr int AR_THREADS = 512;
-constexpr int AR_UNROLL = 4;
+// Threads per block x 16-byte accesses in flight per thread.  The exchange is latency-bound unless a rank's whole slice is
+// in flight at once (a multimem round trip through the switch is several microseconds): 148 x 512 x 4 x 16 B = 4.8 MB in
+// flight took 8 dependent round trips for a 19.5 MB slice at N = 2 (125 us); XV_AR_CFG = 0..3 selects
+// (512,4) / (1024,4) / (512,8) / (1024,8).
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -54,6 +61,7 @@ __device__ __forceinline__ void rank_barrier(uint32_t* const* flags, int rank, i
   __syncthreads();
 }
 
+template <int AR_THREADS, int AR_UNROLL>
 __global__ void __launch_bounds__(AR_THREADS) dp_allreduce_multimem_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ flags,
                                                                            uint32_t* __restrict__ block_epoch, int rank, int world,
                                                                            long long n_vec) {
@@ -88,9 +96,23 @@ extern "C" int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_p
                                      "world <= 32, grid <= 1024)");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
   if (grid > sms) return set_error(XV_ERR_INVALID, "xv_dp_allreduce_multimem: the grid must be co-resident (grid <= SM count)");
-  dp_allreduce_multimem_kernel<<<grid, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<float*>(multicast_ptr), reinterpret_cast<uint32_t* const*>(flag_ptrs_dev), static_cast<uint32_t*>(block_epoch),
-      rank, world, static_cast<long long>(n / 4));
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("XV_AR_CFG");
+    cfg = e ? atoi(e) : XV_AR_CFG_DEFAULT;
+    if (cfg < 0 || cfg > 3) cfg = XV_AR_CFG_DEFAULT;
+  }
+  float* mc = static_cast<float*>(multicast_ptr);
+  uint32_t* const* fl = reinterpret_cast<uint32_t* const*>(flag_ptrs_dev);
+  uint32_t* ep = static_cast<uint32_t*>(block_epoch);
+  const long long nv = static_cast<long long>(n / 4);
+  cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+  switch (cfg) {
+    case 0: dp_allreduce_multimem_kernel<512, 4><<<grid, 512, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 1: dp_allreduce_multimem_kernel<1024, 4><<<grid, 1024, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 2: dp_allreduce_multimem_kernel<512, 8><<<grid, 512, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    default: dp_allreduce_multimem_kernel<1024, 8><<<grid, 1024, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+  }
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
