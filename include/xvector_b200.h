@@ -323,6 +323,10 @@ XV_API int xv_shadow_refresh(const float* params, const int64_t* blk_shadow, con
  * Every rank must call it the same number of times with the same grid (<= SM count); in place, sum. */
 XV_API int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_ptrs_dev, void* block_epoch, int rank, int world,
                                     int64_t n, int grid, void* stream);
+/* Same exchange without multicast: buf_ptrs_dev = device array of `world` pointers to the ranks' symmetric gradient
+ * buffers; rank r sums slice r with direct peer loads and stores it to every peer.  Preferred at world = 2. */
+XV_API int xv_dp_allreduce_p2p(void* const* buf_ptrs_dev, void* const* flag_ptrs_dev, void* block_epoch, int rank, int world,
+                               int64_t n, int grid, void* stream);
 /* Optional bf16 gradient exchange of the data-parallel step: round the flat f32 gradient buffer to bf16 before the
  * all-reduce (half the NVLink bytes) and widen the reduced values again for xv_opt_step.  n % 8 == 0. */
 XV_API int xv_grad_pack_bf16(const float* grads, void* out_bf16, int64_t n, void* stream);

@@ -278,11 +278,15 @@ class DataParallel(object):
                 flags.zero_()
                 torch.cuda.synchronize()
                 dist.barrier()               # nobody signals before every rank has zeroed its flags
-                self._mm = {"mc": int(hdl.multicast_ptr), "flags": int(hdl_f.buffer_ptrs_dev), "flags_t": flags, "hdl_f": hdl_f,
+                mode = os.environ.get("XV_AR_MODE") or ("p2p" if self.world <= 2 else "multimem")
+                self._mm = {"mc": int(hdl.multicast_ptr), "bufs": int(hdl.buffer_ptrs_dev), "mode": mode,
+                            "flags": int(hdl_f.buffer_ptrs_dev), "flags_t": flags, "hdl_f": hdl_f,
                             "epoch": torch.zeros(1024, dtype=torch.int32, device=buf.device),
                             "grid": int(min(eng.num_sms, 8192 // max(self.world, 1)))}
                 self.graph_safe = True
-                self.allreduce_impl = "xv_dp_allreduce_multimem (multimem.ld_reduce / multimem.st over NVSwitch, in the captured step)"
+                self.allreduce_impl = ("xv_dp_allreduce_multimem (multimem.ld_reduce / multimem.st over NVSwitch, in the captured step)"
+                                       if mode == "multimem" else
+                                       "xv_dp_allreduce_p2p (peer-memory loads / stores over NVLink, in the captured step)")
         except Exception as ex:
             self._symm = None
             self._mm = None
@@ -297,8 +301,12 @@ class DataParallel(object):
             import ctypes as C
             from . import _lib as L
             m = self._mm
-            L.check(L.load().xv_dp_allreduce_multimem(C.c_void_p(m["mc"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
-                                                      self.world, C.c_int64(g.numel()), m["grid"], L.stream_ptr()))
+            if m["mode"] == "multimem":
+                L.check(L.load().xv_dp_allreduce_multimem(C.c_void_p(m["mc"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
+                                                          self.world, C.c_int64(g.numel()), m["grid"], L.stream_ptr()))
+            else:
+                L.check(L.load().xv_dp_allreduce_p2p(C.c_void_p(m["bufs"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
+                                                     self.world, C.c_int64(g.numel()), m["grid"], L.stream_ptr()))
             self.trainer.engine.launches += 1
             return
         if self._symm is not None and self.grad_dtype != "bf16":
