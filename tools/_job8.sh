@@ -2,8 +2,10 @@
 mkdir -p gpurun_out
 N=${1:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 400 $TR --master-port 29713 bench.py --gpus $N --no-cpu-baseline > gpurun_out/n${N}_bench.json 2> gpurun_out/n${N}_bench.err
+timeout 150 $TR --master-port 29740 tools/allreduce_bench.py > gpurun_out/n${N}_arbench.json 2> gpurun_out/n${N}_arbench.err
+echo "arbench rc=$?"; grep '"world"' gpurun_out/n${N}_arbench.json || grep -E "Error|error" gpurun_out/n${N}_arbench.err | head -5 | cut -c1-300
+MODE=$(grep '"world"' gpurun_out/n${N}_arbench.json | python -c "import json,sys;d=json.loads(sys.stdin.read())['full 39.0 MB'];print('p2p' if d['p2p_us']<d['multimem_us'] else 'multimem')" 2>/dev/null || echo multimem)
+echo "mode=$MODE"
+XV_AR_MODE=$MODE timeout 300 $TR --master-port 29741 bench.py --gpus $N --no-cpu-baseline --allreduce multimem > gpurun_out/n${N}f_bench_mm.json 2> gpurun_out/n${N}f_bench_mm.err
 echo "bench rc=$?"
-timeout 400 $TR --master-port 29714 bench.py --gpus $N --no-cpu-baseline --head-shard > gpurun_out/n${N}_bench_shard.json 2> gpurun_out/n${N}_bench_shard.err
-echo "bench shard rc=$?"
-for f in n${N}_bench n${N}_bench_shard; do grep '"metric"' gpurun_out/$f.json | python -c "import json,sys;d=json.loads(sys.stdin.read());print('$f',d['value'],d['ms_per_step'])" || tail -12 gpurun_out/$f.err | cut -c1-250; done
+grep '"metric"' gpurun_out/n${N}f_bench_mm.json | python -c "import json,sys;d=json.loads(sys.stdin.read());print('bench',d['value'],d['ms_per_step'],d['config']['parallelism'])" || (grep -E "Error|error" gpurun_out/n${N}f_bench_mm.err | head -8 | cut -c1-300)
