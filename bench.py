@@ -393,7 +393,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head-shard", action="store_true", help="N>1: split the speaker matrix by columns over the ranks")
-    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "symm", "multimem", "auto"],
+    ap.add_argument("--allreduce", default="auto", choices=["nccl", "symm", "multimem", "auto"],
                     help="N>1: gradient all-reduce through NCCL or through symmetric-memory multimem / two-shot kernels")
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"],
                     help="N>1: dtype of the gradient all-reduce (bf16 halves the NVLink bytes; opt-in)")

@@ -227,14 +227,16 @@ class DataParallel(object):
                 "sharded variables must be declared last"
         self.comm.broadcast_(st.params[:self.dp_numel])
         self.comm.broadcast_(st.buffers)
-        # Gradient exchange: NCCL all-reduce, or ("dp_allreduce": "symm") the flat gradient buffer re-homed in CUDA
-        # symmetric memory and reduced in place by PyTorch's multimem (NVLS in-switch reduction over NVSwitch) /
-        # two-shot peer-memory all-reduce kernels -- one launch, no ring/tree pipeline latency for a 39 MB message
+        # Gradient exchange ("dp_allreduce"): "auto" (default) / "multimem": the flat gradient buffer is re-homed in CUDA
+        # symmetric memory and reduced in place by our own kernel INSIDE the captured step (xv_dp_allreduce_multimem: NVLS
+        # in-switch reduction, N > 2; xv_dp_allreduce_p2p: peer loads / stores, N = 2); "auto" falls back to NCCL when
+        # symmetric memory or the multicast mapping is unavailable.  "nccl": one torch.distributed all-reduce between two
+        # graphs.  "symm": PyTorch's symm_mem multimem / two-shot library kernels (measured slower at 39 MB).
         self._symm = None
         self.allreduce_impl = "nccl"
         self._mm = None
         self.graph_safe = False          # True: the exchange is a plain kernel launch and may sit inside the captured step
-        want = str(getattr(getattr(trainer, "params", None), "dict", {}).get("dp_allreduce", "nccl"))
+        want = str(getattr(getattr(trainer, "params", None), "dict", {}).get("dp_allreduce", "auto"))
         if want in ("symm", "multimem", "auto") and self.world > 1 and st.params.is_cuda:
             self._try_symmetric_memory(eng, st, strict=(want != "auto"), own_kernel=(want != "symm"))
         params = getattr(trainer, "params", None)
