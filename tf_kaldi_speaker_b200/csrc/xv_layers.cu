@@ -852,6 +852,9 @@ static inline int grid_for(long long work_items, int block, int sms) {
 // contiguous row range [j * rows_per_block, ...) of the flat-time matrix for one 256-channel group, every block has the
 // same number of rows (+-8), constants are loaded once, and the (segment, frame) position of a row is walked
 // incrementally (one integer division per warp).
+#ifndef XV_BWD_FLAT_MINBLOCKS
+#define XV_BWD_FLAT_MINBLOCKS 4
+#endif
 struct FlatWalk {
   int b, t, L;
 };
@@ -949,8 +952,10 @@ __global__ void __launch_bounds__(256) bn_act_apply_flat_kernel(const __nv_bfloa
   }
 }
 
+// ncu (profiles/r01_hbm_kernels_ncu.md): at 72 registers three blocks per SM were resident (34 % achieved occupancy) and
+// the kernel was latency-bound at 0.42 of the HBM peak; the unfused 1-row variant is held to 64 registers = 4 blocks per SM.
 template <bool FUSED_POOL, int ACT, int NR>
-__global__ void __launch_bounds__(256) bn_act_bwd_apply_flat_kernel(
+__global__ void __launch_bounds__(256, (!FUSED_POOL && NR == 1) ? XV_BWD_FLAT_MINBLOCKS : 1) bn_act_bwd_apply_flat_kernel(
     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dy,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ save_mean,
     const float* __restrict__ save_rstd, const float* __restrict__ dgamma, const float* __restrict__ dbeta,

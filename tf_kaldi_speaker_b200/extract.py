@@ -14,6 +14,7 @@ Output order = input order.
 import sys
 
 import numpy as np
+import torch
 
 from .dataset.kaldi_io import open_or_fd, read_mat_ark, write_vec_flt
 
@@ -61,6 +62,7 @@ def extract_embeddings(trainer, features, wspecifier=None, chunk_size=10000, min
     results = {}
     i = 0
     eng = trainer.engine
+    staging = None
     while i < len(order):
         tmax = _bucket(jobs[order[i]][2].shape[0])
         group = []
@@ -68,13 +70,18 @@ def extract_embeddings(trainer, features, wspecifier=None, chunk_size=10000, min
             group.append(order[i])
             i += 1
         dim = jobs[group[0]][2].shape[1]
-        batch = np.zeros((len(group), tmax, dim), dtype=np.float32)
+        need = len(group) * tmax * dim
+        if staging is None or staging.numel() < need:       # one pinned staging buffer, grown geometrically: async H2D
+            staging = torch.empty(int(need * 1.25), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        batch_t = staging[:need].view(len(group), tmax, dim)
+        batch = batch_t.numpy()
         lengths = np.zeros((len(group),), dtype=np.int32)
         for r, j in enumerate(group):
             f = jobs[j][2]
             batch[r, :f.shape[0]] = f
+            batch[r, f.shape[0]:] = 0.0
             lengths[r] = f.shape[0]
-        emb = trainer.predict_batch_padded(batch, lengths)
+        emb = trainer.predict_batch_padded(batch_t, lengths)
         for r, j in enumerate(group):
             results[(jobs[j][0], jobs[j][1])] = emb[r]
         if len(eng.ws) > 400:       # bound the workspace cache when many distinct batch shapes were seen

@@ -365,6 +365,20 @@ class Engine(object):
     def buf(self, name, shape, dtype, zero=False):
         """Named workspace tensor (allocated once per name/shape).  ``zero=True``: the buffer starts every step at zero;
         fp32 buffers come from the zero arena cleared by begin_step's single fill, others are cleared here."""
+        if not getattr(self, "training", True) and not self.capturing:
+            # Inference (extraction over ragged batches): every distinct padded length would otherwise allocate -- and
+            # zero-fill -- its own multi-GB set of activations.  One growing flat buffer per name instead; each kernel
+            # writes its full output (invalid rows / padded channels included), so stale contents are never read.
+            numel = int(np.prod(shape))
+            ikey = ("infer", name, dtype)
+            flat = self.ws.get(ikey)
+            if flat is None or flat.numel() < numel:
+                flat = torch.empty(max(int(numel * 1.25), 1024), dtype=dtype, device=self.device)
+                self.ws[ikey] = flat
+            t = flat[:numel].view(*shape)
+            if zero:
+                t.zero_()
+            return t
         key = (name, tuple(shape), dtype)
         t = self.ws.get(key)
         if t is None:
