@@ -853,7 +853,7 @@ static inline int grid_for(long long work_items, int block, int sms) {
 // same number of rows (+-8), constants are loaded once, and the (segment, frame) position of a row is walked
 // incrementally (one integer division per warp).
 #ifndef XV_BWD_FLAT_MINBLOCKS
-#define XV_BWD_FLAT_MINBLOCKS 4
+#define XV_BWD_FLAT_MINBLOCKS 1       // 4 (<= 64 registers, 28 bytes spilled, 4 blocks per SM): 21.3 vs 21.1 us -- no gain
 #endif
 struct FlatWalk {
   int b, t, L;
@@ -952,8 +952,8 @@ __global__ void __launch_bounds__(256) bn_act_apply_flat_kernel(const __nv_bfloa
   }
 }
 
-// ncu (profiles/r01_hbm_kernels_ncu.md): at 72 registers three blocks per SM were resident (34 % achieved occupancy) and
-// the kernel was latency-bound at 0.42 of the HBM peak; the unfused 1-row variant is held to 64 registers = 4 blocks per SM.
+// ncu (profiles/r01_hbm_kernels_ncu.md): 72 registers = three blocks per SM (34 % achieved occupancy); forcing 64
+// registers / four blocks (XV_BWD_FLAT_MINBLOCKS=4) changed nothing, so occupancy is not what bounds it.
 template <bool FUSED_POOL, int ACT, int NR>
 __global__ void __launch_bounds__(256, (!FUSED_POOL && NR == 1) ? XV_BWD_FLAT_MINBLOCKS : 1) bn_act_bwd_apply_flat_kernel(
     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dy,
