@@ -179,6 +179,9 @@ def run_ours(args):
     pd["dp_overlap_reserve_sms"] = int(args.overlap_sms)
     pd["dp_grad_dtype"] = args.grad_dtype
     pd["dp_allreduce"] = args.allreduce
+    pd["dp_bucket_overlap"] = bool(args.bucket_overlap)
+    pd["dp_bucket_overlap_sms"] = int(args.overlap_sms)
+    pd["dp_bucket_overlap_gemms"] = int(args.overlap_gemms)
     tr = Trainer(ParamsPlain(**pd), "/tmp/xv_bench_model_%d" % rank)
     tr.build("train", D, LOSS, C)
     if world > 1:
@@ -350,7 +353,9 @@ def run_ours(args):
                                            ("dp%d (batch-sharded replicas, per-replica BN, %s)"
                                             % (world, "two-bucket NCCL all-reduce, head bucket overlapped with the frame-level "
                                                       "backward" if pd["dp_overlap"] else
-                                               ("one flat all-reduce in %s via %s" % (args.grad_dtype, tr.dp.allreduce_impl if tr.dp else "-")))),
+                                               ("%s in %s via %s" % ("two buckets, [tdnn6..head] exchanged beside the tdnn5 backward," if args.bucket_overlap
+                                                                 else "one flat all-reduce", args.grad_dtype,
+                                                                 tr.dp.allreduce_impl if tr.dp else "-")))),
                            "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2 (no flush needed)"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": seg_s_e2e, "unit": "segments/s",
@@ -395,6 +400,9 @@ def main():
     ap.add_argument("--head-shard", action="store_true", help="N>1: split the speaker matrix by columns over the ranks")
     ap.add_argument("--allreduce", default="auto", choices=["nccl", "symm", "multimem", "auto"],
                     help="N>1: gradient all-reduce through NCCL or through symmetric-memory multimem / two-shot kernels")
+    ap.add_argument("--bucket-overlap", action="store_true",
+                    help="N>1, in-graph exchange: exchange the [tdnn6 .. head] bucket beside the tdnn5 backward")
+    ap.add_argument("--overlap-gemms", type=int, default=2, help="GEMM launches whose grid is capped during the overlap")
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"],
                     help="N>1: dtype of the gradient all-reduce (bf16 halves the NVLink bytes; opt-in)")
     ap.add_argument("--dp-overlap", action="store_true",

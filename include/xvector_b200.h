@@ -320,13 +320,14 @@ XV_API int xv_shadow_refresh(const float* params, const int64_t* blk_shadow, con
  * (CUDA symmetric memory, same offset on every rank); rank r reduces slice r with multimem.ld_reduce.add.f32 and
  * broadcasts it with multimem.st.  flag_ptrs_dev: device array of `world` pointers to each rank's u32 flag buffer
  * (>= grid * world entries, zero-initialised once); block_epoch: local u32[grid] launch counters (zero-initialised).
- * Every rank must call it the same number of times with the same grid (<= SM count); in place, sum. */
+ * Reduces floats [offset, offset + n) of the buffers (both multiples of 4).  Every rank must call it the same number of
+ * times with the same grid (<= SM count); in place, sum. */
 XV_API int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_ptrs_dev, void* block_epoch, int rank, int world,
-                                    int64_t n, int grid, void* stream);
+                                    int64_t offset, int64_t n, int grid, void* stream);
 /* Same exchange without multicast: buf_ptrs_dev = device array of `world` pointers to the ranks' symmetric gradient
  * buffers; rank r sums slice r with direct peer loads and stores it to every peer.  Preferred at world = 2. */
 XV_API int xv_dp_allreduce_p2p(void* const* buf_ptrs_dev, void* const* flag_ptrs_dev, void* block_epoch, int rank, int world,
-                               int64_t n, int grid, void* stream);
+                               int64_t offset, int64_t n, int grid, void* stream);
 /* Optional bf16 gradient exchange of the data-parallel step: round the flat f32 gradient buffer to bf16 before the
  * all-reduce (half the NVLink bytes) and widen the reduced values again for xv_opt_step.  n % 8 == 0. */
 XV_API int xv_grad_pack_bf16(const float* grads, void* out_bf16, int64_t n, void* stream);

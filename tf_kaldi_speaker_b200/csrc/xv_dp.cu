@@ -101,11 +101,11 @@ __device__ __forceinline__ void st_sys_v4(float* p, float4 v) {
 template <int AR_THREADS, int AR_UNROLL>
 __global__ void __launch_bounds__(AR_THREADS) dp_allreduce_p2p_kernel(float* const* __restrict__ bufs, uint32_t* const* __restrict__ flags,
                                                                       uint32_t* __restrict__ block_epoch, int rank, int world,
-                                                                      long long n_vec) {
+                                                                      long long off_vec, long long n_vec) {
   const uint32_t epoch0 = block_epoch[blockIdx.x];
   rank_barrier(flags, rank, world, epoch0 + 1);
   const long long per = (n_vec + world - 1) / world;
-  const long long lo = per * rank, hi = (lo + per < n_vec) ? lo + per : n_vec;
+  const long long lo = off_vec + per * rank, hi = off_vec + ((per * rank + per < n_vec) ? per * rank + per : n_vec);
   const long long stride = static_cast<long long>(gridDim.x) * AR_THREADS;
   for (long long i = lo + static_cast<long long>(blockIdx.x) * AR_THREADS + threadIdx.x; i < hi; i += stride * AR_UNROLL) {
     float4 acc[AR_UNROLL];
@@ -137,9 +137,9 @@ __global__ void __launch_bounds__(AR_THREADS) dp_allreduce_p2p_kernel(float* con
 using namespace xv;
 
 extern "C" int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_ptrs_dev, void* block_epoch, int rank, int world,
-                                        int64_t n, int grid, void* stream) {
+                                        int64_t offset, int64_t n, int grid, void* stream) {
   if (!multicast_ptr || !flag_ptrs_dev || !block_epoch || world < 1 || world > 32 || rank < 0 || rank >= world || n <= 0 || (n & 3) ||
-      grid < 1 || grid > 1024 || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15))
+      offset < 0 || (offset & 3) || grid < 1 || grid > 1024 || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15))
     return set_error(XV_ERR_INVALID, "xv_dp_allreduce_multimem: bad arguments (n %% 4 == 0, 16-byte aligned multicast pointer, "
                                      "world <= 32, grid <= 1024)");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
@@ -150,7 +150,7 @@ extern "C" int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_p
     cfg = e ? atoi(e) : XV_AR_CFG_DEFAULT;
     if (cfg < 0 || cfg > 3) cfg = XV_AR_CFG_DEFAULT;
   }
-  float* mc = static_cast<float*>(multicast_ptr);
+  float* mc = static_cast<float*>(multicast_ptr) + offset;
   uint32_t* const* fl = reinterpret_cast<uint32_t* const*>(flag_ptrs_dev);
   uint32_t* ep = static_cast<uint32_t*>(block_epoch);
   const long long nv = static_cast<long long>(n / 4);
@@ -166,16 +166,17 @@ extern "C" int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_p
 }
 
 extern "C" int xv_dp_allreduce_p2p(void* const* buf_ptrs_dev, void* const* flag_ptrs_dev, void* block_epoch, int rank, int world,
-                                   int64_t n, int grid, void* stream) {
+                                   int64_t offset, int64_t n, int grid, void* stream) {
   if (!buf_ptrs_dev || !flag_ptrs_dev || !block_epoch || world < 1 || world > 32 || rank < 0 || rank >= world || n <= 0 || (n & 3) ||
-      grid < 1 || grid > 1024)
+      offset < 0 || (offset & 3) || grid < 1 || grid > 1024)
     return set_error(XV_ERR_INVALID, "xv_dp_allreduce_p2p: bad arguments (n %% 4 == 0, world <= 32, grid <= 1024)");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
   if (grid > sms) return set_error(XV_ERR_INVALID, "xv_dp_allreduce_p2p: the grid must be co-resident (grid <= SM count)");
   float* const* bufs = reinterpret_cast<float* const*>(buf_ptrs_dev);
   uint32_t* const* fl = reinterpret_cast<uint32_t* const*>(flag_ptrs_dev);
   dp_allreduce_p2p_kernel<1024, 4><<<grid, 1024, 0, static_cast<cudaStream_t>(stream)>>>(bufs, fl, static_cast<uint32_t*>(block_epoch),
-                                                                                     rank, world, static_cast<long long>(n / 4));
+                                                                                     rank, world, static_cast<long long>(offset / 4),
+                                                                                     static_cast<long long>(n / 4));
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

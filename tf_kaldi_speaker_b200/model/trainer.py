@@ -259,10 +259,33 @@ class Trainer(object):
         # the multimem all-reduce is a plain kernel with in-kernel rank barriers: the whole data-parallel step (forward,
         # backward, gradient exchange, optimizer) is then ONE captured graph, like the single-GPU step
         in_graph_exchange = self.dp is not None and bool(getattr(self.dp, "graph_safe", False)) and not overlap
+        # dp_bucket_overlap: the [tdnn6 .. head] gradients are complete a third of the way into the backward pass; their
+        # exchange runs as a small-grid kernel on a second stream beside the tdnn5 backward (whose two GEMMs leave it a
+        # few SMs), only the [tdnn1 .. tdnn5] bucket is exchanged after the backward pass
+        bucket_overlap = (in_graph_exchange and bool(self.params.dict.get("dp_bucket_overlap", False)) and not clip
+                          and getattr(self.dp, "_mm", None) is not None and self.dp.split > 0
+                          and self.dp.grad_dtype != "bf16")
+
+        def part_ab_overlapped():
+            ex_sms = int(self.params.dict.get("dp_bucket_overlap_sms", 16))
+            self._fwd_bwd(st["x"], st["y"], l2_loss=False, backward_part="head")
+            with eng.fork_exchange_stream():
+                self.dp.allreduce_range(self.dp.split, self.dp.dp_numel, grid=ex_sms)
+            eng.cap_next_gemms(int(self.params.dict.get("dp_bucket_overlap_gemms", 2)), eng.num_sms - ex_sms)
+            try:
+                eng.backward("trunk")
+            finally:
+                eng.cap_next_gemms(0, 0)
+            eng.join_exchange_stream()
+            self.dp.allreduce_range(0, self.dp.split)
+            part_b()
 
         def run(ga, ga2, gb):
             """forward + head backward | all-reduce(head bucket) overlapping the frame-level backward | all-reduce(trunk
             bucket) | optimizer.  ga / ga2 / gb are captured graphs or None (eager)."""
+            if bucket_overlap:
+                ga.replay() if ga is not None else part_ab_overlapped()
+                return
             ga.replay() if ga is not None else part_a()
             if self.dp is None or in_graph_exchange:
                 if ga is None:
@@ -291,12 +314,15 @@ class Trainer(object):
                     ga = torch.cuda.CUDAGraph()
                     ga2 = gb = None
                     with torch.cuda.graph(ga):
-                        part_a()
-                        if self.dp is None:
-                            part_b()
-                        elif in_graph_exchange:
-                            self.dp.allreduce_gradients()
-                            part_b()
+                        if bucket_overlap:
+                            part_ab_overlapped()
+                        else:
+                            part_a()
+                            if self.dp is None:
+                                part_b()
+                            elif in_graph_exchange:
+                                self.dp.allreduce_gradients()
+                                part_b()
                     if self.dp is not None and not in_graph_exchange:
                         if overlap:
                             ga2 = torch.cuda.CUDAGraph()

@@ -300,16 +300,7 @@ class DataParallel(object):
     def allreduce_gradients(self):
         g = self.trainer.engine.store.grads[:self.dp_numel]
         if self._mm is not None and self.grad_dtype != "bf16":
-            import ctypes as C
-            from . import _lib as L
-            m = self._mm
-            if m["mode"] == "multimem":
-                L.check(L.load().xv_dp_allreduce_multimem(C.c_void_p(m["mc"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
-                                                          self.world, C.c_int64(g.numel()), m["grid"], L.stream_ptr()))
-            else:
-                L.check(L.load().xv_dp_allreduce_p2p(C.c_void_p(m["bufs"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
-                                                     self.world, C.c_int64(g.numel()), m["grid"], L.stream_ptr()))
-            self.trainer.engine.launches += 1
+            self.allreduce_range(0, g.numel())
             return
         if self._symm is not None and self.grad_dtype != "bf16":
             self._symm_op(g, "sum", self._symm_group)
@@ -326,6 +317,20 @@ class DataParallel(object):
             L.check(L.load().xv_grad_unpack_bf16(L.ptr(self._g16), L.ptr(g), C.c_int64(g.numel()), L.stream_ptr()))
             return
         self.comm.allreduce_(g)
+
+    def allreduce_range(self, lo, hi, grid=None):
+        """In-graph exchange of gradient floats [lo, hi) (multiples of 4) with our own kernel on the CURRENT stream."""
+        import ctypes as C
+        from . import _lib as L
+        m = self._mm
+        grid = m["grid"] if grid is None else max(1, min(int(grid), m["grid"]))
+        if m["mode"] == "multimem":
+            L.check(L.load().xv_dp_allreduce_multimem(C.c_void_p(m["mc"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
+                                                      self.world, C.c_int64(lo), C.c_int64(hi - lo), grid, L.stream_ptr()))
+        else:
+            L.check(L.load().xv_dp_allreduce_p2p(C.c_void_p(m["bufs"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
+                                                 self.world, C.c_int64(lo), C.c_int64(hi - lo), grid, L.stream_ptr()))
+        self.trainer.engine.launches += 1
 
     def allreduce_bucket_async(self, which):
         """Enqueue the sum all-reduce of one gradient bucket on NCCL's stream (ordered after the work already on the

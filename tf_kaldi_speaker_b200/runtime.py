@@ -326,6 +326,8 @@ class Engine(object):
         self._side = None
         self._side_used = False
         self._head_prefetch = None       # (kernel name, normalize) whose bf16 operand the side stream is preparing
+        self._gemm_cap_left, self._gemm_cap = 0, 0
+        self._side2 = None               # second side stream: the overlapped gradient exchange of the head bucket
         self.head_shard = None           # parallel.HeadShard: the speaker matrix is split by columns over the ranks
         self.sync_bn = None              # parallel.SyncBN: batch-norm statistics over the GLOBAL batch (all ranks)
         self.segmenter = None            # SegmentedGraph while a step containing collectives is being captured
@@ -402,7 +404,18 @@ class Engine(object):
 
     def gemm(self, *a, **kw):
         self.launches += 1
+        if self._gemm_cap_left > 0:          # leave SMs to the exchange kernel running beside the next few GEMMs
+            L.check(self.lib.xv_gemm_set_cta_limit(self._gemm_cap))
+            try:
+                L.gemm(*a, **kw)
+            finally:
+                self._gemm_cap_left -= 1
+                L.check(self.lib.xv_gemm_set_cta_limit(0))
+            return
         L.gemm(*a, **kw)
+
+    def cap_next_gemms(self, count, max_ctas):
+        self._gemm_cap_left, self._gemm_cap = int(count), int(max_ctas)
 
     def splits_for(self, M, N, K, max_splits=64, min_kb=4):
         """Split-K factor of an f32-output GEMM: the persistent grid runs ceil(tiles*s / SMs) rounds of equal-length
@@ -454,6 +467,17 @@ class Engine(object):
         self._side.wait_stream(torch.cuda.current_stream())
         self._side_used = True
         return torch.cuda.stream(self._side)
+
+    def fork_exchange_stream(self):
+        """Context manager: a second side stream, ordered after the work already on the current stream."""
+        if self._side2 is None:
+            self._side2 = torch.cuda.Stream(device=self.device)
+        self._side2.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self._side2)
+
+    def join_exchange_stream(self):
+        if self._side2 is not None:
+            torch.cuda.current_stream().wait_stream(self._side2)
 
     def join_side_stream(self):
         if self._side_used:

@@ -57,21 +57,21 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         L.check(lib.xv_dp_allreduce_multimem(C.c_void_p(int(hdl.multicast_ptr)), C.c_void_p(int(hf.buffer_ptrs_dev)), L.ptr(epoch),
-                                             rank, world, C.c_int64(n), sms, L.stream_ptr()))
+                                             rank, world, C.c_int64(0), C.c_int64(n), sms, L.stream_ptr()))
         torch.cuda.synchronize()
         want = float(sum(r + 1 for r in range(world)))
         ok = bool((buf[:n] == want).all().item()) and bool((buf[n:n + 1024] == float(rank + 1)).all().item())
         t_mm = timed(lambda: L.check(lib.xv_dp_allreduce_multimem(C.c_void_p(int(hdl.multicast_ptr)), C.c_void_p(int(hf.buffer_ptrs_dev)),
-                                                                  L.ptr(epoch), rank, world, C.c_int64(n), sms, L.stream_ptr())))
+                                                                  L.ptr(epoch), rank, world, C.c_int64(0), C.c_int64(n), sms, L.stream_ptr())))
         buf.fill_(float(rank + 1))
         torch.cuda.synchronize()
         dist.barrier()
         L.check(lib.xv_dp_allreduce_p2p(C.c_void_p(int(hdl.buffer_ptrs_dev)), C.c_void_p(int(hf.buffer_ptrs_dev)), L.ptr(epoch),
-                                        rank, world, C.c_int64(n), sms, L.stream_ptr()))
+                                        rank, world, C.c_int64(0), C.c_int64(n), sms, L.stream_ptr()))
         torch.cuda.synchronize()
         ok = ok and bool((buf[:n] == want).all().item()) and bool((buf[n:n + 1024] == float(rank + 1)).all().item())
         t_p2p = timed(lambda: L.check(lib.xv_dp_allreduce_p2p(C.c_void_p(int(hdl.buffer_ptrs_dev)), C.c_void_p(int(hf.buffer_ptrs_dev)),
-                                                              L.ptr(epoch), rank, world, C.c_int64(n), sms, L.stream_ptr())))
+                                                              L.ptr(epoch), rank, world, C.c_int64(0), C.c_int64(n), sms, L.stream_ptr())))
         g = plain[:n]
         t_nccl = timed(lambda: dist.all_reduce(g))
         out[name] = {"multimem_us": t_mm, "p2p_us": t_p2p, "nccl_us": t_nccl, "correct": ok,
