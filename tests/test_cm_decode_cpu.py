@@ -93,3 +93,38 @@ def test_segment_batch_packing(golden_dir):
         assert False
     except ValueError:
         pass
+
+
+def test_scp_offset_reader_reads_segments(golden_dir, tmp_path):
+    """CompressedFeatureReader.read_segment = the reference's FeatureReader.read_segment (kaldi_io.py:112-149) minus the
+    dequantisation: 'utt path:offset' entries, file descriptors kept open, row ranges cut with the same seek pattern."""
+    from tf_kaldi_speaker_b200.dataset import kaldi_io as K
+    gd, ark, offs = _entries(golden_dir)
+    path = tmp_path / "feats.ark"
+    path.write_bytes(ark)
+    rd = K.CompressedFeatureReader()
+    try:
+        for key, (start, length) in (("spk1-utt1", (100, 200)), ("spk2-utt7", (3, 100)), ("oneframe", (0, 1))):
+            entry = "%s %s:%d" % (key, path, offs[key] - 2)          # scp offsets point at the '\0B' marker
+            raw = rd.read_segment(entry, length=length, start=start)
+            got = CM.decode(raw.globmin, raw.globrange, raw.headers, raw.data)
+            assert np.array_equal(got, gd["sub/%s/%d/%d" % (key, start, length)])
+            whole = rd.read_segment(entry)
+            assert whole.data.shape[1] == whole.rows and np.array_equal(
+                CM.decode(whole.globmin, whole.globrange, whole.headers, whole.data), gd["full/" + key])
+        assert len(rd.fd) == 1                                         # one descriptor for the archive, reused
+    finally:
+        rd.close()
+
+
+def test_column_sharded_varspec_slices_full_checkpoints():
+    """Class-sharded head variables: a full-shape checkpoint array is cut to the shard's columns on load, a shard-shaped
+    one is taken as is, and the padded internal layout round-trips (runtime.VarSpec)."""
+    from tf_kaldi_speaker_b200.runtime import VarSpec
+    full = np.arange(6 * 21, dtype=np.float32).reshape(6, 21)
+    spec = VarSpec("softmax/output/kernel", (6, 5), (6, 8), full_shape=(6, 21), col_range=(16, 21))
+    local = full[:, 16:21]
+    inner = spec.to_internal(local)
+    assert inner.shape == (6, 8) and np.array_equal(inner[:, :5], local) and not inner[:, 5:].any()
+    assert np.array_equal(spec.to_tf(inner), local)
+    assert spec.full_shape == (6, 21) and spec.col_range == (16, 21)
