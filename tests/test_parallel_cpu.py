@@ -92,3 +92,43 @@ def test_world2_gloo_allreduce_equals_global_batch():
     assert sorted(r[0] for r in res) == [0, 1]
     for r in res:
         assert r[1] and r[2] and r[3], r
+
+
+def _syncbn_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from tf_kaldi_speaker_b200 import parallel
+    parallel.init_from_env("gloo")
+    torch.manual_seed(1)
+    B, C = 5, 7
+    y_all = torch.randn(world * B, C, dtype=torch.float64)
+    y = y_all[rank * B:(rank + 1) * B].contiguous()
+    sync = parallel.SyncBN()
+    # frame-level rule: all-reduced (sum, sum of squares) with the global count == statistics of the concatenated batch
+    stats = torch.stack([y.sum(0), (y * y).sum(0)])
+    sync.all_reduce_sum_(stats)
+    n = world * B
+    mean, var = stats[0] / n, stats[1] / n - (stats[0] / n) ** 2
+    ok = torch.allclose(mean, y_all.mean(0)) and torch.allclose(var, y_all.var(0, unbiased=False))
+    # utterance-level rule: rows all-gathered, this rank's rows sit at [rank*B, (rank+1)*B)
+    rows = torch.empty(world * B, C, dtype=torch.float64)
+    sync.all_gather(rows, y)
+    ok = ok and torch.equal(rows, y_all) and sync.world == world and sync.rank == rank
+    # gradients that every rank already holds in full are pre-scaled by 1/N so that the final sum all-reduce restores them
+    g = torch.full((3,), 6.0, dtype=torch.float64) / world
+    sync.all_reduce_sum_(g)
+    ok = ok and torch.allclose(g, torch.full((3,), 6.0, dtype=torch.float64))
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_syncbn_exchanges():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, 29733, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] for r in res), res
