@@ -47,6 +47,8 @@ def ncu_traffic():
     p = os.path.join(ROOT, "profiles", "r01_gemm_ncu_traffic.json")
     if os.path.exists(p):
         j = json.load(open(p))
+        if "tdnn_dram_read_bytes" in j:      # the frame-level launches the roofline fraction is quoted on
+            return float(j["tdnn_dram_read_bytes"]) + float(j["tdnn_dram_write_bytes"]), int(j["tdnn_launches"])
         return float(j["dram_read_bytes"]) + float(j["dram_write_bytes"]), int(j["launches"])
     return None, None
 
@@ -368,8 +370,8 @@ def run_ours(args):
                                                           % (n_tdnn, 100.0 * tdnn_flops / max(gemm_flops, 1.0), n_gemm),
                              "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                              "frac": (achieved / sustained) if achieved else None, "traffic": ncu_traffic()[0],
-                             "traffic_note": "sum of dram__bytes_read + dram__bytes_write over the %s GEMM launches of one "
-                                             "step (profiles/r01_gemm_ncu_full.md); outputs mostly stay in the 126 MB L2"
+                             "traffic_note": "sum of dram__bytes_read + dram__bytes_write over the %s frame-level GEMM launches "
+                                             "of one step (profiles/r01_gemm_ncu_full.md); outputs mostly stay in the 126 MB L2"
                                              % ncu_traffic()[1],
                              "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % (how, burst),
                              "tdnn_gemm_ms_per_step": tdnn_ms / reps_used, "tdnn_gemm_flops_per_step": tdnn_flops / reps_used,
