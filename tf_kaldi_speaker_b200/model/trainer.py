@@ -51,6 +51,8 @@ class Trainer(object):
         self.train_ops = {}
         self.valid_ops = {}
         self._static = {}
+        self._copy_stream = None
+        self._h2d_event = None
         self.use_cuda_graph = bool(params.dict.get("cuda_graph", True))
 
     # ------------------------------------------------------------------ network (trainer.py:168-188)
@@ -139,6 +141,8 @@ class Trainer(object):
         eng = self.engine
         eng.begin_step(True)
         eng.prefetch_head_weights("softmax/output/kernel", normalize=(self.loss_type != "softmax"))
+        if self._h2d_event is not None:
+            self._h2d_event.wait(torch.cuda.current_stream())     # this step's batch has arrived (see _static_batch)
         out, endpoints = self.entire_network(features, self.params, True, True)
         loss, endpoints_loss = self.loss_network(out, labels, self.num_speakers, self.params, True, True)
         endpoints.update(endpoints_loss)
@@ -167,15 +171,28 @@ class Trainer(object):
             self._static[key] = st
         if not torch.is_tensor(labels):
             labels = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
-        if hasattr(features, "decode_into"):
-            # dataset.feeder.CompressedSegmentBatch: H2D of the raw uint8 crops + on-device dequantise / transpose
-            features.decode_into(st["x"])
-            self.engine.launches += 1
-        else:
-            if not torch.is_tensor(features):
-                features = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
-            st["x"].copy_(features, non_blocking=True)       # H2D (or D2D) of this step's batch
-        st["y"].copy_(labels.to(torch.int32), non_blocking=True)
+        if not hasattr(features, "decode_into") and not torch.is_tensor(features):
+            features = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+        from_host = hasattr(features, "decode_into") or not features.is_cuda
+        main = torch.cuda.current_stream()
+        if self._h2d_event is None:
+            self._copy_stream = torch.cuda.Stream(device=self.engine.device)
+            self._h2d_event = torch.cuda.Event(enable_timing=False, external=True)
+        # Host batches are uploaded on a copy stream: the step waits for them only in front of the first kernel that reads
+        # the features (an external event-wait node inside the captured graph, see _fwd_bwd), so the gradient-buffer fill,
+        # the scalar feed and the head weight preparation at the start of the step overlap the PCIe transfer.
+        cs = self._copy_stream if from_host else main
+        if from_host:
+            cs.wait_stream(main)            # the previous step has finished reading the static buffers
+        with torch.cuda.stream(cs):
+            if hasattr(features, "decode_into"):
+                # dataset.feeder.CompressedSegmentBatch: H2D of the raw uint8 crops + on-device dequantise / transpose
+                features.decode_into(st["x"])
+                self.engine.launches += 1
+            else:
+                st["x"].copy_(features, non_blocking=True)       # H2D (or D2D) of this step's batch
+            st["y"].copy_(labels.to(torch.int32), non_blocking=True)
+            self._h2d_event.record(cs)
         return st
 
     def train_step(self, features, labels, learning_rate, global_step=None, fetch_loss=False):
