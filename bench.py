@@ -167,6 +167,8 @@ def run_ours(args):
     from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
     from tf_kaldi_speaker_b200.model.trainer import Trainer
 
+    # stdout carries exactly ONE line (the JSON): NCCL's own banner / debug output ("NCCL version ...") goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.dp_overlap:
         os.environ.setdefault("NCCL_MAX_CTAS", str(args.overlap_sms))     # NCCL stays inside the SMs the GEMMs leave free
     rank, world = parallel.init_from_env("nccl")
