@@ -487,6 +487,14 @@ class Trainer(object):
                     vals[name] = full.reshape(spec.full_shape).cpu().numpy()
             if sh.rank != 0:
                 return
+        if str(self.params.dict.get("checkpoint_format", "npz")) == "tf":
+            # TF tensor-bundle files under the reference's names (model-<step>.index / .data-00000-of-00001)
+            from ..misc.tf_checkpoint import write_tf_checkpoint
+            vals["global_step"] = np.array(step, dtype=np.int64)
+            write_tf_checkpoint(os.path.join(self.model, "model-%d" % step), vals)
+            with open(os.path.join(self.model, "checkpoint"), "w") as f:
+                f.write('model_checkpoint_path: "model-%d"\n' % step)
+            return
         path = os.path.join(self.model, "model-%d.npz" % step)
         extra = {}
         if st.state1 is not None:
@@ -508,8 +516,17 @@ class Trainer(object):
             sys.exit("Cannot find model in %s" % self.model)
         name = re.search(r'"(.*)"', open(ck).readline()).group(1)
         step = int(next(re.finditer(r"(\d+)(?!.*\d)", name)).group(0))      # trainer.py:149-153
-        z = np.load(os.path.join(self.model, name + ".npz"))
         st = self.engine.store
+        base = os.path.join(self.model, os.path.basename(name))
+        if not os.path.exists(base + ".npz") and os.path.exists(base + ".index"):
+            # a checkpoint written by tf.train.Saver (the reference's own format, trainer.py:160-166): variables are
+            # matched by their TF names; optimizer slots and global_step are ignored
+            from ..misc.tf_checkpoint import read_tf_checkpoint
+            st.load_tf(read_tf_checkpoint(base))
+            self.global_step = step
+            self.is_loaded = True
+            return step
+        z = np.load(base + ".npz")
         st.load_tf({k: z[k] for k in z.files if not k.startswith("__")})
         if "__opt_state1" in z.files:
             st.ensure_opt_state(L.OPT_MOMENTUM)
