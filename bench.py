@@ -42,9 +42,30 @@ def flops_train(t, d, c):
     return 3 * flops_fwd(t, d, c) - 2 * 512 * 5 * d * (t - 4)
 
 
+def flops_frame_train(t, d):
+    """ALGORITHMIC FLOPs per segment of the 14 frame-level GEMM launches (fwd + dgrad + wgrad of tdnn1-5, no input
+    gradient for tdnn1): valid rows T-4 / T-8 / T-14 only, K = 5*D for tdnn1, N = 1500 for tdnn5 -- the
+    executed launches also multiply the 7 % invalid rows and the channel padding (K = 192, N = 1536)."""
+    fwd = 2 * 512 * (5 * d * (t - 4) + 2560 * (t - 8) + (3584 + 512 + 1500) * (t - 14))
+    return 3 * fwd - 2 * 512 * 5 * d * (t - 4)
+
+
+def ncu_pipe():
+    """Tensor-pipe activity per launch group from the committed `ncu --set full` capture of the step's GEMM launches."""
+    for name in ("r02_gemm_ncu_pipe.json", "r01_gemm_ncu_pipe.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            j = json.load(open(p))
+            j["source"] = "profiles/" + name
+            return j
+    return None
+
+
 def ncu_traffic():
     """DRAM bytes (read + write) of the GEMM launches of one step from the committed `ncu --set full` capture."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_ncu_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_gemm_ncu_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_gemm_ncu_traffic.json")
     if os.path.exists(p):
         j = json.load(open(p))
         if "tdnn_dram_read_bytes" in j:      # the frame-level launches the roofline fraction is quoted on
@@ -145,7 +166,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 32
+    sample = B_PER_GPU          # the same 128-segment step as our arm (0.5-1 s per step on the box's host cores)
     steps = max(1, min(args.steps, 20))
     val, ms, cores = cpu_reference_arm(steps, max(1, min(args.warmup, 2)), sample)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "segments/s", "n_gpus": args.gpus,
@@ -153,8 +174,9 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B_PER_GPU, "frames": T, "feat_dim": D, "speakers": C},
             "cpu_baseline": {"value": val, "unit": "segments/s", "cores": cores, "kind": "port",
-                             "sample": "%d-segment batches of the same T=200/D=30/C=7200 step, fp32 PyTorch-CPU "
-                                       "restatement of the reference (TF1 not installable)" % sample},
+                             "sample": "%d steps (warm-up %d; capped at 20 / 2 to stay within minutes) of the full "
+                                       "%d-segment T=200/D=30/C=7200 step, fp32 PyTorch-CPU restatement of the "
+                                       "reference (TF1 not installable)" % (steps, max(1, min(args.warmup, 2)), sample)},
             "e2e": {"value": val, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -344,8 +366,14 @@ def run_ours(args):
         seg_s = world * B_PER_GPU * args.steps / (ms * 1e-3)
         seg_s_e2e = world * B_PER_GPU * args.steps / (ms_e2e * 1e-3)
         ftrain = flops_train(T, D, C)
-        achieved_all = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        achieved = tdnn_flops / (tdnn_ms * 1e-3) / 1e12 if tdnn_ms > 0 else None
+        # ALGORITHMIC FLOPs (valid rows, K = 5*D, N = 1500) over the measured kernel time; the FLOPs the launches
+        # actually execute (invalid rows, channel padding: +7 %) are reported beside them as *_executed
+        alg_frame = flops_frame_train(T, D) * B_PER_GPU
+        alg_all = ftrain * B_PER_GPU
+        exec_all = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        exec_frame = tdnn_flops / (tdnn_ms * 1e-3) / 1e12 if tdnn_ms > 0 else None
+        achieved = alg_frame * reps_used / (tdnn_ms * 1e-3) / 1e12 if tdnn_ms > 0 else None
+        achieved_all = alg_all * reps_used / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         n_tdnn = sum(v[2] for k, v in per_shape.items() if k in tdnn_shapes) // max(reps_used, 1)
         line = {"metric": METRIC, "value": seg_s, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -377,16 +405,24 @@ def run_ours(args):
                                              % ncu_traffic()[1],
                              "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % (how, burst),
                              "tdnn_gemm_ms_per_step": tdnn_ms / reps_used, "tdnn_gemm_flops_per_step": tdnn_flops / reps_used,
+                             "flops_basis": "algorithmic (SURVEY 8d: valid rows T-4/T-8/T-14, K = 5*D, N = 1500): %.1f GF per "
+                                            "step for the frame-level launches, %.1f GF for the whole step; *_executed "
+                                            "counts 2*M*N*K of the launches as issued (invalid rows + channel padding)"
+                                            % (alg_frame / 1e9, alg_all / 1e9),
+                             "achieved_executed": exec_frame,
+                             "frac_executed": (exec_frame / sustained) if exec_frame else None,
                              "all_gemm_achieved": achieved_all,
                              "all_gemm_frac": (achieved_all / sustained) if achieved_all else None,
+                             "all_gemm_achieved_executed": exec_all,
+                             "ncu_tensor_pipe": ncu_pipe(),
                              "gemm_ms_per_step": gemm_ms / reps_used, "gemm_flops_per_step": gemm_flops / reps_used,
                              "method": method,
                              "step_frac": seg_s * ftrain / (world * sustained * 1e12),
                              "algorithmic_flops_per_segment": ftrain}}
         if world == 1 and not args.no_cpu_baseline:
-            val, msc, cores = cpu_reference_arm(3, 1, 32)
+            val, msc, cores = cpu_reference_arm(8, 1, B_PER_GPU)
             line["cpu_baseline"] = {"value": val, "unit": "segments/s", "cores": cores, "kind": "port",
-                                    "sample": "3 steps of 32-segment batches (same T=200/D=30/C=7200 step), fp32 "
+                                    "sample": "8 steps (1 warm-up) of the full 128-segment T=200/D=30/C=7200 step, fp32 "
                                               "PyTorch-CPU restatement of the reference; TF1 not installable"}
         print(json.dumps(line), flush=True)
     if world > 1:

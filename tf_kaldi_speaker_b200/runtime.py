@@ -181,12 +181,23 @@ class ParamStore(object):
             self.view(name).copy_(torch.from_numpy(s.to_internal(arr)).to(self.device))
         self.refresh_shadows()
 
-    def export_tf(self, grads=False):
+    def export_tf(self, grads=False, which=None):
+        """name -> array in TF shape.  ``which``: "params" (default), "grads", "state1" / "state2" (optimizer slots:
+        Momentum accumulator / Adam m, Adam v; trainable variables only)."""
+        which = which or ("grads" if grads else "params")
         out = OrderedDict()
         for name, s in self.specs.items():
-            if grads and not s.trainable:
+            if which != "params" and not s.trainable:
                 continue
-            t = self.grad(name) if grads else self.view(name)
+            if which == "params":
+                t = self.view(name)
+            elif which == "grads":
+                t = self.grad(name)
+            else:
+                flat = getattr(self, which)
+                if flat is None:
+                    return out
+                t = flat[s.offset:s.offset + s.numel].view(*s.ishape)
             out[name] = s.to_tf(t.detach().cpu().numpy())
         return out
 
