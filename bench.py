@@ -191,8 +191,6 @@ def run_ours(args):
 
     # stdout carries exactly ONE line (the JSON): NCCL's own banner / debug output ("NCCL version ...") goes to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    if args.dp_overlap:
-        os.environ.setdefault("NCCL_MAX_CTAS", str(args.overlap_sms))     # NCCL stays inside the SMs the GEMMs leave free
     rank, world = parallel.init_from_env("nccl")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -201,13 +199,8 @@ def run_ours(args):
     pd = dict(PD)
     shard = bool(args.head_shard) and world > 1
     pd["head_class_shard"] = shard
-    pd["dp_overlap"] = bool(args.dp_overlap) and world > 1 and not shard
-    pd["dp_overlap_reserve_sms"] = int(args.overlap_sms)
     pd["dp_grad_dtype"] = args.grad_dtype
     pd["dp_allreduce"] = args.allreduce
-    pd["dp_bucket_overlap"] = bool(args.bucket_overlap)
-    pd["dp_bucket_overlap_sms"] = int(args.overlap_sms)
-    pd["dp_bucket_overlap_gemms"] = int(args.overlap_gemms)
     tr = Trainer(ParamsPlain(**pd), "/tmp/xv_bench_model_%d" % rank)
     tr.build("train", D, LOSS, C)
     if world > 1:
@@ -382,12 +375,8 @@ def run_ours(args):
                            "speakers": C, "parallelism": ("dp%d (batch-sharded replicas, per-replica BN, class-sharded head: "
                                             "row all-gather + (max,sum) exchange + dx reduce-scatter, trunk-only NCCL "
                                             "all-reduce)" % world) if shard else
-                                           ("dp%d (batch-sharded replicas, per-replica BN, %s)"
-                                            % (world, "two-bucket NCCL all-reduce, head bucket overlapped with the frame-level "
-                                                      "backward" if pd["dp_overlap"] else
-                                               ("%s in %s via %s" % ("two buckets, [tdnn6..head] exchanged beside the tdnn5 backward," if args.bucket_overlap
-                                                                 else "one flat all-reduce", args.grad_dtype,
-                                                                 tr.dp.allreduce_impl if tr.dp else "-")))),
+                                           ("dp%d (batch-sharded replicas, per-replica BN, one flat all-reduce of gradients + loss "
+                                            "scalars in %s via %s)" % (world, args.grad_dtype, tr.dp.allreduce_impl if tr.dp else "-")),
                            "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2 (no flush needed)"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": seg_s_e2e, "unit": "segments/s",
@@ -440,14 +429,8 @@ def main():
     ap.add_argument("--head-shard", action="store_true", help="N>1: split the speaker matrix by columns over the ranks")
     ap.add_argument("--allreduce", default="auto", choices=["nccl", "symm", "multimem", "auto"],
                     help="N>1: gradient all-reduce through NCCL or through symmetric-memory multimem / two-shot kernels")
-    ap.add_argument("--bucket-overlap", action="store_true",
-                    help="N>1, in-graph exchange: exchange the [tdnn6 .. head] bucket beside the tdnn5 backward")
-    ap.add_argument("--overlap-gemms", type=int, default=2, help="GEMM launches whose grid is capped during the overlap")
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"],
                     help="N>1: dtype of the gradient all-reduce (bf16 halves the NVLink bytes; opt-in)")
-    ap.add_argument("--dp-overlap", action="store_true",
-                    help="N>1: all-reduce the [tdnn6 .. head] gradient bucket while the frame-level backward runs")
-    ap.add_argument("--overlap-sms", type=int, default=16, help="SMs left to NCCL during the overlap (GEMM grid cap)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

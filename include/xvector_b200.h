@@ -69,7 +69,7 @@ typedef struct {
 } xv_operand;
 
 typedef enum {
-  XV_EPI_BF16 = 0,      /* out bf16 [M, ldc] = acc (+ bias[n]); optional per-column sum / sum-of-squares   */
+  XV_EPI_BF16 = 0,      /* out bf16 [M, ldc] = acc (+ bias[n]); optional per-column sum / sum-of-squares of out */
   XV_EPI_F32 = 1,       /* out f32  [M, ldc] = acc (+ bias[n]); splits > 1 => atomic accumulate into out  */
   XV_EPI_HEAD_FWD = 2,  /* fused margin-softmax forward: online log-sum-exp partials, logits never stored  */
   XV_EPI_HEAD_BWD = 3   /* fused margin-softmax backward: recompute logits tile, emit dLoss/dlogit as bf16 */
@@ -90,8 +90,8 @@ typedef struct {
   const int32_t* labels; /* [M]                                                                     */
   const float* xnorm;    /* [M] max(||x_i||, 1e-12)                                                 */
   /* forward outputs */
-  float* part_max;       /* [2*ceil(N/256), M]: online-LSE running max per 128-column half tile      */
-  float* part_sum;       /* [2*ceil(N/256), M]: matching sum of exp(z - part_max)                   */
+  float* part_max;       /* [2*ceil(N/128), M]: online-LSE running max per 64-column half tile       */
+  float* part_sum;       /* [2*ceil(N/128), M]: matching sum of exp(z - part_max)                   */
   float* target_logit;   /* [M] modified target logit z'_{i,y_i}                                    */
   float* logits_out;     /* optional [M, ldc] f32 pre-margin logits (endpoints["logits"]); may be 0 */
   /* backward inputs / outputs */
@@ -127,8 +127,8 @@ typedef struct {
   void* out;
   int64_t ldc;
   const float* bias;     /* optional [N]                                                            */
-  float* col_sum;        /* optional [N]: += sum over valid rows of acc (bias excluded)             */
-  float* col_sumsq;      /* optional [N]: += sum over valid rows of acc^2                           */
+  float* col_sum;        /* optional [N]: += sum over valid rows of the STORED bf16 output           */
+  float* col_sumsq;      /* optional [N]: += sum over valid rows of its square (needs a TMA-storable out, even N) */
   xv_head_args head;
   xv_bn_bwd_args bn_bwd; /* XV_EPI_BF16 only; needs col_sum (-> dbeta) and col_sumsq (-> dgamma), N % 32 == 0 */
 } xv_gemm_args;
@@ -151,7 +151,9 @@ typedef enum { XV_ACT_NONE = 0, XV_ACT_RELU = 1, XV_ACT_LRELU = 2, XV_ACT_PRELU 
 XV_API int xv_pack_input(const float* x, void* out, int B, int T, int D, int k, int dpad, int64_t ldo, void* stream);
 
 /* tf.layers.batch_normalization (model/tdnn.py:46,64,82,102,121), training mode: per-channel sums produced
- * by the GEMM epilogue -> scale/shift (+ saved mean/rstd for backward, + moving-stat update, eps 1e-3). */
+ * by the GEMM epilogue -> scale/shift (+ saved mean/rstd for backward, + moving-stat update, eps 1e-3).
+ * The sums are those of the STORED pre-BN tensor, which carries no layer bias: scale / shift / save_mean refer to that
+ * tensor; `bias` (optional) only enters the moving mean (the statistic of the reference's biased tensor). */
 XV_API int xv_bn_finalize_train(const float* col_sum, const float* col_sumsq, const float* bias, float count,
                                 const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                                 float momentum, float eps, int unbiased_moving_var, float* scale, float* shift,
@@ -167,9 +169,12 @@ XV_API int xv_bn_train_apply(const void* y, void* a, const float* col_sum, const
  * statistics of tf.layers.batch_normalization for layers whose GEMM is too short to hide a reduction epilogue. */
 XV_API int xv_col_stats(const void* y, const float* bias, int64_t rows, int C, int64_t ld, int seg_len, int seg_valid,
                         const int32_t* lengths, float* col_sum, float* col_sumsq, void* stream);
-/* ... inference mode (is_training=False, model/trainer.py:210-225): scale/shift from the moving statistics. */
+/* ... inference mode (is_training=False, model/trainer.py:210-225): scale/shift from the moving statistics.
+ * bias (optional): the layer bias; frame-level pre-BN tensors are stored bias-free (the bias cancels in training-mode
+ * BN), so shift = beta - (moving_mean - bias) * scale. */
 XV_API int xv_bn_finalize_infer(const float* gamma, const float* beta, const float* moving_mean,
-                                const float* moving_var, float eps, float* scale, float* shift, int C, void* stream);
+                                const float* moving_var, const float* bias, float eps, float* scale, float* shift, int C,
+                                void* stream);
 /* a = act(y*scale + shift) on valid rows, 0 on invalid rows  (BN apply + relu, tdnn.py:46-52 etc.). */
 XV_API int xv_bn_act_apply(const void* y, void* a, const float* scale, const float* shift, const float* alpha, int act,
                            int64_t rows, int C, int64_t ld, int seg_len, int seg_valid, const int32_t* lengths,
@@ -275,6 +280,20 @@ XV_API int xv_head_combine(const float* part_max, const float* part_sum, const f
 XV_API int xv_head_finish_dx(const float* dx_gemm, const float* gnorm, const float* x, const float* xnorm, const float* u,
                              const float* u_rinv, float scaling, float* du, int B, int E, void* stream);
 XV_API int xv_head_finish_dw(float* dw, const float* w, const float* inv_norm, int E, int C, void* stream);
+/* Auxiliary losses of the heads (model/loss.py:985-1037, aux_loss_func).
+ * Ring loss  lambda * mean_i (||x_i|| - r)^2 on the head's input features (xnorm from xv_head_prep_features, r = the
+ * trainable scalar softmax_ringloss/r); scale = lambda / global batch.  loss (optional) += scale * sum_i (n_i - r)^2;
+ * gnorm (optional) [B] += 2 scale (n_i - r) -- the dLoss/d||x_i|| input of xv_head_finish_dx -- and dr += -2 scale sum_i (n_i - r). */
+XV_API int xv_ring_loss(const float* xnorm, const float* r, int B, float scale, float* loss, float* gnorm, float* dr,
+                        void* stream);
+/* MHE  lambda / (mean_{i,j} (2 - 2 <wn_{y_i}, wn_j>) + 1e-6), wn = column-normalised speaker matrix (w f32 [E, ldw],
+ * inv_norm [C] from xv_head_prep_weights).  forward: t[E] = sum_j wn_j, S[E] = sum_i wn_{y_i}, hist[C] (zero on entry) =
+ * label histogram, loss += scale * L, kappa[0] = scale * dL/d<S,t>-coefficient;  backward: dWn[e,j] += kappa (hist_j t_e + S_e)
+ * on the un-projected gradient buffer, before xv_head_finish_dw. */
+XV_API int xv_mhe_forward(const float* w, const float* inv_norm, const int32_t* labels, int B, int E, int C, int64_t ldw,
+                          float lambda, float scale, float* t, float* S, float* hist, float* kappa, float* loss, void* stream);
+XV_API int xv_mhe_backward(float* dwn, const float* t, const float* S, const float* hist, const float* kappa, int E, int C,
+                           int64_t ldw, void* stream);
 /* Class-sharded head (north_star "Data parallelism": the speaker matrix split by columns over the ranks; the reference
  * has no multi-device path, README.md:1,82,115).  Each rank runs the XV_EPI_HEAD_* epilogues on its own columns for
  * the all-gathered rows:

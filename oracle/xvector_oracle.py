@@ -11,6 +11,7 @@ the arithmetic of these reference files (paths relative to /root/reference):
   model/pooling.py:78-189            self_attention (multi-head attentive statistics + penalty)
   model/common.py:27-58,113-265      prelu, l2_scaling, dense_* helpers, split_heads
   model/loss.py:29-35,97-159,207-247,293-345   softmax / asoftmax / AM / AAM heads
+  model/loss.py:985-1037             auxiliary ring loss / MHE (pinned: model/test_utils.py:855-884, tests/golden/aux.npz)
   model/trainer.py:168-188           entire_network (feature_norm -> l2_scaling)
   model/trainer.py:261-303           validation-time margin neutralisation
   model/trainer.py:328-358,403-436   optimizer, total loss, gradient clipping, BN update deps
@@ -169,6 +170,8 @@ def init_params(dim, params, num_speakers=None, loss_type=None, seed=0, dtype=to
         P["softmax/output/kernel"] = _glorot_uniform((e, num_speakers), gen)
         if loss_type == "softmax":
             P["softmax/output/bias"] = torch.zeros(num_speakers, dtype=torch.float64)
+        if "ring_loss" in params.dict.get("aux_loss_func", []):
+            P["softmax_ringloss/r"] = torch.tensor(float(params.ring_loss_init), dtype=torch.float64)   # loss.py:1008-1011
     return OrderedDict((k, v.to(dtype)) for k, v in P.items())
 
 
@@ -346,7 +349,7 @@ def tdnn(features, P, params, is_training=False, updates=None, lengths=None, mir
         x = batch_norm(x, P, "tdnn/%s_bn" % name, mom, is_training, updates,
                        unbiased_moving_var=(mirror_tf_fused_bn and kind == "conv"),
                        store=bf16_ste if emulate_bf16 else None,
-                       stats_from_stored=False)   # every layer: statistics from the fp32 accumulators (GEMM epilogue)
+                       stats_from_stored=True)    # the GEMM epilogue takes the statistics of the stored bf16 tensor
         ep["%s_bn" % name] = x
         x = _activation(x, P, "tdnn/%s_relu" % name, relu_type)
         if not (name == "tdnn5" and params.pooling_type == "statistics_pooling"):
@@ -490,12 +493,36 @@ HEADS = {
 }
 
 
+def aux_loss(x, labels, P, params):
+    """model/loss.py:985-1037: ring loss (trainable radius ``softmax_ringloss/r``) and minimum hyperspherical energy of the
+    normalised speaker matrix; pinned against model/test_utils.py:855-884 (tests/golden/aux.npz)."""
+    total = 0.0
+    for name in params.aux_loss_func:
+        if name == "ring_loss":
+            r = P["softmax_ringloss/r"]
+            total = total + float(params.ring_loss_lambda) * ((torch.linalg.norm(x, dim=1) - r) ** 2).mean()
+        elif name == "mhe_loss":
+            w = P["softmax/output/kernel"]
+            wn = w * torch.rsqrt(torch.clamp((w ** 2).sum(0, keepdim=True), min=1e-12))
+            sel = wn.t()[labels.long()]
+            total = total + float(params.mhe_lambda) * (1.0 / ((2.0 - 2.0 * (sel @ wn)).mean() + 1e-6))
+        else:
+            raise NotImplementedError("Unsupported loss function %s" % name)
+    return total
+
+
 def loss_network(loss_type, x, labels, P, params, global_step=None):
     if loss_type not in HEADS:
         raise NotImplementedError("Not implement %s loss" % loss_type)
     if loss_type == "softmax":
-        return softmax_head(x, labels, P, params)
-    return HEADS[loss_type](x, labels, P, params, global_step)
+        loss, logits = softmax_head(x, labels, P, params)
+    else:
+        loss, logits = HEADS[loss_type](x, labels, P, params, global_step)
+        if loss_type == "asoftmax" and int(params.asoftmax_m) == 1:
+            return loss, logits          # loss.py:110-115 returns before the auxiliary losses
+    if "aux_loss_func" in params.dict and len(params.dict["aux_loss_func"]) > 0:
+        loss = loss + aux_loss(x, labels, P, params)
+    return loss, logits
 
 
 # --------------------------------------------------------------------------------------
@@ -584,6 +611,8 @@ def valid_params(params, loss_type):
         vp.amsoftmax_m = 0
     elif loss_type == "additive_angular_margin_softmax":
         vp.arcsoftmax_m = 0
+    if "aux_loss_func" in vp.dict:
+        vp.aux_loss_func = []          # trainer.py:279-282
     return vp
 
 

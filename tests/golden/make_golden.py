@@ -5,8 +5,9 @@ known-answer functions (run in the build container, where /root/reference exists
   heads.npz      model/test_utils.py:157-318 (compute_asoftmax / compute_amsoftmax / compute_arcsoftmax)
                  on the adversarial rows of model/tdnn.py:271-277 (theta~0, theta~pi, tiny norm, x10 norm),
                  m grids and feature_norm on/off as in model/tdnn.py:254-343.
-  statpool.npz   the inline NumPy check of model/multitask_v1/pooling.py:68-83 (restated verbatim in
-                 spirit: E[x^2]-mean^2 with a 1e-12 floor; the original lives under ``__main__``).
+  statpool.npz   the inline NumPy check ``compute_stat_pooling`` of model/multitask_v1/pooling.py:68-80, exec'd from the
+                 reference source text (it lives under ``__main__``).
+  aux.npz        model/test_utils.py:855-884 compute_ring_loss / compute_mhe (auxiliary losses of model/loss.py:985-1037).
   attention.npz  model/test_utils.py:321-376 compute_self_attention, exec'd from the reference source with
                  the two py2 integer divisions (``value_dim/n_heads``, ``key_dim/n_heads``) turned into ``//``.
 
@@ -86,24 +87,45 @@ def make_heads(tu):
 
 
 def make_statpool():
-    # model/multitask_v1/pooling.py:68-83 (inline compute_stat_pooling), row 0 all zeros as at :63
+    # model/multitask_v1/pooling.py:68-80: the inline ``compute_stat_pooling`` of the reference's self-test, exec'd from
+    # the reference SOURCE TEXT (it lives under ``__main__`` next to TensorFlow calls, so it cannot be imported);
+    # inputs as at :62-64 (uniform features, row 0 all zeros, random lengths).
+    src = open(os.path.join(REF, "model", "multitask_v1", "pooling.py")).read()
+    m = re.search(r"^( *)def compute_stat_pooling\(features, length\):\n(?:\1 +.*\n|\s*\n)+", src, re.M)
+    indent = len(m.group(1))
+    body = "\n".join(line[indent:] for line in m.group(0).splitlines())
+    ns = {"np": np, "range": range}
+    exec(body, ns)
+    fn = ns["compute_stat_pooling"]
     rng = np.random.RandomState(20241)
     n, l, d = 12, 96, 40
     x = rng.rand(n, l, d).astype(np.float32)
     x[0] = 0
     length = rng.randint(10, l + 1, size=(n,)).astype(np.int32)
-    mean = np.zeros((n, d))
-    std = np.zeros((n, d))
-    for i in range(n):
-        for j in range(length[i]):
-            mean[i] += x[i, j]
-            std[i] += np.square(x[i, j].astype(np.float64))
-        mean[i] /= length[i]
-        std[i] /= length[i]
-        std[i] = np.sqrt(np.maximum(std[i] - np.square(mean[i]), 1e-12))
-    np.savez_compressed(os.path.join(HERE, "statpool.npz"), x=x, length=length,
-                        out=np.concatenate([mean, std], axis=1))
-    print("statpool.npz")
+    np.savez_compressed(os.path.join(HERE, "statpool.npz"), x=x, length=length, out=fn(x, length))
+    print("statpool.npz (reference text exec'd: %d lines)" % len(body.splitlines()))
+
+
+def make_aux(tu):
+    # model/test_utils.py:855-884 compute_ring_loss / compute_mhe, the known answers of model/loss.py:1054-1087
+    rng = np.random.RandomState(20243)
+    n, d, c = 64, 128, 37
+    labels = rng.randint(0, c, size=(n,)).astype(np.int32)
+    w = xavier(rng, d, c)
+    emb = (rng.randn(n, d) * (0.5 + rng.rand(n, 1) * 3)).astype(np.float32)
+    p = ParamsPlain()
+    out = {"labels": labels, "w": w, "emb": emb}
+    ring, mhe = [], []
+    for r, lam in ((0.1, 0.01), (20.0, 0.01), (5.0, 1.0)):
+        p.dict["ring_loss_lambda"] = lam
+        ring.append((r, lam, float(tu.compute_ring_loss(emb.astype(np.float64), p, r))))
+    for lam in (0.01, 0.1, 1.0):
+        p.dict["mhe_lambda"] = lam
+        mhe.append((lam, float(tu.compute_mhe(labels, p, w.astype(np.float64).copy()))))
+    out["ring_cases"] = np.array(ring, dtype=np.float64)
+    out["mhe_cases"] = np.array(mhe, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "aux.npz"), **out)
+    print("aux.npz: %d ring + %d mhe cases" % (len(ring), len(mhe)))
 
 
 def make_attention(tu):
@@ -142,3 +164,4 @@ if __name__ == "__main__":
     make_heads(tu)
     make_statpool()
     make_attention(tu)
+    make_aux(tu)

@@ -76,3 +76,19 @@ def test_self_attention(golden_dir):
         assert np.allclose(att.numpy()[:, :dv], g[tag + "/att"][:, :dv], rtol=1e-6, atol=1e-9)
         assert np.allclose(att.numpy()[:, dv:], g[tag + "/att"][:, dv:], rtol=1e-3, atol=2e-6)
         assert np.allclose(pen.item(), float(g[tag + "/penalty"]), rtol=1e-8)
+
+
+def test_aux_losses_match_reference_numpy(golden_dir):
+    """Ring loss and MHE (model/loss.py:985-1037) against model/test_utils.py:855-884 (compute_ring_loss, compute_mhe)."""
+    g = np.load(os.path.join(golden_dir, "aux.npz"))
+    labels = torch.from_numpy(g["labels"].astype(np.int64))
+    x = torch.from_numpy(g["emb"].astype(np.float64))
+    P = {"softmax/output/kernel": torch.from_numpy(g["w"].astype(np.float64))}
+    for r, lam, want in g["ring_cases"]:
+        P["softmax_ringloss/r"] = torch.tensor(float(r), dtype=torch.float64)
+        p = O.ParamsPlain(aux_loss_func=["ring_loss"], ring_loss_lambda=float(lam))
+        assert np.allclose(float(O.aux_loss(x, labels, P, p)), want, rtol=1e-9)
+    for lam, want in g["mhe_cases"]:
+        p = O.ParamsPlain(aux_loss_func=["mhe_loss"], mhe_lambda=float(lam))
+        # the NumPy known answer omits the 1e-6 the TF graph adds to the mean (test_utils.py:884 vs loss.py:1029)
+        assert np.allclose(float(O.aux_loss(x, labels, P, p)), want, rtol=1e-5)

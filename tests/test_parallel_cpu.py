@@ -43,8 +43,8 @@ def _worker(rank, world, port, out):
     params = torch.full((4,), float(rank))
     comm.broadcast_(params, src=0)
     ok_bcast = bool((params == 0).all())
-    # the two-bucket overlapped exchange of DataParallel on a stand-in parameter store: [tdnn6 .. head] first (async),
-    # then [tdnn1 .. pooling]; together they must equal one all-reduce of the flat buffer
+    # DataParallel on a stand-in parameter store: ONE exchange covers the flat gradient buffer AND the step's loss scalars
+    # (the first 32 floats of the zero arena behind it), so the logged loss needs no second collective
     class _Spec(object):
         def __init__(self, offset):
             self.offset = offset
@@ -52,15 +52,26 @@ def _worker(rank, world, port, out):
     class _Store(object):
         def __init__(self):
             self.specs = {"tdnn/tdnn1_conv/kernel": _Spec(0), "tdnn/tdnn6_dense/kernel": _Spec(2048)}
-            self.params = torch.zeros(4096)
+            self.n = 4096
+            self.params = torch.zeros(self.n)
             self.buffers = torch.zeros(32)
-            self.grads = torch.arange(4096, dtype=torch.float32) * (rank + 1)
+            self.grads_ext = torch.cat([torch.arange(self.n, dtype=torch.float32) * (rank + 1), torch.zeros(64)])
+            self.grads = self.grads_ext[:self.n]
+            self.arena = self.grads_ext[self.n:]
+            self.arena_used = 0
 
         def refresh_shadows(self):
             pass
 
     class _Eng(object):
-        pass
+        _scalars = None
+
+        @property
+        def scalars(self):
+            if self._scalars is None:
+                self._scalars = self.store.arena[:8]
+                self.store.arena_used = 32
+            return self._scalars
 
     class _Trainer(object):
         pass
@@ -69,12 +80,12 @@ def _worker(rank, world, port, out):
     tr.engine.store = _Store()
     tr.engine.device = "cpu"
     dp = parallel.DataParallel(tr, local_batch=4)
-    ok_dp = dp.split == 2048 and abs(tr.engine.inv_global_batch - 1.0 / (world * 4)) < 1e-12
-    dp.allreduce_bucket_async("head")
-    dp.allreduce_bucket_async("trunk")
-    dp.wait_all()
+    ok_dp = dp.scalars_reduced and dp.reduce_numel == 4096 + 32 and abs(tr.engine.inv_global_batch - 1.0 / (world * 4)) < 1e-12
+    tr.engine.scalars[0] = float(rank + 1)           # this rank's share of the global-batch mean loss
+    dp.allreduce_gradients()
     expect = torch.arange(4096, dtype=torch.float32) * sum(r + 1 for r in range(world))
     ok_dp = ok_dp and torch.equal(tr.engine.store.grads, expect)
+    ok_dp = ok_dp and float(tr.engine.scalars[0]) == float(sum(r + 1 for r in range(world)))
     out.put((rank, ok_grad, ok_loss, ok_bcast and ok_dp))
     dist.destroy_process_group()
 

@@ -83,12 +83,12 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
     if (op->mn_major && op->div && (op->div % 64)) return set_error(XV_ERR_INVALID, "MN-major tap div must be a multiple of 64");
   }
   if (a->a.mn_major && a->a.div && (a->a.div % BLOCK_M)) return set_error(XV_ERR_INVALID, "MN-major A tap div must be a multiple of 128");
-  if (a->b.mn_major && a->b.div && (a->b.div % BLOCK_N)) return set_error(XV_ERR_INVALID, "MN-major B tap div must be a multiple of 256");
+  if (a->b.mn_major && a->b.div && (a->b.div % MAX_BN)) return set_error(XV_ERR_INVALID, "MN-major B tap div must be a multiple of 256");
   if ((a->col_sum == nullptr) != (a->col_sumsq == nullptr) && a->epilogue == XV_EPI_BF16)
     return set_error(XV_ERR_INVALID, "col_sum and col_sumsq must be given together");
 
   // CTA pairs (cta_group::2, 256 x 256 tiles) for the matrix-output epilogues when there are enough tiles to fill
-  // the 74 SM pairs; head epilogues and small problems stay on one CTA per 128 x 256 tile.  XV_GEMM_CG=1|2 forces it.
+  // the 74 SM pairs; head epilogues and small problems run one CTA per 128 x 128 tile.  XV_GEMM_CG=1|2 forces it.
   int cg = 1;
   {
     static int forced = -1;
@@ -98,19 +98,21 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
     }
     const bool can = (a->epilogue == XV_EPI_BF16 || a->epilogue == XV_EPI_F32);
     const long long pair_tiles = static_cast<long long>((a->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) *
-                                 ((a->N + BLOCK_N - 1) / BLOCK_N) * (a->splits > 0 ? a->splits : 1);
-    if (can && ((forced == 2) || (forced == 0 && pair_tiles >= 64))) cg = 2;
+                                 ((a->N + MAX_BN - 1) / MAX_BN) * (a->splits > 0 ? a->splits : 1);
+    // (M <= 128: one row block -- a pair tile would be half empty, the 128 x 128 single-CTA tiles fit exactly)
+    if (can && ((forced == 2) || (forced == 0 && pair_tiles >= 64 && a->M > BLOCK_M))) cg = 2;
   }
   GemmKernelParams kp;
   memset(&kp, 0, sizeof(kp));
   int rc = make_tmap(&kp.tma_a, a->a, BLOCK_M);
   if (rc) return rc;
-  rc = make_tmap(&kp.tma_b, a->b, BLOCK_N / cg);
+  const int bn = cg == 2 ? GemmCfg<2>::BN : GemmCfg<1>::BN;
+  rc = make_tmap(&kp.tma_b, a->b, bn / cg);
   if (rc) return rc;
   kp.M = a->M; kp.N = a->N; kp.K = a->K;
   kp.a_div = a->a.div; kp.a_tap = a->a.tap_rows; kp.b_div = a->b.div; kp.b_tap = a->b.tap_rows;
   kp.num_m = (a->M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
-  kp.num_n = (a->N + BLOCK_N - 1) / BLOCK_N;
+  kp.num_n = (a->N + bn - 1) / bn;
   kp.num_kb = (a->K + BLOCK_K - 1) / BLOCK_K;
   int splits = a->splits < kp.num_kb ? a->splits : kp.num_kb;
   kp.kb_per_split = (kp.num_kb + splits - 1) / splits;
@@ -144,8 +146,10 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   int sms = 0;
   rc = device_sm_count(&sms);
   if (rc) return rc;
-  if (kp.bnb.y != nullptr && !kp.use_tma_out)
-    return set_error(XV_ERR_INVALID, "bn_bwd fusion needs a TMA-storable output (16-byte aligned, no accumulate)");
+  if ((kp.bnb.y != nullptr || (a->epilogue == XV_EPI_BF16 && kp.col_sum != nullptr)) && !kp.use_tma_out)
+    return set_error(XV_ERR_INVALID, "column statistics / bn_bwd fusion need a TMA-storable bf16 output (16-byte aligned, no accumulate)");
+  if (a->epilogue == XV_EPI_BF16 && kp.col_sum != nullptr && (a->N & 1))
+    return set_error(XV_ERR_INVALID, "column statistics need an even N");
   const long long tiles = static_cast<long long>(kp.num_m) * kp.num_n * kp.splits;
   if (g_cta_limit > 0 && g_cta_limit < sms) sms = g_cta_limit < 2 ? 2 : g_cta_limit;   // leave SMs to a concurrent collective
   const int units = sms / cg;                                   // CTAs (cg = 1) or CTA pairs (cg = 2) on the device

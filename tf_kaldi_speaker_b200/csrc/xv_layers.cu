@@ -103,14 +103,16 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ col_sum, cons
   pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float mean_nb = col_sum[c] / count;                       // mean of the bias-free accumulator
+  // y is stored WITHOUT the layer bias (a bias in front of a batch-norm cancels): scale / shift / saved mean refer to the
+  // stored tensor, only the moving mean -- the statistic of the reference's biased tensor -- adds the bias back
+  const float mean_nb = col_sum[c] / count;
   const float var = fmaxf(col_sumsq[c] / count - mean_nb * mean_nb, 0.f);
   const float mean = mean_nb + (bias ? bias[c] : 0.f);
   const float rstd = rsqrtf(var + eps);
   const float sc = gamma[c] * rstd;
   scale[c] = sc;
-  shift[c] = beta[c] - mean * sc;
-  save_mean[c] = mean;
+  shift[c] = beta[c] - mean_nb * sc;
+  save_mean[c] = mean_nb;
   save_rstd[c] = rstd;
   if (moving_mean) {
     const float mv = unbiased ? var * (count / fmaxf(count - 1.f, 1.f)) : var;
@@ -119,14 +121,14 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ col_sum, cons
   }
 }
 __global__ void bn_finalize_infer_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         const float* __restrict__ mm, const float* __restrict__ mv, float eps,
-                                         float* scale, float* shift, int C) {
+                                         const float* __restrict__ mm, const float* __restrict__ mv,
+                                         const float* __restrict__ bias, float eps, float* scale, float* shift, int C) {
   pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] * rsqrtf(mv[c] + eps);
   scale[c] = sc;
-  shift[c] = beta[c] - mm[c] * sc;
+  shift[c] = beta[c] - (mm[c] - (bias ? bias[c] : 0.f)) * sc;     // the stored tensor is bias-free: fold the bias in here
 }
 
 // Row-streaming layout shared by the BN kernels below: grid = (C/128, row chunks of STREAM_ROWS); a block is 8 warps,
@@ -297,18 +299,18 @@ __global__ void __launch_bounds__(256) bn_act_apply_kernel(const __nv_bfloat16* 
   if (bt.col_sum != nullptr) {      // one channel per thread, shared through smem (not 8 per thread: 2x the kernel time)
     const int c = wb.cgroup * WCH + threadIdx.x;
     if (c < C) {
-      const float mean_nb = bt.col_sum[c] / bt.count;                       // mean of the bias-free accumulator
+      const float mean_nb = bt.col_sum[c] / bt.count;                       // mean of the stored (bias-free) tensor
       const float var = fmaxf(bt.col_sumsq[c] / bt.count - mean_nb * mean_nb, 0.f);
-      const float mean = mean_nb + (bt.bias ? bt.bias[c] : 0.f);
+      const float mean = mean_nb + (bt.bias ? bt.bias[c] : 0.f);            // moving mean only (see bn_finalize_train_kernel)
       const float rstd = rsqrtf(var + bt.eps);
       const float scv = bt.gamma[c] * rstd;
-      const float shv = bt.beta[c] - mean * scv;
+      const float shv = bt.beta[c] - mean_nb * scv;
       s_sc[threadIdx.x] = scv;
       s_sh[threadIdx.x] = shv;
       if ((blockIdx.x / rg.col_groups) == 0) {     // first row chunk: publish for the backward pass, update moving stats
         bt.scale_out[c] = scv;
         bt.shift_out[c] = shv;
-        bt.save_mean[c] = mean;
+        bt.save_mean[c] = mean_nb;
         bt.save_rstd[c] = rstd;
         if (bt.moving_mean) {
           const float mv = bt.unbiased ? var * (bt.count / fmaxf(bt.count - 1.f, 1.f)) : var;
@@ -890,18 +892,18 @@ __global__ void __launch_bounds__(256) bn_act_apply_flat_kernel(const __nv_bfloa
   if (bt.col_sum != nullptr) {      // training-mode finalisation folded in (see bn_act_apply_kernel)
     const int c = cgroup * WCH + threadIdx.x;
     if (c < C) {
-      const float mean_nb = bt.col_sum[c] / bt.count;
+      const float mean_nb = bt.col_sum[c] / bt.count;                       // mean of the stored (bias-free) tensor
       const float var = fmaxf(bt.col_sumsq[c] / bt.count - mean_nb * mean_nb, 0.f);
-      const float mean = mean_nb + (bt.bias ? bt.bias[c] : 0.f);
+      const float mean = mean_nb + (bt.bias ? bt.bias[c] : 0.f);            // moving mean only (see bn_finalize_train_kernel)
       const float rstd = rsqrtf(var + bt.eps);
       const float scv = bt.gamma[c] * rstd;
-      const float shv = bt.beta[c] - mean * scv;
+      const float shv = bt.beta[c] - mean_nb * scv;
       s_sc[threadIdx.x] = scv;
       s_sh[threadIdx.x] = shv;
       if (rb == 0) {
         bt.scale_out[c] = scv;
         bt.shift_out[c] = shv;
-        bt.save_mean[c] = mean;
+        bt.save_mean[c] = mean_nb;
         bt.save_rstd[c] = rstd;
         if (bt.moving_mean) {
           const float mv = bt.unbiased ? var * (bt.count / fmaxf(bt.count - 1.f, 1.f)) : var;
@@ -1108,11 +1110,12 @@ extern "C" int xv_bn_finalize_train(const float* col_sum, const float* col_sumsq
 }
 
 extern "C" int xv_bn_finalize_infer(const float* gamma, const float* beta, const float* moving_mean,
-                                    const float* moving_var, float eps, float* scale, float* shift, int C, void* stream) {
+                                    const float* moving_var, const float* bias, float eps, float* scale, float* shift,
+                                    int C, void* stream) {
   if (!gamma || !beta || !moving_mean || !moving_var || !scale || !shift || C <= 0)
     return set_error(XV_ERR_INVALID, "xv_bn_finalize_infer: bad arguments");
   ::xv::launch_pdl((bn_finalize_infer_kernel), ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream), gamma, beta, moving_mean,
-                                                                                            moving_var, eps, scale, shift, C);
+                   moving_var, bias, eps, scale, shift, C);
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

@@ -27,6 +27,7 @@ class CompressedSegmentBatch(object):
         self.headers = self._headers.numpy().view(np.uint16)
         self.glob = self._glob.numpy()
         self._dev = None
+        self._copied = None          # event recorded after the H2D copies of the last decode_into()
 
     @property
     def shape(self):
@@ -56,9 +57,17 @@ class CompressedSegmentBatch(object):
         d.copy_(self._data, non_blocking=True)
         h.copy_(self._headers, non_blocking=True)
         g.copy_(self._glob, non_blocking=True)
+        if self._copied is None:
+            self._copied = torch.cuda.Event()
+        self._copied.record()
         L.check(L.load().xv_cm_decode(L.ptr(d), L.ptr(h), L.ptr(g), L.ptr(out), self.B, self.T, self.D,
                                       C.c_int64(self.T), C.c_int64(self.D), L.stream_ptr()))
         return out
+
+    def wait_reusable(self):
+        """Block until the pinned arrays may be overwritten (the last upload has read them)."""
+        if self._copied is not None:
+            self._copied.synchronize()
 
     def to_device(self, device=None):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

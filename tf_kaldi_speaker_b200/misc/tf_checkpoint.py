@@ -48,13 +48,61 @@ def _crc_table():
     return _CRC_TABLE
 
 
-def crc32c(data, crc=0):
-    """CRC-32C (Castagnoli), as crc32c::Extend."""
+def _crc32c_bytewise(data, crc=0):
     t = _crc_table()
     c = crc ^ 0xFFFFFFFF
     for b in bytes(data):
         c = t[(c ^ b) & 0xFF] ^ (c >> 8)
     return c ^ 0xFFFFFFFF
+
+
+def _gf2_apply(cols, x):
+    """y = M x over GF(2) for a 32 x 32 matrix given by its 32 uint32 columns; x may be an array."""
+    y = np.zeros_like(x)
+    for j in range(32):
+        y ^= np.where((x >> np.uint32(j)) & np.uint32(1), cols[j], np.uint32(0)).astype(np.uint32)
+    return y
+
+
+def crc32c(data, crc=0):
+    """CRC-32C (Castagnoli), as crc32c::Extend.  Large buffers (a 30 MB speaker matrix) are cut into 2^k equal chunks
+    whose raw CRC registers advance in lock-step as NumPy vectors, then merged pairwise with the GF(2) "append n zero
+    bytes" operator (the crc32_combine construction): seconds of pure-Python byte loop become milliseconds."""
+    data = bytes(data)
+    n = len(data)
+    if n < (1 << 16):
+        return _crc32c_bytewise(data, crc)
+    table = np.array(_crc_table(), dtype=np.uint32)
+    levels = 12
+    N = 1 << levels
+    L = -(-n // N)
+    buf = np.zeros(N * L, dtype=np.uint8)
+    buf[N * L - n:] = np.frombuffer(data, dtype=np.uint8)       # leading zeros leave a zero-initialised register at zero
+    chunks = buf.reshape(N, L)
+    reg = np.zeros(N, dtype=np.uint32)
+    for i in range(L):
+        reg = table[(reg ^ chunks[:, i]) & np.uint32(0xFF)] ^ (reg >> np.uint32(8))
+    # operator "append one zero byte" as matrix columns, raised to the power L by repeated squaring
+    one = np.uint32(1)
+    cols = np.array([table[(one << np.uint32(j)) & np.uint32(0xFF)] ^ ((one << np.uint32(j)) >> np.uint32(8)) for j in range(32)],
+                    dtype=np.uint32)
+
+    def power(c, e):
+        result = np.array([one << np.uint32(j) for j in range(32)], dtype=np.uint32)      # identity
+        base = c.copy()
+        while e:
+            if e & 1:
+                result = _gf2_apply(base, result)
+            base = _gf2_apply(base, base)
+            e >>= 1
+        return result
+    shift = power(cols, L)
+    for _ in range(levels):
+        reg = _gf2_apply(shift, reg[0::2]) ^ reg[1::2]
+        shift = _gf2_apply(shift, shift)
+    init = np.array([(crc ^ 0xFFFFFFFF) & 0xFFFFFFFF], dtype=np.uint32)
+    head = _gf2_apply(power(cols, n), init)                    # the initial register pushed through n bytes
+    return int(reg[0] ^ head[0]) ^ 0xFFFFFFFF
 
 
 def mask_crc(c):
@@ -191,8 +239,9 @@ def _read_index(prefix):
             if 7 in e:
                 raise NotImplementedError("%s: partitioned (sliced) variables are not supported" % key.decode())
             code = e.get(1, [0])[0]
-            if code not in DTYPES:
-                raise NotImplementedError("%s: dtype code %d" % (key.decode(), code))
+            if code not in DTYPES:       # e.g. DT_STRING bookkeeping entries: only an error if somebody asks for them
+                out[key.decode()] = (None, code, e.get(3, [0])[0], e.get(4, [0])[0], e.get(5, [0])[0], None)
+                continue
             shape = []
             if 2 in e:
                 for d in _parse_proto(e[2][0]).get(2, []):
@@ -216,6 +265,10 @@ def read_tf_checkpoint(prefix, names=None, verify_crc=False):
     try:
         for name, (dt, shape, shard, offset, size, crc) in meta.items():
             if names is not None and name not in names:
+                continue
+            if dt is None:
+                if names is not None:
+                    raise NotImplementedError("%s: dtype code %d" % (name, shape))
                 continue
             if shard not in files:
                 files[shard] = open("%s.data-%05d-of-%05d" % (prefix, shard, num), "rb")

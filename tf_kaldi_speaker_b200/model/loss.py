@@ -40,6 +40,9 @@ def declare_head_variables(engine, embedding_dim, num_outputs, params, loss_type
                        init="glorot", fans=(embedding_dim, num_outputs)))
     if loss_type == "softmax":
         st.declare(VarSpec(name + "/output/bias", (num_outputs,), (cpad,)))
+    if "ring_loss" in params.dict.get("aux_loss_func", []):
+        # the trainable ring radius, tf.get_variable("r", initializer=ring_loss_init) under <name>_ringloss (loss.py:1008-1011)
+        st.declare(VarSpec(name + "_ringloss/r", (), (1,), init=float(params.ring_loss_init)))
 
 
 def margin_lambda(lambda_min, lambda_base, lambda_gamma, lambda_power, global_step):
@@ -62,29 +65,44 @@ def margin_schedule(loss_type, params, global_step):
     return fa, fs
 
 
+def _aux_config(params, name, with_aux):
+    """params.aux_loss_func (model/loss.py:985-1037) -> what Engine.margin_head fuses: ring loss on the head's input
+    features with the trainable radius ``<name>_ringloss/r`` (loss.py:1008-1012) and MHE on the normalised weights."""
+    if not with_aux or "aux_loss_func" not in params.dict or len(params.dict["aux_loss_func"]) == 0:
+        return None
+    aux = {}
+    for loss_func in params.aux_loss_func:
+        if loss_func == "ring_loss":
+            aux["ring"] = (name + "_ringloss/r", float(params.ring_loss_lambda))
+        elif loss_func == "mhe_loss":
+            aux["mhe"] = float(params.mhe_lambda)
+        else:
+            raise NotImplementedError("Unsupported loss function %s" % loss_func)
+    return aux
+
+
 def _run_head(features, labels, num_outputs, params, is_training, name, head_type, margin=0.0, asoftmax_m=1,
-              fa=1.0, fs=0.0):
+              fa=1.0, fs=0.0, with_aux=True):
     eng = get_engine()
     assert features.data.dim() == labels.dim() + 1
     eng.set_sched(fa, fs)
     scaling = float(getattr(features, "scaling", 0.0) or 0.0)
     bias = (name + "/output/bias") if head_type == L.HEAD_SOFTMAX and (name + "/output/bias") in eng.store else None
     want_logits = bool(params.dict.get("debug_logits", False))
+    aux = _aux_config(params, name, with_aux)
     if eng.head_shard is not None:
-        if want_logits:
-            raise NotImplementedError("debug_logits is not available with the class-sharded head")
+        if want_logits or aux:
+            raise NotImplementedError("debug_logits / aux_loss_func are not available with the class-sharded head")
         loss, logits, x = eng.margin_head_sharded(features, labels, name + "/output/kernel", bias, head_type, num_outputs,
                                                   bool(is_training), margin=margin, asoftmax_m=asoftmax_m, scaling=scaling)
     else:
         loss, logits, x = eng.margin_head(features, labels, name + "/output/kernel", bias, head_type, num_outputs,
                                           bool(is_training), margin=margin, asoftmax_m=asoftmax_m, scaling=scaling,
-                                          want_logits=want_logits)
+                                          want_logits=want_logits, aux=aux)
     params.dict["softmax_w"] = eng.store.view(name + "/output/kernel")      # loss.py:103,211,297
     endpoints = OrderedDict()
     endpoints["logits"] = None if logits is None else logits[:, :num_outputs]
     endpoints["labels"] = labels
-    if 'aux_loss_func' in params.dict and len(params.dict['aux_loss_func']) > 0:
-        raise NotImplementedError("aux_loss_func (ring / MHE, loss.py:985-1037) is outside the accelerated path")
     return loss, endpoints
 
 
@@ -103,7 +121,8 @@ def asoftmax(features, labels, num_outputs, params, is_training=None, reuse_vari
     if m == 1:
         # plain xent on ||x|| cos(theta): no margin, no lambda (loss.py:110-115)
         # = the additive-margin epilogue with m = 0, fa = 0, fs = 1 (normalised weights, untouched target logit)
-        return _run_head(features, labels, num_outputs, params, is_training, name, L.HEAD_AM, margin=0.0, fa=0.0, fs=1.0)
+        return _run_head(features, labels, num_outputs, params, is_training, name, L.HEAD_AM, margin=0.0, fa=0.0, fs=1.0,
+                         with_aux=False)       # loss.py:110-115 returns before the auxiliary losses
     if m not in (2, 4):
         raise NotImplementedError("[ERROR] m=%d is not unsupported." % m)
     _, fa, fs = margin_lambda(params.asoftmax_lambda_min, params.asoftmax_lambda_base, params.asoftmax_lambda_gamma,

@@ -54,6 +54,8 @@ class Trainer(object):
         self._copy_stream = None
         self._h2d_event = None
         self.use_cuda_graph = bool(params.dict.get("cuda_graph", True))
+        self._captured = 0           # batch shapes whose step has been captured
+        self._in_memory = False      # True once this object holds parameters newer than (or loaded from) the checkpoint
 
     # ------------------------------------------------------------------ network (trainer.py:168-188)
     def entire_network(self, features, params, is_training, reuse_variables, lengths=None):
@@ -126,6 +128,8 @@ class Trainer(object):
     # ------------------------------------------------------------------ one step = sess.run(train_op)
     def _to_device(self, features, labels=None):
         dev = self.engine.device
+        if hasattr(features, "decode_into"):       # dataset.feeder.CompressedSegmentBatch: raw uint8 crops, decoded on the device
+            features = features.to_device(dev)
         if not torch.is_tensor(features):
             features = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
         features = features.to(dev, dtype=torch.float32, non_blocking=True)
@@ -135,7 +139,7 @@ class Trainer(object):
             labels = labels.to(dev, dtype=torch.int32, non_blocking=True)
         return features, labels
 
-    def _fwd_bwd(self, features, labels, l2_loss=True, backward_part=None):
+    def _fwd_bwd(self, features, labels, l2_loss=True):
         """Forward + backward of one device-resident batch; gradients are left in the flat gradient buffer.
         ``l2_loss=False``: the regularisation loss is left to the optimizer kernel (same pass over the parameters)."""
         eng = self.engine
@@ -149,7 +153,7 @@ class Trainer(object):
         self.endpoints = endpoints
         if l2_loss:
             eng.l2_loss()
-        eng.backward(backward_part)
+        eng.backward()
 
     def forward_backward(self, features, labels, global_step):
         """Eager forward + backward (no optimizer step); used by tests and gradient inspection."""
@@ -212,23 +216,8 @@ class Trainer(object):
                       float(self.params.dict.get("clip_gradient_norm", 0.0)) if clip else 0.0, flush=False)
         eng.set_sched(*margin_schedule(self.loss_type, self.params, global_step))
 
-        # dp_overlap: all-reduce the [tdnn6 .. head] gradient bucket while the frame-level backward runs.  Measured on
-        # 2 x B200: 1.169 ms/step with, 1.160 ms without (the 39 MB exchange costs ~75 us either way and the NCCL CTAs
-        # take SMs from the persistent GEMMs), so it stays opt-in.
-        overlap = self.dp is not None and bool(self.params.dict.get("dp_overlap", False))
-
         def part_a():
-            self._fwd_bwd(st["x"], st["y"], l2_loss=False, backward_part=("head" if overlap else None))
-
-        def part_a2():
-            # the head-bucket all-reduce is in flight: cap the persistent GEMM grids so that NCCL's CTAs do not strand
-            # GEMM CTAs behind them (xv_gemm_set_cta_limit); the cap is baked into the captured launches
-            reserve = int(self.params.dict.get("dp_overlap_reserve_sms", 16))
-            L.check(eng.lib.xv_gemm_set_cta_limit(max(eng.num_sms - reserve, 2)))
-            try:
-                eng.backward("trunk")
-            finally:
-                L.check(eng.lib.xv_gemm_set_cta_limit(0))
+            self._fwd_bwd(st["x"], st["y"], l2_loss=False)
 
         def part_b():
             if eng.head_shard is not None:       # regularisation loss of this rank's head columns, for the logged total
@@ -273,36 +262,12 @@ class Trainer(object):
                     body()
             return self._finish_step(global_step, fetch_loss)
 
-        # the multimem all-reduce is a plain kernel with in-kernel rank barriers: the whole data-parallel step (forward,
-        # backward, gradient exchange, optimizer) is then ONE captured graph, like the single-GPU step
-        in_graph_exchange = self.dp is not None and bool(getattr(self.dp, "graph_safe", False)) and not overlap
-        # dp_bucket_overlap: the [tdnn6 .. head] gradients are complete a third of the way into the backward pass; their
-        # exchange runs as a small-grid kernel on a second stream beside the tdnn5 backward (whose two GEMMs leave it a
-        # few SMs), only the [tdnn1 .. tdnn5] bucket is exchanged after the backward pass
-        bucket_overlap = (in_graph_exchange and bool(self.params.dict.get("dp_bucket_overlap", False)) and not clip
-                          and getattr(self.dp, "_mm", None) is not None and self.dp.split > 0
-                          and self.dp.grad_dtype != "bf16")
+        # Default: the gradient exchange is our own kernel with in-kernel rank barriers (xv_dp_allreduce_*), so the whole
+        # data-parallel step (forward, backward, exchange, optimizer) is ONE captured graph, like the single-GPU step.
+        # Fallback (no symmetric memory / dp_allreduce = "nccl"): graph(forward + backward) | NCCL all-reduce | graph(optimizer).
+        in_graph_exchange = self.dp is not None and bool(getattr(self.dp, "graph_safe", False))
 
-        def part_ab_overlapped():
-            ex_sms = int(self.params.dict.get("dp_bucket_overlap_sms", 16))
-            self._fwd_bwd(st["x"], st["y"], l2_loss=False, backward_part="head")
-            with eng.fork_exchange_stream():
-                self.dp.allreduce_range(self.dp.split, self.dp.dp_numel, grid=ex_sms)
-            eng.cap_next_gemms(int(self.params.dict.get("dp_bucket_overlap_gemms", 2)), eng.num_sms - ex_sms)
-            try:
-                eng.backward("trunk")
-            finally:
-                eng.cap_next_gemms(0, 0)
-            eng.join_exchange_stream()
-            self.dp.allreduce_range(0, self.dp.split)
-            part_b()
-
-        def run(ga, ga2, gb):
-            """forward + head backward | all-reduce(head bucket) overlapping the frame-level backward | all-reduce(trunk
-            bucket) | optimizer.  ga / ga2 / gb are captured graphs or None (eager)."""
-            if bucket_overlap:
-                ga.replay() if ga is not None else part_ab_overlapped()
-                return
+        def run(ga, gb):
             ga.replay() if ga is not None else part_a()
             if self.dp is None or in_graph_exchange:
                 if ga is None:
@@ -310,51 +275,45 @@ class Trainer(object):
                         self.dp.allreduce_gradients()
                     part_b()
                 return
-            if overlap:
-                self.dp.allreduce_bucket_async("head")
-                ga2.replay() if ga2 is not None else part_a2()
-                self.dp.allreduce_bucket_async("trunk")
-                self.dp.wait_all()
-            else:
-                self.dp.allreduce_gradients()
+            self.dp.allreduce_gradients()
             gb.replay() if gb is not None else part_b()
 
+        if st["graphs"] is not None and st.get("gen") != eng.ws_generation:
+            st["graphs"], st["calls"] = None, 1      # a scratch buffer grew since the capture: its addresses are stale
         if st["graphs"] is not None:
             run(*st["graphs"])
             eng.launches += st["launches"]
         else:
             st["calls"] += 1
-            if self.use_cuda_graph and st["calls"] > 2:
+            # two eager calls for the first batch shape (lazy allocations, optimizer slots), one for every further
+            # segment length (its views of the shared scratch buffers), then capture
+            warm = 2 if self._captured == 0 else 1
+            if self.use_cuda_graph and st["calls"] > warm:
                 l0 = eng.launches
                 eng.capturing = True
                 try:
                     ga = torch.cuda.CUDAGraph()
-                    ga2 = gb = None
+                    gb = None
                     with torch.cuda.graph(ga):
-                        if bucket_overlap:
-                            part_ab_overlapped()
-                        else:
-                            part_a()
-                            if self.dp is None:
-                                part_b()
-                            elif in_graph_exchange:
-                                self.dp.allreduce_gradients()
-                                part_b()
+                        part_a()
+                        if self.dp is None:
+                            part_b()
+                        elif in_graph_exchange:
+                            self.dp.allreduce_gradients()
+                            part_b()
                     if self.dp is not None and not in_graph_exchange:
-                        if overlap:
-                            ga2 = torch.cuda.CUDAGraph()
-                            with torch.cuda.graph(ga2):
-                                part_a2()
                         gb = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(gb):
                             part_b()
                 finally:
                     eng.capturing = False
                 st["launches"] = eng.launches - l0
-                st["graphs"] = (ga, ga2, gb)
-                run(ga, ga2, gb)
+                st["graphs"] = (ga, gb)
+                st["gen"] = eng.ws_generation
+                self._captured += 1
+                run(ga, gb)
             else:
-                run(None, None, None)
+                run(None, None)
         return self._finish_step(global_step, fetch_loss)
 
     def _finish_step(self, global_step, fetch_loss):
@@ -362,43 +321,93 @@ class Trainer(object):
         self.global_step = int(global_step) + 1
         if fetch_loss:
             vals = eng.scalars[:5].tolist()          # one D2H read
-            raw = vals[0]
-            l2 = vals[1]
-            if self.dp is not None:
+            raw, l2, pen = vals[0], vals[1], vals[3]
+            if self.dp is not None and not self.dp.scalars_reduced:
+                # NCCL fallback / segmented step: the loss and penalty scalars are rank-local sums over the local rows
                 raw = self.dp.mean_scalar(raw)
-                if eng.head_shard is not None:       # add the regularisation loss of the other ranks' head columns
-                    l2 += self.dp.sum_scalar(vals[4]) - vals[4]
-            self.train_ops = {"raw_loss": raw, "loss": raw + l2 + vals[3]}
+                if float(self.params.dict.get("att_penalty_term", 0.0) or 0.0) != 0.0:      # same decision on every rank
+                    pen = self.dp.sum_scalar(pen)
+            if self.dp is not None and eng.head_shard is not None:       # regularisation loss of the other ranks' head columns
+                l2 += self.dp.sum_scalar(vals[4]) - vals[4]
+            self.train_ops = {"raw_loss": raw, "loss": raw + l2 + pen}
             return dict(self.train_ops)
         return None
 
+    def reserve(self, batch, max_frames, dim=None):
+        """Size every scratch buffer for the longest batch the loop will see ([batch, max_frames, dim]) with one eager
+        forward/backward on zeros, so that no buffer grows (and no captured step is invalidated) when a longer segment
+        length is drawn later.  Moving statistics are restored; gradients are cleared by the next step anyway."""
+        eng = self.engine
+        dim = self.dim if dim is None else dim
+        saved = eng.store.buffers.clone()
+        x = torch.zeros((int(batch), int(max_frames), int(dim)), dtype=torch.float32, device=eng.device)
+        y = torch.zeros((int(batch),), dtype=torch.int32, device=eng.device)
+        eng.set_sched(*margin_schedule(self.loss_type, self.params, self.global_step or 0))
+        self._fwd_bwd(x, y)
+        eng.store.buffers.copy_(saved)
+        torch.cuda.synchronize()
+
+    def _open_loader(self, data, spklist, kind, **kw):
+        """``data``: a Kaldi data directory (the reference's call, train.py:98-104) or an object that already speaks the
+        start()/fetch()/stop() protocol of KaldiDataRandomQueue."""
+        if hasattr(data, "fetch"):
+            return data
+        from ..dataset.data_loader import KaldiDataRandomQueue, KaldiDataSeqQueue
+        p = self.params
+        if kind == "random":
+            return KaldiDataRandomQueue(data, spklist, num_parallel=p.num_parallel_datasets, max_qsize=p.max_queue_size,
+                                        num_speakers=kw.get("num_speakers", p.num_speakers_per_batch),
+                                        num_segments=kw.get("num_segments", p.num_segments_per_speaker),
+                                        min_len=p.min_segment_len, max_len=p.max_segment_len, shuffle=True,
+                                        base_seed=p.dict.get("data_seed"))
+        return KaldiDataSeqQueue(data, spklist, num_parallel=2, max_qsize=10,
+                                 batch_size=p.num_speakers_per_batch * p.num_segments_per_speaker,
+                                 min_len=p.min_segment_len, max_len=p.max_segment_len, shuffle=kw.get("shuffle", True),
+                                 base_seed=p.dict.get("data_seed"))
+
     def train(self, data, spklist, learning_rate, aux_data=None):
-        """One epoch (trainer.py:451-520).  ``data``: object with start()/fetch()/stop() yielding (features, labels)."""
+        """One epoch (model/trainer.py:451-520).  ``data`` / ``spklist``: the training data directory and the speaker
+        list, as nnet/lib/train.py:98 passes them (a loader object with start()/fetch()/stop() is accepted too)."""
+        from ..dataset.data_loader import DataOutOfRange
         assert "train" in self.modes
-        if not hasattr(data, "fetch"):
-            raise NotImplementedError("The Kaldi feature pipeline stays on the host: pass a loader object with "
-                                      "start()/fetch()/stop() (e.g. dataset.data_loader.KaldiDataRandomQueue).")
-        curr_step = self.global_step or 0
-        if hasattr(data, "start"):
-            data.start()
+        curr_step = 0
+        if self._in_memory:                      # this object has been training: its state is the newest there is
+            curr_step = self.global_step or 0
+        elif os.path.isfile(os.path.join(self.model, "checkpoint")):
+            curr_step = self.load()              # trainer.py:467-469
+        data_loader = self._open_loader(data, spklist, "random")
+        if not hasattr(data, "fetch") and "max_segment_len" in self.params.dict:
+            shape = (self.params.num_speakers_per_batch * self.params.num_segments_per_speaker, self.params.max_segment_len)
+            if getattr(self, "_reserved", None) != shape:
+                self.reserve(*shape)
+                self._reserved = shape
+        if hasattr(data_loader, "start"):
+            data_loader.start()
         steps = int(self.params.num_steps_per_epoch)
-        t0 = time.time()
-        for step in range(curr_step % steps, steps):
-            show = (step % int(self.params.show_training_progress) == 0)
-            features, labels = data.fetch()
-            res = self.train_step(features, labels, learning_rate, curr_step, fetch_loss=show)
-            if show:
-                dt = time.time() - t0
-                t0 = time.time()
-                print("Epoch: [%2d] step: [%2d/%2d] time: %.4f s/step, raw loss: %f, total loss: %f"
-                      % (curr_step // steps, step, steps, dt / int(self.params.show_training_progress),
-                         res["raw_loss"], res["loss"]))
-            if curr_step % int(self.params.save_checkpoints_steps) == 0 and curr_step != 0:
-                self.save(curr_step)
-            curr_step += 1
+        epoch = int(curr_step / steps)
+        try:
+            for step in range(curr_step % steps, steps):
+                try:
+                    show = (step % int(self.params.save_summary_steps) == 0 or
+                            step % int(self.params.show_training_progress) == 0)
+                    t0 = time.time()
+                    features, labels = data_loader.fetch()
+                    res = self.train_step(features, labels, learning_rate, curr_step, fetch_loss=show)
+                    if show:
+                        print("Epoch: [%2d] step: [%2d/%2d] time: %.4f s/step, raw loss: %f, total loss: %f"
+                              % (epoch, step, steps, time.time() - t0, res["raw_loss"], res["loss"]), flush=True)
+                    self._in_memory = True
+                    if step % int(self.params.save_checkpoints_steps) == 0 and curr_step != 0:
+                        self.save(curr_step)
+                    curr_step += 1
+                except DataOutOfRange:
+                    print("Finished reading features.")
+                    break
+        finally:
+            if hasattr(data_loader, "stop"):
+                data_loader.stop()
+        self.global_step = curr_step
         self.save(curr_step)
-        if hasattr(data, "stop"):
-            data.stop()
         return
 
     # ------------------------------------------------------------------ validation (trainer.py:261-303, 592-706)
@@ -428,28 +437,61 @@ class Trainer(object):
         return float(loss.item()), endpoints["output"].dense()
 
     def valid(self, data, spklist, batch_type="softmax", output_embeddings=False, aux_data=None):
+        """model/trainer.py:592-706: mean validation loss over at most ``valid_max_iterations`` batches (margins
+        neutralised, BN in inference mode) and, with ``output_embeddings``, the embeddings / labels of every segment read in
+        order.  ``data``: the validation data directory (or a loader object)."""
+        from ..dataset.data_loader import DataOutOfRange
         assert "valid" in self.modes or "train" in self.modes
-        if not hasattr(data, "fetch"):
-            raise NotImplementedError("pass a loader object with start()/fetch()/stop()")
-        if hasattr(data, "start"):
-            data.start()
-        losses, embs, labs = [], [], []
-        for _ in range(int(self.params.valid_max_iterations)):
-            try:
-                features, labels = data.fetch()
-            except Exception:
-                break
-            l, e = self.valid_step(features, labels)
-            losses.append(l)
-            if output_embeddings:
+        assert batch_type == "softmax" or batch_type == "end2end", "The batch_type can only be softmax or end2end"
+        if not self._in_memory:
+            if os.path.isfile(os.path.join(self.model, "checkpoint")):
+                self.load()
+            else:
+                print("[Warning] Cannot find model in %s. Random initialization is used in validation." % self.model)
+        embeddings_val, labels_val = None, None
+        if output_embeddings:
+            loader = self._open_loader(data, spklist, "seq", shuffle=False)
+            if hasattr(loader, "start"):
+                loader.start()
+            embs, labs = [], []
+            while True:
+                try:
+                    features, labels = loader.fetch()
+                except (DataOutOfRange, StopIteration):
+                    break
+                _, e = self.valid_step(features, labels)
                 embs.append(e.cpu().numpy())
                 labs.append(np.asarray(labels))
-        if hasattr(data, "stop"):
-            data.stop()
+                if hasattr(data, "fetch") and len(embs) >= int(self.params.valid_max_iterations):
+                    break
+            if hasattr(loader, "stop"):
+                loader.stop()
+            if embs:
+                embeddings_val, labels_val = np.concatenate(embs, 0), np.concatenate(labs, 0)
+            if hasattr(data, "fetch"):          # a caller-supplied loader is consumed once: both results from this pass
+                return 0.0, embeddings_val, labels_val
+        if batch_type == "softmax":
+            loader = self._open_loader(data, spklist, "seq", shuffle=True)
+        else:
+            assert "num_valid_speakers_per_batch" in self.params.dict and "num_valid_segments_per_speaker" in self.params.dict, \
+                "Valid parameters should be set if E2E loss is selected"
+            loader = self._open_loader(data, spklist, "random", num_speakers=self.params.num_valid_speakers_per_batch,
+                                       num_segments=self.params.num_valid_segments_per_speaker)
+        if hasattr(loader, "start"):
+            loader.start()
+        losses = []
+        for _ in range(int(self.params.valid_max_iterations)):
+            try:
+                features, labels = loader.fetch()
+            except (DataOutOfRange, StopIteration):
+                break
+            l, _ = self.valid_step(features, labels)
+            losses.append(l)
+        if hasattr(loader, "stop"):
+            loader.stop()
         loss = float(np.mean(losses)) if losses else 0.0
-        if output_embeddings:
-            return loss, np.concatenate(embs, 0), np.concatenate(labs, 0)
-        return loss, None, None
+        print("[Validation %d batches] valid loss: %f" % (len(losses), loss), flush=True)
+        return loss, embeddings_val, labels_val
 
     # ------------------------------------------------------------------ prediction (trainer.py:708-726)
     def predict(self, features):
@@ -461,54 +503,114 @@ class Trainer(object):
         emb = self.predict_batch_padded(features, None)
         return emb[0] if rank == 2 else emb
 
-    def predict_batch_padded(self, features, lengths):
+    def predict_batch_padded(self, features, lengths, as_device=False):
         """[N, Tmax, D] (+ optional lengths [N]) -> np [N, E]; rows are independent (BN in inference mode, masked
-        pooling), so a ragged batch gives the same result as one call per utterance (extract.py:90)."""
+        pooling), so a ragged batch gives the same result as one call per utterance (extract.py:90).
+        ``as_device``: return a device tensor (a copy: the workspace is reused by the next call) without synchronising,
+        so the caller can overlap the next batch's upload with this one's compute."""
         eng = self.engine
         feats, _ = self._to_device(features)
-        ln = None if lengths is None else torch.as_tensor(np.asarray(lengths), dtype=torch.int32, device=eng.device)
+        ln = None if lengths is None else torch.as_tensor(np.asarray(lengths), dtype=torch.int32).to(eng.device, non_blocking=True)
         eng.begin_step(False)
         _, endpoints = self.entire_network(feats, self.params, False, True, lengths=ln)
         self.endpoints = endpoints
         node = endpoints[self.params.embedding_node]
+        if as_device:
+            return node.dense().float().clone()
         return node.dense().float().cpu().numpy()
 
     # ------------------------------------------------------------------ checkpoints (trainer.py:142-166)
-    def save(self, step):
-        os.makedirs(self.model, exist_ok=True)
+    def _export_full(self, which):
+        """Variables (or optimizer slots) in their full TF shapes; the column shards of a class-sharded head are
+        gathered (a collective: every rank calls this)."""
         st = self.engine.store
-        vals = st.export_tf()
+        vals = st.export_tf(which=which)
         sh = self.engine.head_shard
-        if sh is not None:          # every rank calls save(); the sharded variables are written in their full TF shape
+        if sh is not None:
             for name, spec in st.specs.items():
-                if spec.col_range is not None:
+                if spec.col_range is not None and name in vals:
                     loc = torch.from_numpy(vals[name]).to(self.engine.device)
                     full = sh.gather_columns(loc.reshape(-1, loc.shape[-1]))
                     vals[name] = full.reshape(spec.full_shape).cpu().numpy()
-            if sh.rank != 0:
-                return
-        if str(self.params.dict.get("checkpoint_format", "npz")) == "tf":
-            # TF tensor-bundle files under the reference's names (model-<step>.index / .data-00000-of-00001)
-            from ..misc.tf_checkpoint import write_tf_checkpoint
-            vals["global_step"] = np.array(step, dtype=np.int64)
-            write_tf_checkpoint(os.path.join(self.model, "model-%d" % step), vals)
-            with open(os.path.join(self.model, "checkpoint"), "w") as f:
+        return vals
+
+    def _slot_names(self):
+        """TF slot-variable suffixes of the optimizer in use (tf.train.MomentumOptimizer / AdamOptimizer)."""
+        if self.opt in (L.OPT_MOMENTUM, L.OPT_NESTEROV):
+            return {"state1": "/Momentum"}
+        if self.opt == L.OPT_ADAM:
+            return {"state1": "/Adam", "state2": "/Adam_1"}
+        return {}
+
+    def save(self, step):
+        """Every rank calls save() (the sharded variables are gathered collectively); rank 0 alone writes, to a temporary
+        name followed by os.replace, and the ranks meet at a barrier before anyone goes on (a later load() or pruning
+        never sees a torn file)."""
+        import torch.distributed as dist
+        multi = self.dp is not None and dist.is_initialized() and dist.get_world_size() > 1
+        rank = dist.get_rank() if multi else 0
+        vals = self._export_full("params")
+        slots = {}
+        for which, suffix in self._slot_names().items():
+            if getattr(self.engine.store, which) is not None:
+                for k, v in self._export_full(which).items():
+                    slots[k + suffix] = v
+        if rank == 0:
+            os.makedirs(self.model, exist_ok=True)
+            keep = int(self.params.dict.get("keep_checkpoint_max", 5))
+            if str(self.params.dict.get("checkpoint_format", "npz")) == "tf":
+                # TF tensor-bundle files under the reference's names (model-<step>.index / .data-00000-of-00001), slot
+                # variables under tf.train.Saver's names so that a reference training graph restores them
+                from ..misc.tf_checkpoint import write_tf_checkpoint
+                allv = dict(vals)
+                allv.update(slots)
+                allv["global_step"] = np.array(step, dtype=np.int64)
+                if self.opt == L.OPT_ADAM:
+                    allv["beta1_power"] = np.array(0.9 ** max(self.adam_t, 0), dtype=np.float32)
+                    allv["beta2_power"] = np.array(0.999 ** max(self.adam_t, 0), dtype=np.float32)
+                tmp = os.path.join(self.model, ".tmp-model-%d" % step)
+                write_tf_checkpoint(tmp, allv)
+                for ext in (".data-00000-of-00001", ".index"):
+                    os.replace(tmp + ext, os.path.join(self.model, "model-%d%s" % (step, ext)))
+                pattern, rx = "model-*.index", r"model-(\d+)\.index"
+            else:
+                path = os.path.join(self.model, "model-%d.npz" % step)
+                tmp = os.path.join(self.model, ".tmp-model-%d.npz" % step)
+                np.savez(tmp, __step=np.int64(step), __adam_t=np.int64(self.adam_t), **vals,
+                         **{"__slot:" + k: v for k, v in slots.items()})
+                os.replace(tmp, path)
+                pattern, rx = "model-*.npz", r"model-(\d+)\.npz"
+            tmpck = os.path.join(self.model, ".tmp-checkpoint")
+            with open(tmpck, "w") as f:
                 f.write('model_checkpoint_path: "model-%d"\n' % step)
-            return
-        path = os.path.join(self.model, "model-%d.npz" % step)
-        extra = {}
-        if st.state1 is not None:
-            extra["__opt_state1"] = st.state1.cpu().numpy()
-        if st.state2 is not None:
-            extra["__opt_state2"] = st.state2.cpu().numpy()
-        np.savez(path, __step=np.int64(step), __adam_t=np.int64(self.adam_t), **vals, **extra)
-        with open(os.path.join(self.model, "checkpoint"), "w") as f:
-            f.write('model_checkpoint_path: "model-%d"\n' % step)
-        keep = int(self.params.dict.get("keep_checkpoint_max", 5))
-        ckpts = sorted(glob.glob(os.path.join(self.model, "model-*.npz")),
-                       key=lambda p: int(re.search(r"model-(\d+)\.npz", p).group(1)))
-        for old in ckpts[:-keep] if keep > 0 else []:
-            os.remove(old)
+            os.replace(tmpck, os.path.join(self.model, "checkpoint"))
+            ckpts = sorted(glob.glob(os.path.join(self.model, pattern)), key=lambda p: int(re.search(rx, p).group(1)))
+            for old in ckpts[:-keep] if keep > 0 else []:
+                os.remove(old)
+                if old.endswith(".index"):
+                    data = old[:-len(".index")] + ".data-00000-of-00001"
+                    if os.path.exists(data):
+                        os.remove(data)
+        if multi:
+            dist.barrier()
+
+    def _load_slots(self, values):
+        """values: '<var><slot suffix>' -> array in the variable's (full) TF shape; each rank keeps its own columns."""
+        st = self.engine.store
+        for which, suffix in self._slot_names().items():
+            found = {k[:-len(suffix)]: v for k, v in values.items() if k.endswith(suffix) and k[:-len(suffix)] in st.specs}
+            if not found:
+                continue
+            st.ensure_opt_state(self.opt)
+            flat = getattr(st, which)
+            for name, arr in found.items():
+                sp = st.specs[name]
+                if not sp.trainable:
+                    continue
+                arr = np.asarray(arr)
+                if sp.col_range is not None and tuple(arr.shape) == sp.full_shape and sp.full_shape != sp.tf_shape:
+                    arr = arr[..., sp.col_range[0]:sp.col_range[1]]
+                flat[sp.offset:sp.offset + sp.numel].copy_(torch.from_numpy(sp.to_internal(arr)).reshape(-1).to(flat.device))
 
     def load(self):
         ck = os.path.join(self.model, "checkpoint")
@@ -519,16 +621,22 @@ class Trainer(object):
         st = self.engine.store
         base = os.path.join(self.model, os.path.basename(name))
         if not os.path.exists(base + ".npz") and os.path.exists(base + ".index"):
-            # a checkpoint written by tf.train.Saver (the reference's own format, trainer.py:160-166): variables are
-            # matched by their TF names; optimizer slots and global_step are ignored
+            # a checkpoint in tf.train.Saver's format (the reference's own, trainer.py:160-166): variables and optimizer
+            # slots are matched by their TF names
             from ..misc.tf_checkpoint import read_tf_checkpoint
-            st.load_tf(read_tf_checkpoint(base))
+            vals = read_tf_checkpoint(base)
+            st.load_tf(vals)
+            self._load_slots(vals)
+            if "beta1_power" in vals and self.opt == L.OPT_ADAM:
+                b1p = float(np.asarray(vals["beta1_power"]))
+                self.adam_t = int(round(np.log(max(b1p, 1e-300)) / np.log(0.9))) if 0 < b1p < 1 else 0
             self.global_step = step
             self.is_loaded = True
             return step
         z = np.load(base + ".npz")
         st.load_tf({k: z[k] for k in z.files if not k.startswith("__")})
-        if "__opt_state1" in z.files:
+        self._load_slots({k[len("__slot:"):]: z[k] for k in z.files if k.startswith("__slot:")})
+        if "__opt_state1" in z.files:       # round-1 checkpoints: flat single-rank slot buffers
             st.ensure_opt_state(L.OPT_MOMENTUM)
             st.state1.copy_(torch.from_numpy(z["__opt_state1"]))
         if "__opt_state2" in z.files:
@@ -537,6 +645,7 @@ class Trainer(object):
         self.adam_t = int(z["__adam_t"]) if "__adam_t" in z.files else 0
         self.global_step = step
         self.is_loaded = True
+        self._in_memory = True
         return step
 
     def reset(self):

@@ -244,11 +244,17 @@ class DataParallel(object):
             eng.sync_bn = SyncBN()
         st.refresh_shadows()
         trainer.dp = self
-
-        # Two gradient buckets of the flat buffer: [tdnn6 .. head] is complete once the utterance-level backward has
-        # run (a third of the way into the backward pass), [tdnn1 .. pooling] only at its end.
-        self.split = st.specs["tdnn/tdnn6_dense/kernel"].offset if "tdnn/tdnn6_dense/kernel" in st.specs else 0
-        self._pending = []
+        # The loss / penalty scalars are the first thing carved from the zero arena, i.e. they sit directly behind the
+        # gradients in the same (symmetric) buffer: the gradient exchange covers them too, so the logged loss is the
+        # global-batch mean on every rank without a second collective (Trainer._finish_step).
+        self.scalars_reduced = False
+        self.reduce_numel = self.dp_numel
+        if self.head_shard is None and st.arena_used == 0:
+            eng._scalars = None
+            sc = eng.scalars
+            if sc.data_ptr() == st.arena.data_ptr() and self.dp_numel == st.n:
+                self.reduce_numel = st.n + 32
+                self.scalars_reduced = True
 
     def _try_symmetric_memory(self, eng, st, strict, own_kernel=True):
         try:
@@ -298,7 +304,11 @@ class DataParallel(object):
                 raise
 
     def allreduce_gradients(self):
-        g = self.trainer.engine.store.grads[:self.dp_numel]
+        st = self.trainer.engine.store
+        if self.scalars_reduced and self.grad_dtype != "bf16":
+            g = st.grads_ext[:self.reduce_numel]         # gradients + the step's loss scalars
+        else:
+            g = st.grads[:self.dp_numel]
         if self._mm is not None and self.grad_dtype != "bf16":
             self.allreduce_range(0, g.numel())
             return
@@ -331,19 +341,6 @@ class DataParallel(object):
             L.check(L.load().xv_dp_allreduce_p2p(C.c_void_p(m["bufs"]), C.c_void_p(m["flags"]), L.ptr(m["epoch"]), self.rank,
                                                  self.world, C.c_int64(lo), C.c_int64(hi - lo), grid, L.stream_ptr()))
         self.trainer.engine.launches += 1
-
-    def allreduce_bucket_async(self, which):
-        """Enqueue the sum all-reduce of one gradient bucket on NCCL's stream (ordered after the work already on the
-        current stream) and return immediately, so later kernels of the current stream overlap it."""
-        g = self.trainer.engine.store.grads[:self.dp_numel]
-        t = g[self.split:] if which == "head" else g[:self.split]
-        if self.world > 1 and t.numel() > 0:
-            self._pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.comm.group, async_op=True))
-
-    def wait_all(self):
-        for w in self._pending:
-            w.wait()          # the current stream waits for the collective; the host does not block
-        self._pending = []
 
     def mean_scalar(self, local_mean_scaled):
         # each rank's loss scalar is sum_i CE_i / (N*B): the global mean is their sum

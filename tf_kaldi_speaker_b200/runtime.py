@@ -247,6 +247,7 @@ class FrameAct(object):
         self.bn_bwd = None        # (y, scale, shift, mean, rstd, neg_slope, dgamma, dbeta) of the layer that produced us
         self.bn_reduced = False   # dgamma / dbeta already accumulated by the consumer's dgrad epilogue
         self.pool_sums = None     # [B, 4, C] sums of the fused pooling forward (BN backward reductions without a pass over y)
+        self.bias = None          # layer bias of a pre-BN tensor (stored bias-free)
         self._materialize = None
 
     def materialize(self):
@@ -256,7 +257,10 @@ class FrameAct(object):
 
     def dense(self):
         """fp32 [B, valid, C] copy (inspection / endpoints only; uniform valid length)."""
-        return self.materialize().view(self.B, self.T, self.ld)[:, :self.valid, :self.C].float()
+        d = self.materialize().view(self.B, self.T, self.ld)[:, :self.valid, :self.C].float()
+        if self.bias is not None:        # pre-BN tensors are stored bias-free
+            d = d + self.bias[:self.C]
+        return d
 
     def lengths_ptr(self):
         return L.ptr(self.lengths)
@@ -314,7 +318,10 @@ class Engine(object):
         if int(info[1]) != 10:
             raise L.XvError("xvector_b200 kernels are sm_100a only (found cc %d.%d)" % (info[1], info[2]))
         self.store = ParamStore(self.device)
-        self.ws = {}
+        self.ws = {}                     # (name, shape, dtype) -> view
+        self._flat = {}                  # (name, dtype) -> backing allocation of the scratch buffers (largest shape seen)
+        self._step_shapes = {}
+        self.ws_generation = 0           # bumped whenever a backing allocation is replaced by a larger one
         self._arena_bufs = set()
         self.tape = []
         self.penalties = []
@@ -337,8 +344,6 @@ class Engine(object):
         self._side = None
         self._side_used = False
         self._head_prefetch = None       # (kernel name, normalize) whose bf16 operand the side stream is preparing
-        self._gemm_cap_left, self._gemm_cap = 0, 0
-        self._side2 = None               # second side stream: the overlapped gradient exchange of the head bucket
         self.head_shard = None           # parallel.HeadShard: the speaker matrix is split by columns over the ranks
         self.sync_bn = None              # parallel.SyncBN: batch-norm statistics over the GLOBAL batch (all ranks)
         self.segmenter = None            # SegmentedGraph while a step containing collectives is being captured
@@ -403,10 +408,34 @@ class Engine(object):
                     self._arena_bufs.add(key)
                     t.zero_()
                     return t
-            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            if zero:
+                t = torch.zeros(shape, dtype=dtype, device=self.device)
+                self.ws[key] = t
+                return t
+            # Scratch buffers are backed by ONE flat allocation per name, sized for the largest shape seen: the training
+            # loop draws a new segment length per batch (data_loader.py:273, 200..400 frames), and a full set of activations
+            # per distinct length would not fit in HBM.  Every length sees the same base address; a captured step of one
+            # length stays valid as long as no buffer has to grow (ws_generation; Trainer.reserve sizes them up front).
+            numel = int(np.prod(shape))
+            fkey = (name, dtype)
+            prev = self._step_shapes.get(name)
+            if prev is not None and prev != tuple(shape):      # same name, two shapes inside one step: never alias those
+                fkey = (name, dtype, tuple(shape))
+            self._step_shapes[name] = tuple(shape)
+            flat = self._flat.get(fkey)
+            if flat is None or flat.numel() < numel:
+                if flat is not None:
+                    self.ws_generation += 1
+                    for k in [k for k in self.ws if len(k) == 3 and k[0] == name and k[2] == dtype and k not in self._arena_bufs]:
+                        del self.ws[k]
+                flat = torch.zeros(numel, dtype=dtype, device=self.device)
+                self._flat[fkey] = flat
+            t = flat[:numel].view(*shape)
             self.ws[key] = t
         elif zero and key not in self._arena_bufs:
             t.zero_()
+        else:
+            self._step_shapes.setdefault(name, tuple(shape))
         return t
 
     def call(self, fn, *args):
@@ -415,34 +444,35 @@ class Engine(object):
 
     def gemm(self, *a, **kw):
         self.launches += 1
-        if self._gemm_cap_left > 0:          # leave SMs to the exchange kernel running beside the next few GEMMs
-            L.check(self.lib.xv_gemm_set_cta_limit(self._gemm_cap))
-            try:
-                L.gemm(*a, **kw)
-            finally:
-                self._gemm_cap_left -= 1
-                L.check(self.lib.xv_gemm_set_cta_limit(0))
-            return
         L.gemm(*a, **kw)
 
-    def cap_next_gemms(self, count, max_ctas):
-        self._gemm_cap_left, self._gemm_cap = int(count), int(max_ctas)
-
     def splits_for(self, M, N, K, max_splits=64, min_kb=4):
-        """Split-K factor of an f32-output GEMM: the persistent grid runs ceil(tiles*s / SMs) rounds of equal-length
-        work units, so SM occupancy is tiles*s / (rounds * SMs).  Pick the smallest s within 6 % (relative) of the best
-        occupancy (fewer splits = fewer TMA reduce-add epilogues); every split keeps >= ``min_kb`` 64-deep k-blocks."""
-        tiles = ((M + 127) // 128) * ((N + 255) // 256)
+        """Split-K factor of an f32-output GEMM: the persistent grid runs ceil(tiles*s / units) rounds of equal-length
+        work units, so occupancy is tiles*s / (rounds * units).  Pick the smallest s within 6 % (relative) of the best
+        occupancy (fewer splits = fewer TMA reduce-add epilogues); every split keeps >= ``min_kb`` 64-deep k-blocks.
+        Tile shape as xv_gemm_bf16 chooses it: 256 x 256 on the 74 SM pairs once there are >= 64 such tiles, else
+        128 x 128 on the 148 SMs."""
+        pair = ((M + 255) // 256) * ((N + 255) // 256)
+        single = ((M + 127) // 128) * ((N + 127) // 128)
         kb = (K + 63) // 64
         smax = max(1, min(max_splits, kb // min_kb))
-        effs = []
-        for s_ in range(1, smax + 1):
-            units = tiles * s_
-            rounds = (units + self.num_sms - 1) // self.num_sms
-            effs.append(units / float(rounds * self.num_sms))
-        best = max(effs)
-        for s_, e in enumerate(effs, 1):
-            if e >= 0.94 * best:
+        # a problem that can reach the 64 pair tiles is kept on the CTA-pair kernel (256 x 256 tiles need a third less
+        # L2 -> SM traffic per FLOP than 128 x 128 ones: tdnn5's wgrad ran 51 us on single tiles, 39 us on pairs)
+        smin = 1
+        pairs_ok = M > 128           # a single 128-row block would leave half of every pair tile empty
+        if pairs_ok and pair * smax >= 64:
+            smin = -(-64 // pair)
+        effs = {}
+        for s_ in range(smin, smax + 1):
+            if pairs_ok and pair * s_ >= 64:
+                units, cap = pair * s_, self.num_sms // 2
+            else:
+                units, cap = single * s_, self.num_sms
+            rounds = (units + cap - 1) // cap
+            effs[s_] = units / float(rounds * cap)
+        best = max(effs.values())
+        for s_ in sorted(effs):
+            if effs[s_] >= 0.94 * best:
                 return s_
         return 1
 
@@ -450,6 +480,7 @@ class Engine(object):
     def begin_step(self, training):
         self.tape = []
         self.tape_mark = None
+        self._step_shapes = {}
         self.penalties = []
         self.training = training
         sc = self.scalars                   # make sure the scalars exist before the fill
@@ -479,31 +510,13 @@ class Engine(object):
         self._side_used = True
         return torch.cuda.stream(self._side)
 
-    def fork_exchange_stream(self):
-        """Context manager: a second side stream, ordered after the work already on the current stream."""
-        if self._side2 is None:
-            self._side2 = torch.cuda.Stream(device=self.device)
-        self._side2.wait_stream(torch.cuda.current_stream())
-        return torch.cuda.stream(self._side2)
-
-    def join_exchange_stream(self):
-        if self._side2 is not None:
-            torch.cuda.current_stream().wait_stream(self._side2)
-
     def join_side_stream(self):
         if self._side_used:
             torch.cuda.current_stream().wait_stream(self._side)
             self._side_used = False
 
-    def backward(self, part=None):
-        """part=None: everything; "head": closures after the pooling mark (head, tdnn7, tdnn6); "trunk": the rest."""
-        mark = self.tape_mark if self.tape_mark is not None else 0
-        if part == "head":
-            fns, self.tape = self.tape[mark:], self.tape[:mark]
-        elif part == "trunk":
-            fns, self.tape = self.tape[:mark], []
-        else:
-            fns, self.tape = self.tape, []
+    def backward(self):
+        fns, self.tape = self.tape, []
         for fn in reversed(fns):
             fn()
         self.join_side_stream()
@@ -545,11 +558,14 @@ class Engine(object):
         # BN statistics come out of the GEMM epilogue (warp-shuffle column sums + shared-memory atomics, one global
         # atomic per tile column): +4 us on the K=512 layers against 17-45 us for a separate pass over y.
         epi_stats = use_stats and self.epilogue_stats
-        self.gemm(a_op, L.operand(W, True), R, cout_pad, K, y, epilogue=L.EPI_BF16, bias=st.view(bias),
+        # y is stored WITHOUT the layer bias: in front of a batch-norm the bias cancels (its gradient is exactly zero), so it
+        # is folded into the BN shift (inference) / the moving mean (training) instead of costing an epilogue pass; a layer
+        # without BN gets it through shift = bias.
+        self.gemm(a_op, L.operand(W, True), R, cout_pad, K, y, epilogue=L.EPI_BF16,
                   col_sum=stats[0] if epi_stats else None, col_sumsq=stats[1] if epi_stats else None,
                   seg_len=x.T, seg_valid=valid)
         if use_stats and not epi_stats:
-            self.call(self.lib.xv_col_stats, L.ptr(y), L.ptr(st.view(bias)), C.c_int64(R), cout_pad, C.c_int64(cout_pad),
+            self.call(self.lib.xv_col_stats, L.ptr(y), L.ptr(None), C.c_int64(R), cout_pad, C.c_int64(cout_pad),
                       x.T, valid, L.ptr(lengths), L.ptr(stats[0]), L.ptr(stats[1]), L.stream_ptr())
         if use_stats and lengths is not None:
             raise NotImplementedError("training-mode BN needs one valid length per batch (data_loader.py:273)")
@@ -563,7 +579,7 @@ class Engine(object):
         count = float(x.B * valid) * (sync.world if sync is not None else 1)
         if bn is None:
             scale.fill_(1.0)
-            shift.zero_()
+            shift.copy_(st.view(bias))
             smean.zero_()
             srstd.fill_(1.0)
         elif training:
@@ -575,11 +591,13 @@ class Engine(object):
                           L.ptr(scale), L.ptr(shift), L.ptr(smean), L.ptr(srstd), cout_pad, L.stream_ptr())
         else:
             self.call(self.lib.xv_bn_finalize_infer, L.ptr(st.view(bn[0])), L.ptr(st.view(bn[1])), L.ptr(st.view(bn[2])),
-                      L.ptr(st.view(bn[3])), C.c_float(BN_EPS), L.ptr(scale), L.ptr(shift), cout_pad, L.stream_ptr())
+                      L.ptr(st.view(bn[3])), L.ptr(st.view(bias)), C.c_float(BN_EPS), L.ptr(scale), L.ptr(shift), cout_pad,
+                      L.stream_ptr())
         alpha_t = None if alpha is None else st.view(alpha)
         lp = L.ptr(lengths)
         ya = FrameAct(y, x.B, x.T, valid, cout, lengths, name + "/y")
         ya.affine = (scale, shift)
+        ya.bias = st.view(bias)          # endpoints["tdnnN_conv"].dense() adds it back (the reference's tensor carries it)
         aa = FrameAct(None, x.B, x.T, valid, cout, lengths, name + "/a", ld=cout_pad)
 
         def apply_now():
@@ -732,6 +750,10 @@ class Engine(object):
         self.call(self.lib.xv_att_pool_fwd, L.ptr(vd), L.ptr(w), L.ptr(out), L.ptr(out3), B, H, T, valid, lp, value.C, cpad,
                   C.c_int64(cpad), s())
         gram = None
+        if penalty_coef != 0.0 and self.inv_global_batch is not None:
+            # data parallel: the kernels divide by the rank-local B, the penalty (pooling.py:185-188) by the GLOBAL batch
+            # -- gradients and the scalar are summed over the ranks afterwards, like the head's 1/(N*B)
+            penalty_coef = penalty_coef * (B * self.inv_global_batch)
         if penalty_coef != 0.0:
             gram = self.buf("att/gram", (B, H, H), torch.float32)
             self.call(self.lib.xv_att_penalty_fwd, L.ptr(w), L.ptr(gram), L.ptr(self.scalars[3:4]), B, H, T, valid, lp,
@@ -887,7 +909,7 @@ class Engine(object):
         self._head_prefetch = (kernel, int(normalize))
 
     def margin_head(self, u, labels, kernel, bias, head_type, num_outputs, training, margin=0.0, asoftmax_m=1,
-                    scaling=0.0, want_logits=False):
+                    scaling=0.0, want_logits=False, aux=None):
         """Fused normalise -> cosine GEMM -> margin -> online log-sum-exp (model/loss.py heads + l2_scaling).
         ``u`` is the network output before feature_norm; returns (loss scalar tensor view, logits or None, x)."""
         st = self.store
@@ -911,7 +933,7 @@ class Engine(object):
         self.call(self.lib.xv_head_prep_features, L.ptr(u.data), C.c_float(scaling), L.ptr(x), L.ptr(x3), L.ptr(xnorm),
                   L.ptr(urinv), B, E, L.stream_ptr())
         labels = labels.to(device=self.device, dtype=torch.int32).contiguous()
-        nblk = 2 * ((Cn + 255) // 256)      # one (max, sum) partial per 128-column half tile (two epilogue warps per row)
+        nblk = 2 * ((Cn + 127) // 128)      # one (max, sum) partial per 64-column half tile (two epilogue warps per row)
         pmax = self.buf("head/pmax", (nblk, B), torch.float32)
         psum = self.buf("head/psum", (nblk, B), torch.float32)
         tgt = self.buf("head/target", (B,), torch.float32)
@@ -933,15 +955,42 @@ class Engine(object):
                   bias=bias_t, head=h, ldc=cpad)
         self.call(self.lib.xv_head_combine, L.ptr(pmax), L.ptr(psum), L.ptr(tgt), nblk, B, C.c_float(inv_batch),
                   L.ptr(lse), L.ptr(None), L.ptr(self.scalars[0:1]), L.stream_ptr())
+        # auxiliary losses (model/loss.py:985-1037); they add to the head loss like the reference's ``loss += loss_aux``
+        aux = aux or {}
+        ring = aux.get("ring")            # (variable name of r, lambda)
+        mhe = aux.get("mhe")              # lambda
+        if ring is not None:
+            self.call(self.lib.xv_ring_loss, L.ptr(xnorm), L.ptr(st.view(ring[0])), B, C.c_float(ring[1] * inv_batch),
+                      L.ptr(self.scalars[0:1]), L.ptr(None), L.ptr(None), L.stream_ptr())
+        if mhe is not None:
+            if not normalize:
+                raise NotImplementedError("mhe_loss needs a head with normalised weights (asoftmax / AM / AAM)")
+            # data parallel: every replica evaluates the energy on its own labels; the summed scalars / gradients are the
+            # mean over replicas (the term is not linear in the batch, like per-replica batch-norm)
+            rep = 1.0 / max(1, int(round(1.0 / (inv_batch * B))))
+            mt = self.buf("head/mhe_t", (E,), torch.float32)
+            mS = self.buf("head/mhe_S", (E,), torch.float32)
+            mk = self.buf("head/mhe_kappa", (8,), torch.float32)
+            mh = self.buf("head/mhe_hist", (cpad,), torch.float32, zero=True)
+            self.call(self.lib.xv_mhe_forward, L.ptr(Wm), L.ptr(inv_norm), L.ptr(labels), B, E, Cn, C.c_int64(cpad),
+                      C.c_float(mhe), C.c_float(rep), L.ptr(mt), L.ptr(mS), L.ptr(mh), L.ptr(mk), L.ptr(self.scalars[0:1]),
+                      L.stream_ptr())
+            self.launches += 1
         if training:
             def bwd():
                 d = self.buf("head/d", (B, cpad), torch.bfloat16)
                 self.gemm(L.operand(x3, False), L.operand(wn3, True, cols=Cn), B, Cn, 3 * E, d, epilogue=L.EPI_HEAD_BWD,
                           bias=bias_t, head=h, col_sum=(st.grad(bias) if bias is not None else None))
+                if ring is not None:      # d ring / d||x_i|| joins the margin term's gnorm; d ring / dr is a scalar
+                    self.call(self.lib.xv_ring_loss, L.ptr(xnorm), L.ptr(st.view(ring[0])), B, C.c_float(ring[1] * inv_batch),
+                              L.ptr(None), L.ptr(gnorm), L.ptr(st.grad(ring[0])), L.stream_ptr())
                 # dWn[e, c] = sum_i x[i, e] d[i, c]
                 gw = st.grad(kernel)
                 with self.on_side_stream(self.side_utt):
                     self.gemm(L.operand(x3, True, cols=E), L.operand(d, True, cols=Cn), E, Cn, B, gw, epilogue=L.EPI_F32)
+                    if mhe is not None:
+                        self.call(self.lib.xv_mhe_backward, L.ptr(gw), L.ptr(mt), L.ptr(mS), L.ptr(mh), L.ptr(mk), E, Cn,
+                                  C.c_int64(cpad), L.stream_ptr())
                     if normalize:
                         self.call(self.lib.xv_head_finish_dw, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), E, cpad, L.stream_ptr())
                 # dx[i, e] = sum_c d[i, c] wn[e, c]
@@ -950,7 +999,7 @@ class Engine(object):
                 self.gemm(L.operand(d, False, cols=Cn), L.operand(wn3, False, rows=E, cols=Cn), B, E, Cn, dxg,
                           epilogue=L.EPI_F32, splits=sp)
                 du = self.buf(u.name + "/grad", (B, E), torch.float32)
-                use_margin = head_type != L.HEAD_SOFTMAX
+                use_margin = head_type != L.HEAD_SOFTMAX or ring is not None
                 self.call(self.lib.xv_head_finish_dx, L.ptr(dxg), L.ptr(gnorm if use_margin else None), L.ptr(x),
                           L.ptr(xnorm), L.ptr(u.data), L.ptr(urinv), C.c_float(scaling), L.ptr(du), B, E, L.stream_ptr())
                 u.grad = du
@@ -997,7 +1046,7 @@ class Engine(object):
                   L.ptr(urinv), R, E, s())
         lab = self.buf("head/labels_shard", (R,), torch.int32)
         self.call(self.lib.xv_head_local_labels, L.ptr(l_all), sh.lo, Cn, L.ptr(lab), R, s())
-        nblk = 2 * ((Cn + 255) // 256)
+        nblk = 2 * ((Cn + 127) // 128)
         pmax = self.buf("head/pmax", (nblk, R), torch.float32)
         psum = self.buf("head/psum", (nblk, R), torch.float32)
         tgt = self.buf("head/target", (R,), torch.float32, zero=True)       # written by the owning shard only

@@ -41,8 +41,6 @@ def run(shard, args, rank, world, x, y):
     pd["head_class_shard"] = bool(shard) and args.variant == "shard"
     pd["dp_grad_dtype"] = "bf16" if (shard and args.variant == "bf16") else "fp32"
     pd["dp_allreduce"] = args.variant if (shard and args.variant in ("symm", "multimem")) else "nccl"
-    if shard and args.variant == "bucket":
-        pd["dp_allreduce"], pd["dp_bucket_overlap"] = "multimem", True
     tr = Trainer(ParamsPlain(**pd), "/tmp/xv_shardcheck_%d_%d" % (int(shard), rank))
     tr.build("train", bench.D, args.loss, args.speakers)
     dp = parallel.DataParallel(tr, args.batch)
@@ -85,7 +83,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--speakers", type=int, default=1003)
     ap.add_argument("--loss", default="additive_angular_margin_softmax")
-    ap.add_argument("--variant", default="shard", choices=["shard", "bf16", "symm", "multimem", "bucket"],
+    ap.add_argument("--variant", default="shard", choices=["shard", "bf16", "symm", "multimem"],
                     help="trainer B: class-sharded head, or the replicated head with the bf16 gradient all-reduce")
     args = ap.parse_args()
     rank, world = parallel.init_from_env("nccl")
@@ -134,7 +132,7 @@ def main():
                                     "bf16": "bf16 gradient all-reduce vs fp32 all-reduce (NCCL, %d ranks)",
                                     "symm": "symmetric-memory all-reduce vs NCCL all-reduce (%d ranks)",
                                     "multimem": "xv_dp_allreduce_multimem (in-graph NVLS kernel) vs NCCL all-reduce (%d ranks)",
-                                    "bucket": "in-graph two-bucket exchange overlapped with the tdnn5 backward vs NCCL all-reduce (%d ranks)"}[args.variant] % world,
+                                    }[args.variant] % world,
                           "allreduce_impl": info.get("allreduce"), "ok": bool(flag.item() > 0),
                           "loss": args.loss, "steps": args.steps, "raw_loss_replicated": [p[0] for p in la],
                           "raw_loss_sharded": [p[0] for p in lb], "max_rel_raw_loss": lerr, "max_rel_total_loss": terr,

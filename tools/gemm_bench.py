@@ -50,20 +50,18 @@ def main():
         print("%-22s M=%6d N=%5d K=%6d  ours %7.1f us %7.1f TF/s | cuBLAS %7.1f us %7.1f TF/s"
               % (name, M, N, K, us, fl / us / 1e6, us_ref, fl / us_ref / 1e6), flush=True)
 
-    for name, k, cin, cout, stats in (("tdnn1 fwd", 1, 192, 512, False), ("tdnn2 fwd", 5, 512, 512, True),
-                                      ("tdnn3 fwd", 7, 512, 512, True), ("tdnn4 fwd", 1, 512, 512, False),
-                                      ("tdnn5 fwd", 1, 512, 1536, False)):
+    for name, k, cin, cout in (("tdnn1 fwd", 1, 192, 512), ("tdnn2 fwd", 5, 512, 512), ("tdnn3 fwd", 7, 512, 512),
+                               ("tdnn4 fwd", 1, 512, 512), ("tdnn5 fwd", 1, 512, 1536)):
         x, w = mk(R, cin), mk(k * cin, cout)
-        bias = torch.zeros(cout, device=dev)
         y = torch.empty(R, cout, dtype=torch.bfloat16, device=dev)
         st = torch.zeros(2, cout, device=dev)
         a_op = L.operand(x, False, div=(cin if k > 1 else 0), tap_rows=(1 if k > 1 else 0))
-        run(name, lambda: L.gemm(a_op, L.operand(w, True), R, cout, k * cin, y, epilogue=L.EPI_BF16, bias=bias,
-                                 col_sum=st[0] if stats else None, col_sumsq=st[1] if stats else None, seg_len=T,
-                                 seg_valid=T - 14), R, cout, k * cin)
-        if stats is False and k == 1 and cin == 512:
-            run(name + " +stats", lambda: L.gemm(a_op, L.operand(w, True), R, cout, k * cin, y, epilogue=L.EPI_BF16,
-                                                 bias=bias, col_sum=st[0], col_sumsq=st[1], seg_len=T, seg_valid=T - 14),
+        # as in the training step: no bias (BN follows), BN statistics of the stored tensor from the epilogue
+        run(name + " +stats", lambda: L.gemm(a_op, L.operand(w, True), R, cout, k * cin, y, epilogue=L.EPI_BF16,
+                                             col_sum=st[0], col_sumsq=st[1], seg_len=T, seg_valid=T - 14),
+            R, cout, k * cin)
+        if k == 1:
+            run(name + " plain", lambda: L.gemm(a_op, L.operand(w, True), R, cout, k * cin, y, epilogue=L.EPI_BF16),
                 R, cout, k * cin)
         if name in ("tdnn1 fwd",):
             continue
@@ -83,8 +81,8 @@ def main():
                                k * cout, dx, epilogue=L.EPI_BF16, col_sum=acc2[0], col_sumsq=acc2[1],
                                bn_bwd=(yprev, cst[0], cst[1], cst[2], cst[3], 0.0)), R, cin, k * cout)
         gw = torch.zeros(k * cin, cout, device=dev)
-        tiles = ((k * cin + 127) // 128) * ((cout + 255) // 256)
-        splits = max(1, min(32, 148 // tiles))
+        tiles = ((k * cin + 255) // 256) * ((cout + 255) // 256)
+        splits = max(1, min(32, 74 // tiles))
         run(name.replace("fwd", "wgrad") + " s%d" % splits,
             lambda: L.gemm(L.operand(x, True, div=(cin if k > 1 else 0), tap_rows=(1 if k > 1 else 0)),
                            L.operand(dy, True), k * cin, cout, R, gw, epilogue=L.EPI_F32, splits=splits), k * cin, cout, R)

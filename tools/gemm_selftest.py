@@ -61,9 +61,11 @@ def case_conv_fwd(B_=3, T=40, cin=128, cout=512, k=5, stats=True):
     cs = torch.zeros(cout, device="cuda")
     cq = torch.zeros(cout, device="cuda")
     valid = T - (k - 1)
+    # with statistics the layer passes no bias (the stored pre-BN tensor is bias-free; the sums are those of the STORED
+    # bf16 values over the valid rows)
     L.gemm(L.operand(x, False, div=cin, tap_rows=1), L.operand(w, True), R, cout, k * cin, y,
-           epilogue=L.EPI_BF16, bias=bias, col_sum=cs if stats else None, col_sumsq=cq if stats else None,
-           seg_len=T, seg_valid=valid)
+           epilogue=L.EPI_BF16, bias=None if stats else bias, col_sum=cs if stats else None,
+           col_sumsq=cq if stats else None, seg_len=T, seg_valid=valid)
     torch.cuda.synchronize()
     xf = x.float().reshape(B_, T, cin)
     wf = w.float().reshape(k, cin, cout)
@@ -71,10 +73,10 @@ def case_conv_fwd(B_=3, T=40, cin=128, cout=512, k=5, stats=True):
     for j in range(k):
         ref += xf[:, j:j + valid] @ wf[j]
     yv = y.float().reshape(B_, T, cout)[:, :valid]
-    res = {"err": _err(yv, ref + bias)}
+    res = {"err": _err(yv, ref if stats else ref + bias)}
     if stats:
-        res["err_sum"] = _err(cs, ref.sum((0, 1)))
-        res["err_sumsq"] = _err(cq, (ref ** 2).sum((0, 1)))
+        res["err_sum"] = _err(cs, yv.sum((0, 1)))
+        res["err_sumsq"] = _err(cq, (yv ** 2).sum((0, 1)))
     return res
 
 
@@ -180,6 +182,10 @@ def _cases():
         "persistent_big": lambda: case_plain(25600, 512, 512, False, True, L.EPI_BF16),
         "conv_fwd": lambda: case_conv_fwd(),
         "conv_fwd_k7": lambda: case_conv_fwd(B_=5, T=100, cin=512, cout=512, k=7),
+        "conv_fwd_bias_nostats": lambda: case_conv_fwd(stats=False),
+        "conv_fwd_stats_edges": lambda: case_conv_fwd(B_=3, T=45, cin=128, cout=1000, k=5),
+        "conv_fwd_stats_pairs": lambda: case_conv_fwd(B_=64, T=200, cin=128, cout=512, k=5),
+        "dense_stats_pairs_1536": lambda: case_conv_fwd(B_=128, T=200, cin=512, cout=1536, k=1),
         "dgrad": lambda: case_dgrad(),
         "dgrad_bnbwd_relu": lambda: case_dgrad_bnbwd(),
         "dgrad_bnbwd_lrelu_dense": lambda: case_dgrad_bnbwd(B_=3, T=50, cin=512, cout=1536, k=1, neg_slope=0.2),
