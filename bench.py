@@ -419,8 +419,160 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_extract(args):
+    """BASELINE.json config 5: embedding extraction (extract.sh path) over variable-length synthetic utterances of up to
+    10 000 frames, batched inference of TDNN + statistics pooling, utterances sharded over the ranks (no collective).
+    A "step" = one pass over this rank's fixed set of utterances.  value: padded batches resident in HBM; e2e: the public
+    call ``extract_embeddings`` on host arrays (packing, H2D, compute, D2H of the embeddings)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tf_kaldi_speaker_b200 import parallel
+    from tf_kaldi_speaker_b200 import extract as X
+    from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
+    from tf_kaldi_speaker_b200.model.trainer import Trainer
+
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    rank, world = parallel.init_from_env("nccl")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    pd = dict(PD)
+    tr = Trainer(ParamsPlain(**pd), "/tmp/xv_bench_extract_%d" % rank)
+    tr.build("predict", D)
+    n_utts = int(args.utterances)
+    rng = np.random.RandomState(1000 + rank)
+    lens = rng.randint(25, 10001, size=n_utts)
+    utts = [("utt%05d" % i, (rng.randn(1, D) + rng.randn(int(t), D)).astype(np.float32)) for i, t in enumerate(lens)]
+    frames = int(lens.sum())
+    max_batch_frames = 600000
+
+    # device-resident batches, grouped exactly as extract_embeddings groups them: utterances concatenated back to back
+    # (no padding) up to max_batch_frames rows per batch
+    groups, g, rows = [], [], 0
+    for j in range(n_utts):
+        if g and rows + lens[j] > max_batch_frames:
+            groups.append(g)
+            g, rows = [], 0
+        g.append(j)
+        rows += int(lens[j])
+    if g:
+        groups.append(g)
+    dev_groups = []
+    for g in groups:
+        ln = np.asarray([lens[j] for j in g], dtype=np.int32)
+        st0 = np.zeros_like(ln)
+        st0[1:] = np.cumsum(ln)[:-1]
+        flat = torch.from_numpy(np.concatenate([utts[j][1] for j in g], 0)).cuda()
+        dev_groups.append((flat, st0, ln))
+    groups = dev_groups
+    l0 = tr.engine.launches
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_pass():
+        for flat, st0, ln in groups:
+            tr.predict_ragged(flat, st0, ln, as_device=True)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        dev_pass()
+    l1 = tr.engine.launches
+    ms = timed(dev_pass, args.steps)
+    launches = (tr.engine.launches - l1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    def e2e_pass():
+        X.extract_embeddings(tr, utts, None, max_batch_frames=max_batch_frames)
+
+    e2e_pass()
+    t0 = time.perf_counter()
+    barrier()
+    for _ in range(args.steps):
+        e2e_pass()
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    tot_frames = frames
+    if world > 1:
+        t = torch.tensor([float(frames)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot_frames = float(t.item())
+    if rank == 0:
+        sustained, burst, how = measured_peaks()
+        fps = tot_frames * args.steps / (ms * 1e-3)
+        fps_e2e = tot_frames * args.steps / dt
+        flop_per_frame = 2 * 512 * (5 * D + 2560 + 3584 + 512 + 1500)          # SURVEY 8a (a12): 8.5 MFLOP per frame
+        line = {"metric": "extraction frames/sec (x-vector TDNN + stats pooling, variable-length utterances <= 10000 frames)",
+                "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "config 5: embedding extraction (extract.sh path), %d utterances per GPU with lengths "
+                                       "U[25, 10000] frames x %d-dim, concatenated (padding-free) batches of <= %d frames, BN in "
+                                       "inference mode, output tdnn6_dense (512-d); utterances sharded over the ranks, no "
+                                       "collective" % (n_utts, D, max_batch_frames),
+                           "utterances_per_gpu": n_utts, "frames_per_gpu": frames, "parallelism": "shard%d (independent utterances)" % world,
+                           "l2": "inputs + activations of a 600k-frame batch (>= 1.8 GB) >> 126 MB L2 (no flush needed)"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(sum(g[0].numel() for g in groups) * 4),
+                        "d2h_bytes_per_step": int(n_utts * 512 * 4), "seconds_per_step": dt / args.steps,
+                        "utterances_per_s": world * n_utts * args.steps / dt,
+                        "note": "wall clock through extract_embeddings(host arrays): packing into pinned staging on two "
+                                "threads, H2D, compute, D2H"},
+                "roofline": {"bound": "tensor", "kernel": "xv::gemm_kernel<EPI_BF16> (inference frame layers)",
+                             "achieved": fps * flop_per_frame / world / 1e12, "peak": sustained, "unit": "TFLOP/s",
+                             "frac": fps * flop_per_frame / world / 1e12 / sustained, "traffic": None,
+                             "flops_basis": "algorithmic 8.50 MFLOP per VALID frame (padding and invalid rows not counted), "
+                                            "whole pass (all kernels) over the device time",
+                             "peak_source": "%s bf16_tflops_sustained" % how}}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import xvector_oracle as O
+            torch.set_num_threads(1)             # the reference extracts on ONE CPU thread per job (trainer.py:46-50)
+            po = O.ParamsPlain(**dict(PD))
+            P = O.init_params(D, po, None, None, seed=0, dtype=torch.float32)
+            sample = [u for u in utts if 500 <= u[1].shape[0] <= 3000][:4]
+            t0 = time.perf_counter()
+            nfr = 0
+            for _, f in sample:
+                O.extract_embedding(torch.from_numpy(f), P, po)
+                nfr += f.shape[0]
+            dtc = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nfr / dtc, "unit": "frames/s", "cores": 1, "kind": "port",
+                                    "sample": "%d utterances (%d frames) through the fp32 PyTorch-CPU restatement on one "
+                                              "thread, as the reference's single_cpu extraction jobs run" % (len(sample), nfr)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="train", choices=["train", "extract"],
+                    help="train: the headline config-2 training step; extract: config 5 (embedding extraction, frames/s)")
+    ap.add_argument("--utterances", type=int, default=192, help="--workload extract: synthetic utterances per GPU")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
@@ -435,6 +587,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "extract":
+        if args.steps == 200:
+            args.steps = 5
+        run_extract(args)
     else:
         run_ours(args)
 

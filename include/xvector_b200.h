@@ -131,6 +131,14 @@ typedef struct {
   float* col_sumsq;      /* optional [N]: += sum over valid rows of its square (needs a TMA-storable out, even N) */
   xv_head_args head;
   xv_bn_bwd_args bn_bwd; /* XV_EPI_BF16 only; needs col_sum (-> dbeta) and col_sumsq (-> dgamma), N % 32 == 0 */
+  /* XV_EPI_BF16, inference: out = act(acc * affine_scale[n] + affine_shift[n]) with act(z) = z > 0 ? z : neg_slope * z --
+   * batch-norm with moving statistics (tf.layers.batch_normalization, training=False; model/trainer.py:210-225) folded
+   * into scale / shift by xv_bn_finalize_infer, plus relu / leaky_relu / identity, in the GEMM epilogue; rows outside the
+   * valid frames (seg_len / seg_valid) are written as zeros.  NULL disables.  Needs a TMA-storable output. */
+  const float* affine_scale;
+  const float* affine_shift;
+  float affine_neg_slope;
+  int32_t _pad2;
 } xv_gemm_args;
 
 XV_API int xv_gemm_bf16(const xv_gemm_args* args, void* stream);
@@ -206,6 +214,13 @@ XV_API int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int B, 
                              const int32_t* lengths, int c_real, int cpad, int64_t ld, const float* scale,
                              const float* shift, const float* alpha, int act, const float* save_mean,
                              const float* save_rstd, float* bwd_sums, void* stream);
+/* Ragged form for extraction (egs/voxceleb/v1/nnet/lib/extract.py:65-94 batched): the utterances of a batch are
+ * CONCATENATED in one flat row space -- no padding -- and segment b occupies rows [starts[b], starts[b] + lengths[b]).
+ * Frame layers in inference mode are row-local apart from the temporal taps, and a valid output row only ever reads
+ * rows of its own utterance, so the rows straddling two utterances are simply never pooled. */
+XV_API int xv_stats_pool_ragged(const void* x, float* out, void* out_split, int num_segments, const int32_t* starts,
+                                const int32_t* lengths, int c_real, int cpad, int64_t ld, const float* scale,
+                                const float* shift, const float* alpha, int act, void* stream);
 /* dgamma[c] += sum_b ca S3 + cb S4, dbeta[c] += sum_b ca S1 + cb S2 with (ca, cb) the pooling-gradient coefficients
  * da_t = ca + cb a_t derived from pooled = [mean | std] and dpooled (model/pooling.py:22-32 backward). */
 XV_API int xv_pool_bn_bwd_reduce(const float* pooled, const float* dpooled, const float* bwd_sums, int B, int seg_valid,

@@ -76,3 +76,37 @@ def test_predict_matches_reference_shapes():
     for i in range(4):
         ei = tr.predict(x[i, :lens[i]])
         assert np.allclose(er[i], ei, rtol=2e-3, atol=2e-3), i
+
+
+def test_ragged_layout_equals_one_at_a_time():
+    """Trainer.predict_ragged: utterances concatenated in one flat row space (no padding) give the embeddings of
+    one predict() call per utterance -- the frames straddling two utterances never reach a pooled row -- and the same as
+    the padded, length-masked batch."""
+    from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
+    from tf_kaldi_speaker_b200.model.trainer import Trainer
+    D = 30
+    pd = base_params()
+    tr = Trainer(ParamsPlain(**dict(pd)), "/tmp/xv_ragged_test")
+    tr.build("predict", D)
+    rng = np.random.RandomState(3)
+    lens = np.array([25, 300, 15 + 1, 77, 1000, 26, 513], dtype=np.int32)
+    feats = [(10.0 * rng.randn(1, D) + rng.randn(int(t), D) * (1 + 5 * rng.rand())).astype(np.float32) for t in lens]
+    starts = np.zeros_like(lens)
+    starts[1:] = np.cumsum(lens)[:-1]
+    er = tr.predict_ragged(np.concatenate(feats, 0), starts, lens)
+    assert er.shape == (len(lens), 512)
+    tmax = int(lens.max())
+    padded = np.zeros((len(lens), tmax, D), dtype=np.float32)
+    for i, f in enumerate(feats):
+        padded[i, :f.shape[0]] = f
+    ep = tr.predict_batch_padded(padded, lens)
+    for i, f in enumerate(feats):
+        ei = tr.predict(f)
+        assert np.allclose(er[i], ei, rtol=2e-3, atol=2e-3), (i, int(lens[i]))
+        assert np.allclose(er[i], ep[i], rtol=2e-3, atol=2e-3), (i, int(lens[i]))
+    # order independence: the neighbours of an utterance do not matter
+    perm = np.array([4, 0, 6, 2, 5, 1, 3])
+    st2 = np.zeros_like(lens)
+    st2[1:] = np.cumsum(lens[perm])[:-1]
+    e2 = tr.predict_ragged(np.concatenate([feats[i] for i in perm], 0), st2, lens[perm])
+    assert np.allclose(e2, er[perm], rtol=2e-3, atol=2e-3)

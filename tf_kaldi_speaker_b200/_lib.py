@@ -45,7 +45,9 @@ class GemmArgs(C.Structure):
     _fields_ = [("a", Operand), ("b", Operand), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("splits", C.c_int32), ("epilogue", C.c_int32), ("seg_len", C.c_int32), ("seg_valid", C.c_int32),
                 ("accumulate", C.c_int32), ("out", C.c_void_p), ("ldc", C.c_int64), ("bias", C.c_void_p),
-                ("col_sum", C.c_void_p), ("col_sumsq", C.c_void_p), ("head", HeadArgs), ("bn_bwd", BnBwdArgs)]
+                ("col_sum", C.c_void_p), ("col_sumsq", C.c_void_p), ("head", HeadArgs), ("bn_bwd", BnBwdArgs),
+                ("affine_scale", C.c_void_p), ("affine_shift", C.c_void_p), ("affine_neg_slope", C.c_float),
+                ("_pad2", C.c_int32)]
 
 
 _lib = None
@@ -92,7 +94,7 @@ def operand(t, mn_major=False, div=0, tap_rows=0, rows=None, cols=None):
 
 
 def gemm(a_op, b_op, M, N, K, out, epilogue=EPI_BF16, splits=1, bias=None, col_sum=None, col_sumsq=None,
-         seg_len=0, seg_valid=0, head=None, ldc=None, accumulate=False, bn_bwd=None):
+         seg_len=0, seg_valid=0, head=None, ldc=None, accumulate=False, bn_bwd=None, affine=None):
     args = GemmArgs()
     args.a, args.b = a_op, b_op
     args.M, args.N, args.K = M, N, K
@@ -112,4 +114,7 @@ def gemm(a_op, b_op, M, N, K, out, epilogue=EPI_BF16, splits=1, bias=None, col_s
         args.bn_bwd.scale, args.bn_bwd.shift = scale.data_ptr(), shift.data_ptr()
         args.bn_bwd.mean, args.bn_bwd.rstd = mean.data_ptr(), rstd.data_ptr()
         args.bn_bwd.neg_slope = float(neg_slope)
+    if affine is not None:       # (scale, shift, neg_slope): inference-mode BN + activation folded into the epilogue
+        args.affine_scale, args.affine_shift = affine[0].data_ptr(), affine[1].data_ptr()
+        args.affine_neg_slope = float(affine[2])
     check(load().xv_gemm_bf16(C.byref(args), stream_ptr()))

@@ -9,6 +9,7 @@
 // optimizer.  Ranks synchronise through per-block flags in a second small symmetric buffer (system-scope
 // release / acquire), so every rank must launch this kernel the same number of times with the same grid.
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
 #include "xv_internal.h"
@@ -19,6 +20,9 @@
 #endif
 #ifndef XV_AR_CFG_DEFAULT
 #define XV_AR_CFG_DEFAULT 3
+#endif
+#ifndef XV_DP_BARRIER_TIMEOUT_S
+#define XV_DP_BARRIER_TIMEOUT_S 20ull      // rank skew at the exchange is micro- to milliseconds; first-step JIT / capture < 20 s
 #endif
 
 namespace xv {
@@ -59,7 +63,21 @@ __device__ __forceinline__ void rank_barrier(uint32_t* const* flags, int rank, i
     __threadfence_system();
     st_release_sys(flags[peer] + blockIdx.x * world + rank, epoch);
     const uint32_t* mine = flags[rank] + blockIdx.x * world + peer;
+    // Bounded wait: a rank that died (or never launched this kernel) must not hang the other seven GPUs forever -- after
+    // XV_DP_BARRIER_TIMEOUT_S seconds the waiting block traps, which surfaces as a sticky CUDA error on this rank
+    // (the same policy as the GEMM's mbarrier waits, xv_ptx.cuh).
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (ld_acquire_sys(mine) < epoch) {
+      if ((++spins & 0xfff) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > XV_DP_BARRIER_TIMEOUT_S * 1000000000ull) {
+          printf("xv: rank barrier timeout (rank %d waits for rank %d, block %d, epoch %u)\n", rank, peer, blockIdx.x, epoch);
+          __trap();
+        }
+      }
     }
   }
   __syncthreads();

@@ -130,6 +130,12 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
       return set_error(XV_ERR_INVALID, "bn_bwd fusion needs the bf16 epilogue, col_sum/col_sumsq, N %% 32 == 0 and a 16-byte aligned y with ldy %% 8 == 0");
     kp.bnb = a->bn_bwd;
   }
+  if (a->affine_scale != nullptr) {
+    if (a->epilogue != XV_EPI_BF16 || !a->affine_shift || a->accumulate || a->col_sum || a->bn_bwd.y || (a->N % 4) ||
+        (reinterpret_cast<uintptr_t>(a->affine_scale) & 15) || (reinterpret_cast<uintptr_t>(a->affine_shift) & 15))
+      return set_error(XV_ERR_INVALID, "affine epilogue: bf16 output without statistics / accumulate, 16-byte aligned scale / shift, N %% 4 == 0");
+    kp.aff_scale = a->affine_scale; kp.aff_shift = a->affine_shift; kp.aff_neg_slope = a->affine_neg_slope;
+  }
   // Matrix outputs leave through TMA stores (split-K partials through the TMA reduce-add unit) whenever the layout
   // allows a tensor map; the gradient fan-in mode (read-modify-write of bf16) keeps the direct path.
   kp.use_tma_out = 0;
@@ -146,7 +152,7 @@ extern "C" int xv_gemm_bf16(const xv_gemm_args* a, void* stream) {
   int sms = 0;
   rc = device_sm_count(&sms);
   if (rc) return rc;
-  if ((kp.bnb.y != nullptr || (a->epilogue == XV_EPI_BF16 && kp.col_sum != nullptr)) && !kp.use_tma_out)
+  if ((kp.bnb.y != nullptr || kp.aff_scale != nullptr || (a->epilogue == XV_EPI_BF16 && kp.col_sum != nullptr)) && !kp.use_tma_out)
     return set_error(XV_ERR_INVALID, "column statistics / bn_bwd fusion need a TMA-storable bf16 output (16-byte aligned, no accumulate)");
   if (a->epilogue == XV_EPI_BF16 && kp.col_sum != nullptr && (a->N & 1))
     return set_error(XV_ERR_INVALID, "column statistics need an even N");

@@ -75,6 +75,9 @@ struct alignas(64) GemmKernelParams {
   float* col_sumsq;
   xv_head_args head;
   xv_bn_bwd_args bnb;     // y != nullptr: BN-backward reductions of the layer whose activation gradient this GEMM emits
+  const float* aff_scale; // != nullptr (bf16 TMA epilogue): out = act(acc * aff_scale[n] + aff_shift[n]) -- inference-mode
+  const float* aff_shift; //   batch-norm (moving statistics folded into scale / shift) + activation in the epilogue
+  float aff_neg_slope;    //   act(z) = z > 0 ? z : neg_slope * z   (relu 0, leaky_relu 0.2, identity 1)
 };
 
 // Sum over the 32 lanes of a warp of v[j] for each of 32 columns j, in 31 shuffles (recursive halving).
@@ -430,6 +433,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             if (!second) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) r1[j] = 0u;
+            }
+            if (p.aff_scale != nullptr) {
+              // folded batch-norm + activation: per-column constants are warp-uniform (every lane holds one ROW), so
+              // they arrive as broadcast 16-byte loads
+              const float ns = p.aff_neg_slope;
+              if (bc0 + 64 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.aff_scale + bc0) + j);
+                  const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.aff_shift + bc0) + j);
+                  const float4 s5 = __ldg(reinterpret_cast<const float4*>(p.aff_scale + bc0 + 32) + j);
+                  const float4 h5 = __ldg(reinterpret_cast<const float4*>(p.aff_shift + bc0 + 32) + j);
+                  const float sc[8] = {s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, s5.w};
+                  const float sh[8] = {h4.x, h4.y, h4.z, h4.w, h5.x, h5.y, h5.z, h5.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    float z0 = fmaf(__uint_as_float(r0[4 * j + q]), sc[q], sh[q]);
+                    float z1 = fmaf(__uint_as_float(r1[4 * j + q]), sc[4 + q], sh[4 + q]);
+                    z0 = z0 > 0.f ? z0 : z0 * ns;
+                    z1 = z1 > 0.f ? z1 : z1 * ns;
+                    r0[4 * j + q] = __float_as_uint(z0);
+                    r1[4 * j + q] = __float_as_uint(z1);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (bc0 + j < p.N) {
+                    const float z = fmaf(__uint_as_float(r0[j]), __ldg(p.aff_scale + bc0 + j), __ldg(p.aff_shift + bc0 + j));
+                    r0[j] = __float_as_uint(z > 0.f ? z : z * ns);
+                  }
+                  if (bc0 + 32 + j < p.N) {
+                    const float z = fmaf(__uint_as_float(r1[j]), __ldg(p.aff_scale + bc0 + 32 + j), __ldg(p.aff_shift + bc0 + 32 + j));
+                    r1[j] = __float_as_uint(z > 0.f ? z : z * ns);
+                  }
+                }
+              }
+              if (p.seg_len > 0 && !row_valid) {      // activations of invalid frames are zeros (as xv_bn_act_apply writes them)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { r0[j] = 0u; r1[j] = 0u; }
+              }
             }
             if (zero_invalid && !row_valid) {     // rows outside the valid frames are stored as zeros: no mask in the column pass
 #pragma unroll

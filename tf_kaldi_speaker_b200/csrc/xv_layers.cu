@@ -629,7 +629,8 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
                                                              const float* __restrict__ alpha,
                                                              const float* __restrict__ save_mean,
                                                              const float* __restrict__ save_rstd,
-                                                             float* __restrict__ bwd_sums) {
+                                                             float* __restrict__ bwd_sums,
+                                                             const int* __restrict__ starts) {
   pdl_entry();
   // scale != nullptr: x is the PRE-BN tensor and the pooled quantity is act(x*scale + shift) (fused tdnn5 BN+ReLU)
   constexpr int BC = 32 * CPT;     // channels per block
@@ -638,7 +639,8 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * BC + lane * CPT;
   const int L = lengths ? lengths[b] : seg_valid;
-  const __nv_bfloat16* xb = x + static_cast<long long>(b) * seg_len * ld;
+  // starts != nullptr: ragged layout -- segment b occupies rows [starts[b], starts[b] + L) of one flat row space
+  const __nv_bfloat16* xb = x + (starts ? static_cast<long long>(starts[b]) : static_cast<long long>(b) * seg_len) * ld;
   float s1[CPT], s2[CPT], x0[CPT];
   float q1[CPT], q2[CPT], q3[CPT], q4[CPT];     // dead code (and registers) when !BWD_SUMS
 #pragma unroll
@@ -1301,14 +1303,32 @@ extern "C" int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int
     dim3 grid(ceil_div(cpad, 32 * XV_POOL_CPT), B);
     XV_ACT_DISPATCH(act, (::xv::launch_pdl((stats_pool_fwd_kernel<true, XV_POOL_CPT, A_>), grid, 256, 0, s_, xb, out, o3, seg_len,
                                            seg_valid, lengths, c_real, cpad, ld, scale, shift, alpha, save_mean, save_rstd,
-                                           bwd_sums)));
+                                           bwd_sums, static_cast<const int*>(nullptr))));
   } else {
     dim3 grid(ceil_div(cpad, 256), B);
     const float* nf = nullptr;
     float* nfm = nullptr;
     XV_ACT_DISPATCH(act, (::xv::launch_pdl((stats_pool_fwd_kernel<false, 8, A_>), grid, 256, 0, s_, xb, out, o3, seg_len,
-                                           seg_valid, lengths, c_real, cpad, ld, scale, shift, alpha, nf, nf, nfm)));
+                                           seg_valid, lengths, c_real, cpad, ld, scale, shift, alpha, nf, nf, nfm,
+                                           static_cast<const int*>(nullptr))));
   }
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_stats_pool_ragged(const void* x, float* out, void* out_split, int num_segments, const int32_t* starts,
+                                    const int32_t* lengths, int c_real, int cpad, int64_t ld, const float* scale,
+                                    const float* shift, const float* alpha, int act, void* stream) {
+  if (scale && (!shift || (act == ACT_PRELU && !alpha))) return set_error(XV_ERR_INVALID, "xv_stats_pool_ragged: fused BN needs shift (and alpha for prelu)");
+  if (!x || !out || !starts || !lengths || num_segments <= 0 || cpad % 8 || c_real > cpad || ld % 8 || ld < cpad)
+    return set_error(XV_ERR_INVALID, "xv_stats_pool_ragged: bad arguments");
+  if (act < ACT_NONE || act > ACT_TANH) return set_error(XV_ERR_INVALID, "xv_stats_pool_ragged: unknown activation %d", act);
+  dim3 grid(ceil_div(cpad, 256), num_segments);
+  const float* nf = nullptr;
+  float* nfm = nullptr;
+  XV_ACT_DISPATCH(act, (::xv::launch_pdl((stats_pool_fwd_kernel<false, 8, A_>), grid, 256, 0, static_cast<cudaStream_t>(stream),
+                                         static_cast<const __nv_bfloat16*>(x), out, static_cast<__nv_bfloat16*>(out_split), 1, 0,
+                                         lengths, c_real, cpad, ld, scale, shift, alpha, nf, nf, nfm, starts)));
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }

@@ -7,10 +7,13 @@ embedding is ``endpoints[params.embedding_node]`` with BN in inference mode; opt
 
 What changes is the batching: the reference runs one ``[1, T, D]`` ``sess.run`` per utterance on one CPU thread
 (``extract.py:90``, ``trainer.py:46-50``).  Here the input is STREAMED in bounded windows (``window_utts`` utterances /
-``window_frames`` frames: memory stays O(window), output is written window by window in input order); inside a window
-the chunks are length-sorted and packed into padded ``[N, Tmax, D]`` batches (Tmax bucketed to a multiple of 256
-frames); packer threads fill pinned staging buffers for the next batches while the GPU runs the current one, and the
-length-masked statistics pooling keeps every row independent of its padding, so batching does not change any result.
+``window_frames`` frames: memory stays O(window), output is written window by window in input order).  With statistics
+pooling the chunks of a batch are simply CONCATENATED in one flat row space (``Trainer.predict_ragged``): frame layers in
+inference mode are row-local apart from the temporal taps, a valid frame never reads rows of a neighbouring utterance,
+and the pooling kernel is given each utterance's (start, length) -- no padding, no length sorting, every batch as large
+as ``max_batch_frames`` allows.  (Attention pooling keeps the padded, length-bucketed ``[N, Tmax, D]`` batches with
+length masks.)  Packer threads fill pinned staging buffers for the next batches while the GPU runs the current one;
+neither layout changes any result.
 
 Several GPUs: the reference fans extraction out as ``nj`` independent jobs over a split data directory
 (``run_extract_embeddings.sh:68-71``); the same works here (one process per GPU, ``--gpu JOB``).  Under ``torchrun`` the
@@ -49,6 +52,17 @@ def _bucket(t, q=256):
     return max(q, (t + q - 1) // q * q)
 
 
+_COPY_THREADS = 6
+_copy_executor = None
+
+
+def _copy_pool():
+    global _copy_executor
+    if _copy_executor is None:
+        _copy_executor = ThreadPoolExecutor(max_workers=_COPY_THREADS)
+    return _copy_executor
+
+
 class _Staging(object):
     """A ring of pinned host buffers; a slot is refilled only after the H2D copy that read it has completed."""
 
@@ -83,19 +97,63 @@ def _pack(slot, group, jobs, tmax, dim):
     return batch_t, lengths
 
 
+def _pack_ragged(slot, group, jobs, dim):
+    """Packer thread, padding-free layout: the chunks of one batch back to back in slot's pinned [R, dim]."""
+    if slot["event"] is not None:
+        slot["event"].synchronize()
+    lengths = np.array([jobs[j][2].shape[0] for j in group], dtype=np.int32)
+    starts = np.zeros_like(lengths)
+    starts[1:] = np.cumsum(lengths)[:-1]
+    rows = int(lengths.sum())
+    need = rows * dim
+    if slot["buf"] is None or slot["buf"].numel() < need:
+        slot["buf"] = torch.empty(int(need * 1.25), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+    flat_t = slot["buf"][:need].view(rows, dim)
+    flat = flat_t.numpy()
+
+    def copy_range(lo, hi):          # NumPy releases the GIL inside large slice copies: the sub-copies run in parallel
+        for k in range(lo, hi):
+            flat[starts[k]:starts[k] + lengths[k]] = jobs[group[k]][2]
+    n = len(group)
+    if rows * dim * 4 < (8 << 20) or n < 2 * _COPY_THREADS:
+        copy_range(0, n)
+    else:
+        # contiguous utterance ranges of roughly equal frame counts
+        cum = np.concatenate([[0], np.cumsum(lengths)])
+        cuts = [int(np.searchsorted(cum, rows * t / _COPY_THREADS)) for t in range(_COPY_THREADS + 1)]
+        cuts[0], cuts[-1] = 0, n
+        list(_copy_pool().map(lambda ab: copy_range(*ab), [(cuts[t], cuts[t + 1]) for t in range(_COPY_THREADS) if cuts[t + 1] > cuts[t]]))
+    return flat_t, (starts, lengths)
+
+
 def _run_window(trainer, utts, jobs, max_batch_frames, normalize, fd, out, staging, pool):
     """Embed the chunks of one window and emit its utterances in input order."""
-    order = sorted(range(len(jobs)), key=lambda i: jobs[i][2].shape[0])
+    ragged = trainer.params.pooling_type == "statistics_pooling"
     groups = []
-    i = 0
-    while i < len(order):
-        tmax = _bucket(jobs[order[i]][2].shape[0])
-        group = []
-        while i < len(order) and _bucket(jobs[order[i]][2].shape[0]) == tmax and \
-                (len(group) + 1) * tmax <= max(max_batch_frames, tmax):
-            group.append(order[i])
-            i += 1
-        groups.append((tmax, group))
+    if ragged:
+        # statistics pooling: utterances are CONCATENATED (Trainer.predict_ragged) -- no padding, no length sorting, every
+        # batch as large as max_batch_frames allows
+        group, rows = [], 0
+        for i in range(len(jobs)):
+            n = jobs[i][2].shape[0]
+            if group and rows + n > max_batch_frames:
+                groups.append((0, group))
+                group, rows = [], 0
+            group.append(i)
+            rows += n
+        if group:
+            groups.append((0, group))
+    else:
+        order = sorted(range(len(jobs)), key=lambda i: jobs[i][2].shape[0])
+        i = 0
+        while i < len(order):
+            tmax = _bucket(jobs[order[i]][2].shape[0])
+            group = []
+            while i < len(order) and _bucket(jobs[order[i]][2].shape[0]) == tmax and \
+                    (len(group) + 1) * tmax <= max(max_batch_frames, tmax):
+                group.append(order[i])
+                i += 1
+            groups.append((tmax, group))
     results = {}
     pending = collections.deque()      # packed batches waiting for the GPU
     done = collections.deque()         # (group, device embeddings) whose D2H read is deferred by one batch
@@ -103,7 +161,10 @@ def _run_window(trainer, utts, jobs, max_batch_frames, normalize, fd, out, stagi
     def launch(item):
         (tmax, group), slot, fut = item
         batch_t, lengths = fut.result()
-        emb = trainer.predict_batch_padded(batch_t, lengths, as_device=True)
+        if ragged:
+            emb = trainer.predict_ragged(batch_t, lengths[0], lengths[1], as_device=True)
+        else:
+            emb = trainer.predict_batch_padded(batch_t, lengths, as_device=True)
         if torch.cuda.is_available():
             if slot["event"] is None:
                 slot["event"] = torch.cuda.Event()
@@ -121,7 +182,10 @@ def _run_window(trainer, utts, jobs, max_batch_frames, normalize, fd, out, stagi
     for g in groups:
         slot = staging.take()
         dim = jobs[g[1][0]][2].shape[1]
-        pending.append((g, slot, pool.submit(_pack, slot, g[1], jobs, g[0], dim)))
+        if ragged:
+            pending.append((g, slot, pool.submit(_pack_ragged, slot, g[1], jobs, dim)))
+        else:
+            pending.append((g, slot, pool.submit(_pack, slot, g[1], jobs, g[0], dim)))
         if len(pending) >= len(staging.slots) - 1:
             launch(pending.popleft())
     while pending:

@@ -91,7 +91,7 @@ def _bn_names(prefix):
     return (prefix + "/gamma", prefix + "/beta", prefix + "/moving_mean", prefix + "/moving_variance")
 
 
-def tdnn(features, params, is_training=None, reuse_variables=None, aux_features=None, lengths=None):
+def tdnn(features, params, is_training=None, reuse_variables=None, aux_features=None, lengths=None, ragged=None):
     """Build (= run) the TDNN.
 
     Args:
@@ -102,6 +102,8 @@ def tdnn(features, params, is_training=None, reuse_variables=None, aux_features=
         aux_features: unused by the TDNN (tdnn.py:8), accepted for compatibility.
         lengths: optional int tensor [batch] of valid input frames per row (batched variable-length extraction;
                  an extension -- the reference runs one utterance per call, extract.py:65-90).
+        ragged: optional (starts, lengths) int32 device tensors: ``features`` is then ONE row [1, sum of lengths, dim]
+                holding the utterances back to back (no padding); statistics pooling only, inference only.
     :return: (features, endpoints) -- output of the last layer and an OrderedDict of every component's output.
     """
     eng = get_engine()
@@ -133,7 +135,9 @@ def tdnn(features, params, is_training=None, reuse_variables=None, aux_features=
         x = a
 
     # Pooling layer (tdnn.py:133-143)
-    if params.pooling_type == "statistics_pooling":
+    if params.pooling_type == "statistics_pooling" and ragged is not None:
+        u = eng.stats_pool(x, training, ragged=(ragged[0], ragged[1] - 14))      # pooled-domain lengths: T - 4 - 4 - 6
+    elif params.pooling_type == "statistics_pooling":
         u = statistics_pooling(x, aux_features, endpoints, params, is_training)
     elif params.pooling_type == "self_attention":
         u = self_attention(x, aux_features, endpoints, params, is_training)

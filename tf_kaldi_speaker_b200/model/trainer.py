@@ -58,8 +58,8 @@ class Trainer(object):
         self._in_memory = False      # True once this object holds parameters newer than (or loaded from) the checkpoint
 
     # ------------------------------------------------------------------ network (trainer.py:168-188)
-    def entire_network(self, features, params, is_training, reuse_variables, lengths=None):
-        features, endpoints = self.network(features, params, is_training, reuse_variables, lengths=lengths)
+    def entire_network(self, features, params, is_training, reuse_variables, lengths=None, ragged=None):
+        features, endpoints = self.network(features, params, is_training, reuse_variables, lengths=lengths, ragged=ragged)
         endpoints["output"] = features
         if "feature_norm" in params.dict and params.feature_norm:
             assert "feature_scaling_factor" in params.dict, "If feature normalization is applied, scaling factor is necessary."
@@ -515,6 +515,28 @@ class Trainer(object):
         _, endpoints = self.entire_network(feats, self.params, False, True, lengths=ln)
         self.endpoints = endpoints
         node = endpoints[self.params.embedding_node]
+        if as_device:
+            return node.dense().float().clone()
+        return node.dense().float().cpu().numpy()
+
+    def predict_ragged(self, flat_features, starts, lengths, as_device=False):
+        """Extraction without padding: ``flat_features`` [R, D] holds the utterances back to back, utterance i occupying
+        rows [starts[i], starts[i] + lengths[i]) -> [N, E] embeddings, identical to one predict() call per utterance
+        (a valid frame never reads rows of a neighbouring utterance; rows straddling two utterances are never pooled).
+        Statistics pooling only."""
+        if self.params.pooling_type != "statistics_pooling":
+            raise NotImplementedError("predict_ragged supports statistics_pooling; use predict_batch_padded")
+        eng = self.engine
+        feats, _ = self._to_device(flat_features)
+        feats = feats.view(1, feats.shape[0], feats.shape[1])
+        st = torch.as_tensor(np.asarray(starts), dtype=torch.int32).to(eng.device, non_blocking=True)
+        ln = torch.as_tensor(np.asarray(lengths), dtype=torch.int32).to(eng.device, non_blocking=True)
+        eng.begin_step(False)
+        _, endpoints = self.entire_network(feats, self.params, False, True, ragged=(st, ln))
+        self.endpoints = endpoints
+        node = endpoints[self.params.embedding_node]
+        if not hasattr(node, "col_map"):
+            raise NotImplementedError("predict_ragged: embedding_node must be an utterance-level endpoint")
         if as_device:
             return node.dense().float().clone()
         return node.dense().float().cpu().numpy()

@@ -336,6 +336,7 @@ class Engine(object):
         self.capturing = False           # True while a CUDA graph of the step is being captured
         self.epilogue_stats = True       # False: BN batch statistics from the separate xv_col_stats pass (tests)
         self.fuse_bn_bwd = True          # dgrad epilogues accumulate the producer layer's BN dgamma / dbeta
+        self.fold_inference_bn = True    # inference: BN (moving statistics) + relu in the GEMM epilogue, no separate apply pass
         self.side_wgrad = False          # frame-level wgrad GEMMs on a second stream: measured 1.067 vs 1.056 ms (no gain)
         # utterance-level weight-gradient work (tdnn6 / tdnn7 / head dW GEMMs, head_finish_dw) and the head's weight
         # normalisation run on a second stream: the utterance-level chain is ~20 dependent, latency-bound launches that
@@ -548,7 +549,12 @@ class Engine(object):
         valid = x.valid - shrink
         lengths = None if x.lengths is None else (x.lengths - shrink)
         assert K == k * x.ld, "%s: kernel rows %d != k*ld %d" % (name, K, k * x.ld)
-        y = self.buf(name + "/y", (R, cout_pad), torch.bfloat16)
+        # Inference (extraction): scale / shift are known before the GEMM (moving statistics), so BN + relu / leaky_relu run
+        # in the GEMM epilogue and the activation is written directly -- the pre-BN tensor and the separate apply pass
+        # (2 x 2 bytes per element written + read) disappear.  The pre-BN endpoint stays available lazily.
+        fold_infer = (not training and not defer_apply and alpha is None and act in (L.ACT_NONE, L.ACT_RELU, L.ACT_LRELU)
+                      and self.fold_inference_bn)
+        y = None if fold_infer else self.buf(name + "/y", (R, cout_pad), torch.bfloat16)
         use_stats = training and bn is not None
         if use_stats:
             stats = self.buf(name + "/stats", (2, cout_pad), torch.float32, zero=True)
@@ -561,9 +567,12 @@ class Engine(object):
         # y is stored WITHOUT the layer bias: in front of a batch-norm the bias cancels (its gradient is exactly zero), so it
         # is folded into the BN shift (inference) / the moving mean (training) instead of costing an epilogue pass; a layer
         # without BN gets it through shift = bias.
-        self.gemm(a_op, L.operand(W, True), R, cout_pad, K, y, epilogue=L.EPI_BF16,
-                  col_sum=stats[0] if epi_stats else None, col_sumsq=stats[1] if epi_stats else None,
-                  seg_len=x.T, seg_valid=valid)
+        def run_plain_gemm(y=y):
+            self.gemm(a_op, L.operand(W, True), R, cout_pad, K, y, epilogue=L.EPI_BF16,
+                      col_sum=stats[0] if epi_stats else None, col_sumsq=stats[1] if epi_stats else None,
+                      seg_len=x.T, seg_valid=valid)
+        if not fold_infer:
+            run_plain_gemm()
         if use_stats and not epi_stats:
             self.call(self.lib.xv_col_stats, L.ptr(y), L.ptr(None), C.c_int64(R), cout_pad, C.c_int64(cout_pad),
                       x.T, valid, L.ptr(lengths), L.ptr(stats[0]), L.ptr(stats[1]), L.stream_ptr())
@@ -595,7 +604,7 @@ class Engine(object):
                       L.stream_ptr())
         alpha_t = None if alpha is None else st.view(alpha)
         lp = L.ptr(lengths)
-        ya = FrameAct(y, x.B, x.T, valid, cout, lengths, name + "/y")
+        ya = FrameAct(y, x.B, x.T, valid, cout, lengths, name + "/y", ld=cout_pad)
         ya.affine = (scale, shift)
         ya.bias = st.view(bias)          # endpoints["tdnnN_conv"].dense() adds it back (the reference's tensor carries it)
         aa = FrameAct(None, x.B, x.T, valid, cout, lengths, name + "/a", ld=cout_pad)
@@ -615,6 +624,19 @@ class Engine(object):
         aa._materialize = apply_now
         if defer_apply:     # the consumer (statistics pooling) applies BN + activation on the fly
             aa.lazy = (y, scale, shift, alpha_t, act, smean, srstd)
+        elif fold_infer:
+            a = self.buf(name + "/a", (R, cout_pad), torch.bfloat16)
+            neg = {L.ACT_NONE: 1.0, L.ACT_RELU: 0.0, L.ACT_LRELU: 0.2}[act]
+            self.gemm(a_op, L.operand(W, True), R, cout_pad, K, a, epilogue=L.EPI_BF16, affine=(scale, shift, neg),
+                      seg_len=(x.T if lengths is None else 0), seg_valid=valid)
+            aa.data = a
+            ya.data = None
+
+            def materialize_y():            # pre-BN endpoint on demand (e.g. embedding_node = "tdnn5_dense")
+                yb = self.buf(name + "/y", (R, cout_pad), torch.bfloat16)
+                run_plain_gemm(yb)
+                ya.data = yb
+            ya._materialize = materialize_y
         else:
             apply_now()
 
@@ -686,9 +708,25 @@ class Engine(object):
             aa.needs_grad = True
         return ya, aa
 
-    def stats_pool(self, x, training):
+    def stats_pool(self, x, training, ragged=None):
         cpad = x.ld
         x.consumers += 1
+        if ragged is not None:
+            # extraction: ``x`` is one flat row space holding the concatenated utterances; (starts, lengths) int32 device
+            # tensors give each utterance's rows in the POOLED domain (see xv_stats_pool_ragged)
+            assert not training, "the ragged layout is an inference-only path (training draws one length per batch)"
+            starts, plen = ragged
+            n = int(starts.shape[0])
+            out = self.buf("pool/out", (n, 2 * cpad), torch.float32)
+            out3 = self.buf("pool/out3", (n, 6 * cpad), torch.bfloat16)
+            if x.lazy is not None:
+                y_, scale_, shift_, alpha_, act_, _, _ = x.lazy
+                src, sc, sh, al, ac = y_, scale_, shift_, alpha_, act_
+            else:
+                src, sc, sh, al, ac = x.materialize(), None, None, None, 0
+            self.call(self.lib.xv_stats_pool_ragged, L.ptr(src), L.ptr(out), L.ptr(out3), n, L.ptr(starts), L.ptr(plen), x.C,
+                      cpad, C.c_int64(cpad), L.ptr(sc), L.ptr(sh), L.ptr(al), ac, L.stream_ptr())
+            return UttAct(out, out3, "pool", (x.C, cpad))
         out = self.buf("pool/out", (x.B, 2 * cpad), torch.float32)
         out3 = self.buf("pool/out3", (x.B, 6 * cpad), torch.bfloat16)
         if x.lazy is not None:      # fused tdnn5 BN + activation: pool act(y*scale + shift) straight from y
