@@ -34,6 +34,26 @@ WORKLOAD = ("config 2: x-vector TDNN (conv k=5/5/7 x512, dense 512/1500, stats p
             "(forward, backward, optimizer, BN moving stats)")
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE line (the JSON).  Libraries print banners on file descriptor 1 (NCCL's "NCCL version
+    ..." at communicator creation, from C, past sys.stdout): point fd 1 at stderr for the whole run and keep a private
+    duplicate of the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def flops_fwd(t, d, c):
     return 2 * 512 * (5 * d * (t - 4) + 2560 * (t - 8) + (3584 + 512 + 1500) * (t - 14)) + 2 * (3000 * 512 + 512 * 512 + 512 * c)
 
@@ -56,8 +76,11 @@ def ncu_pipe():
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             j = json.load(open(p))
-            j["source"] = "profiles/" + name
-            return j
+            return {"source": "profiles/" + name, "counter": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                    "time_weighted_frame_launches_pct": j.get("time_weighted_over_the_14_frame_level_launches_pct"),
+                    "reference_point": j.get("reference_point"),
+                    "per_launch_pct": {r["launch"]: r["tensor_pipe_active_pct"] for r in j.get("launches", [])
+                                       if r["launch"].startswith(("tdnn1", "tdnn2", "tdnn3", "tdnn4", "tdnn5"))}}
     return None
 
 
@@ -178,7 +201,7 @@ def run_reference(args):
                                        "%d-segment T=200/D=30/C=7200 step, fp32 PyTorch-CPU restatement of the "
                                        "reference (TF1 not installable)" % (steps, max(1, min(args.warmup, 2)), sample)},
             "e2e": {"value": val, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -413,7 +436,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": val, "unit": "segments/s", "cores": cores, "kind": "port",
                                     "sample": "8 steps (1 warm-up) of the full 128-segment T=200/D=30/C=7200 step, fp32 "
                                               "PyTorch-CPU restatement of the reference; TF1 not installable"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -562,7 +585,7 @@ def run_extract(args):
             line["cpu_baseline"] = {"value": nfr / dtc, "unit": "frames/s", "cores": 1, "kind": "port",
                                     "sample": "%d utterances (%d frames) through the fp32 PyTorch-CPU restatement on one "
                                               "thread, as the reference's single_cpu extraction jobs run" % (len(sample), nfr)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -585,6 +608,7 @@ def main():
                     help="N>1: dtype of the gradient all-reduce (bf16 halves the NVLink bytes; opt-in)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "extract":

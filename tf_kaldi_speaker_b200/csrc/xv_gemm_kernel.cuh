@@ -255,8 +255,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
   }
   tc_fence_before();
+  __syncthreads();                      // publishes tmem_ptr inside the CTA (compute-sanitizer's racecheck does not model
+                                        // barrier.cluster as a shared-memory synchronisation point; once per kernel, free)
   if (CG == 2) cluster_sync_all();      // the peer's barriers exist before anything signals them
-  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   // Everything above (barrier init, TMEM allocation, tensor-map prefetch) is independent of earlier kernels; global

@@ -30,9 +30,17 @@ B, T, C = 32, 100, 503
 LOSS = "additive_angular_margin_softmax"
 
 
+ATTENTION = "--attention" in sys.argv      # multi-head attention pooling with a non-zero penalty term (model/pooling.py:185-189):
+                                           # the penalty is divided by the GLOBAL batch, so N ranks must reproduce the 1-GPU value
+
+
 def run(mode, rank, world, x, y):
     pd = dict(bench.PD)
     pd["sync_bn"] = (mode == "sync")
+    if ATTENTION:
+        pd.update(pooling_type="self_attention", att_key_input="tdnn4_relu", att_key_num_nodes=[256, 256],
+                  att_key_network_type=3, att_value_input="tdnn5_relu", att_value_num_nodes=[], att_value_network_type=0,
+                  att_apply_nonlinear=False, att_use_scale=True, att_num_heads=4, att_split_key=True, att_penalty_term=0.5)
     tr = Trainer(ParamsPlain(**pd), "/tmp/xv_syncbn_%s_%d" % (mode, rank))
     tr.build("train", bench.D, LOSS, C)
     if mode != "single":
@@ -43,13 +51,13 @@ def run(mode, rank, world, x, y):
     out = []
     r = tr.train_step(x, y, 0.01, 20000, fetch_loss=True)
     torch.cuda.synchronize()
-    out.append((r["raw_loss"], {k: v.copy() for k, v in st.export_tf().items()}))
+    out.append((r["raw_loss"], {k: v.copy() for k, v in st.export_tf().items()}, r["loss"]))
     for _ in range(3):
         tr.train_step(x, y, 0.01, 20000, fetch_loss=False)
     st.load_tf(p0)
     r = tr.train_step(x, y, 0.01, 20000, fetch_loss=True)
     torch.cuda.synchronize()
-    out.append((r["raw_loss"], {k: v.copy() for k, v in st.export_tf().items()}))
+    out.append((r["raw_loss"], {k: v.copy() for k, v in st.export_tf().items()}, r["loss"]))
     assert tr._static[tuple(x.shape)]["graphs"] is not None
     return p0, out
 
@@ -87,11 +95,14 @@ def main():
                 worst["%s[%s]" % (k, "eager" if which == 0 else "graph")] = (e, nk)
         replica_gap = max(replica_gap, upd_err(single[0][1], plain[0][1], k) / tol)
     lerr = max(abs(a[0] - b[0]) / max(abs(a[0]), 1e-6) for a, b in zip(single, sync))
-    ok = ok and lerr < 2e-3
+    terr = max(abs(a[2] - b[2]) / max(abs(a[2]), 1e-6) for a, b in zip(single, sync))       # total loss: includes the penalty
+    ok = ok and lerr < 2e-3 and terr < 2e-3
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"check": "SyncBN data-parallel step (%d ranks x %d rows) == 1-GPU step on the %d-row batch" % (world, B, R),
+        print(json.dumps({"check": "SyncBN data-parallel step (%d ranks x %d rows) == 1-GPU step on the %d-row batch%s"
+                                   % (world, B, R, " [self-attention pooling, 4 heads, penalty 0.5]" if ATTENTION else ""),
+                          "total_loss_single": [a[2] for a in single], "total_loss_sync_bn": [a[2] for a in sync],
                           "ok": bool(flag.item() > 0), "raw_loss_single": [a[0] for a in single],
                           "raw_loss_sync_bn": [a[0] for a in sync], "raw_loss_per_replica_bn": [a[0] for a in plain],
                           "max_rel_raw_loss": lerr, "violations": worst, "max_error_over_tolerance": ratio,
