@@ -66,4 +66,4 @@ def test_save_load_roundtrip_with_optimizer_slots(tmp_path, fmt, opt):
     pa, pb = st.export_tf(), tr2.engine.store.export_tf()
     num = sum(float(np.linalg.norm(pa[k].astype(np.float64) - pb[k])) ** 2 for k in pa)
     den = sum(float(np.linalg.norm(pa[k].astype(np.float64) - want[k])) ** 2 for k in pa)
-    assert (num / den) ** 0.5 <= 0.15, (num / den) ** 0.5          # same update up to the run-to-run rounding floor
+    assert (num / den) ** 0.5 <= 0.25, (num / den) ** 0.5          # same update up to the run-to-run rounding floor (16 segments)

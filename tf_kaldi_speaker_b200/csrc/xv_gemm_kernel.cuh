@@ -534,14 +534,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
                 }
               } else if (col_ok) {
                 // Fused BN backward of the producer layer: g = dX * act'(y*scale + shift); dbeta += g,
-                // dgamma += g * (y - mean) * rstd.  y is read with coalesced 128-byte rows, the per-column constants live
-                // in 8 registers; g uses the STORED (bf16) gradient, like the stand-alone kernel.
-                const float sc0 = __ldg(p.bnb.scale + colb), sc1 = __ldg(p.bnb.scale + colb + 1);
-                const float sh0 = __ldg(p.bnb.shift + colb), sh1 = __ldg(p.bnb.shift + colb + 1);
-                const float mu0 = __ldg(p.bnb.mean + colb), mu1 = __ldg(p.bnb.mean + colb + 1);
+                // dgamma += g * (y - mean) * rstd = (sum g*y - mean * sum g) * rstd.  y is read with coalesced 128-byte rows, the
+                // per-column constants live in registers; g uses the STORED (bf16) gradient, like the stand-alone kernel.
+                // Packed f32x2 arithmetic for the lane's two columns; rows >= M hold zeros (TMA zero fill), so no row mask.
+                const uint64_t sc2 = pack_f32x2(__float_as_uint(__ldg(p.bnb.scale + colb)), __float_as_uint(__ldg(p.bnb.scale + colb + 1)));
+                const uint64_t sh2 = pack_f32x2(__float_as_uint(__ldg(p.bnb.shift + colb)), __float_as_uint(__ldg(p.bnb.shift + colb + 1)));
+                const float ns = p.bnb.neg_slope;
                 const uint32_t* yp = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(p.bnb.y) +
                                                                        static_cast<long long>(row0) * p.bnb.ldy + colb);
                 const long long ystep = p.bnb.ldy >> 1;                   // row stride in 4-byte words
+                uint64_t sa = 0ull, qa = 0ull;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                   uint32_t yw[16];
@@ -552,17 +554,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
                   for (int rr = 0; rr < 16; ++rr) {
                     const int r = half * 16 + rr;
                     const uint32_t w = *reinterpret_cast<const uint32_t*>(sbase + r * 128 + ((jc ^ (r & 7)) << 4));
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-                    const float2 yv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[rr]));
-                    const bool live = (okmask >> r) & 1u;
-                    const float g0 = live ? f.x * (fmaf(yv.x, sc0, sh0) > 0.f ? 1.0f : p.bnb.neg_slope) : 0.f;
-                    const float g1 = live ? f.y * (fmaf(yv.y, sc1, sh1) > 0.f ? 1.0f : p.bnb.neg_slope) : 0.f;
-                    s0 += g0; s1 += g1;
-                    q0 = fmaf(g0, yv.x - mu0, q0); q1 = fmaf(g1, yv.y - mu1, q1);
+                    const uint64_t y2 = pack_f32x2(yw[rr] << 16, yw[rr] & 0xffff0000u);
+                    const uint64_t z2 = fma_f32x2(y2, sc2, sh2);
+                    const float z0 = __uint_as_float(static_cast<uint32_t>(z2)), z1 = __uint_as_float(static_cast<uint32_t>(z2 >> 32));
+                    const float f0 = __uint_as_float(w << 16), f1 = __uint_as_float(w & 0xffff0000u);
+                    const float g0 = z0 > 0.f ? f0 : f0 * ns;
+                    const float g1 = z1 > 0.f ? f1 : f1 * ns;
+                    const uint64_t g2 = pack_f32x2(__float_as_uint(g0), __float_as_uint(g1));
+                    sa = add_f32x2(sa, g2);
+                    qa = fma_f32x2(g2, y2, qa);
                   }
                 }
-                q0 *= __ldg(p.bnb.rstd + colb);
-                q1 *= __ldg(p.bnb.rstd + colb + 1);
+                s0 = __uint_as_float(static_cast<uint32_t>(sa)); s1 = __uint_as_float(static_cast<uint32_t>(sa >> 32));
+                q0 = (__uint_as_float(static_cast<uint32_t>(qa)) - __ldg(p.bnb.mean + colb) * s0) * __ldg(p.bnb.rstd + colb);
+                q1 = (__uint_as_float(static_cast<uint32_t>(qa >> 32)) - __ldg(p.bnb.mean + colb + 1) * s1) * __ldg(p.bnb.rstd + colb + 1);
               }
             }
           }

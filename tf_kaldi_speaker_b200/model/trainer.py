@@ -142,7 +142,7 @@ class Trainer(object):
     def _fwd_bwd(self, features, labels, l2_loss=True):
         """Forward + backward of one device-resident batch; gradients are left in the flat gradient buffer.
         ``l2_loss=False``: the regularisation loss is left to the optimizer kernel (same pass over the parameters)."""
-        eng = self.engine
+        eng = set_engine(self.engine)      # the operator functions (model/tdnn.py, loss.py) act on the current engine
         eng.begin_step(True)
         eng.prefetch_head_weights("softmax/output/kernel", normalize=(self.loss_type != "softmax"))
         if self._h2d_event is not None:
@@ -426,7 +426,7 @@ class Trainer(object):
 
     def valid_step(self, features, labels):
         """Loss of the validation graph (is_training=False, margins neutralised) and the output embeddings."""
-        eng = self.engine
+        eng = set_engine(self.engine)
         features, labels = self._to_device(features, labels)
         vp = self._valid_params()
         vp.dict["global_step"] = self.global_step or 0
@@ -508,7 +508,7 @@ class Trainer(object):
         pooling), so a ragged batch gives the same result as one call per utterance (extract.py:90).
         ``as_device``: return a device tensor (a copy: the workspace is reused by the next call) without synchronising,
         so the caller can overlap the next batch's upload with this one's compute."""
-        eng = self.engine
+        eng = set_engine(self.engine)
         feats, _ = self._to_device(features)
         ln = None if lengths is None else torch.as_tensor(np.asarray(lengths), dtype=torch.int32).to(eng.device, non_blocking=True)
         eng.begin_step(False)
@@ -526,7 +526,7 @@ class Trainer(object):
         Statistics pooling only."""
         if self.params.pooling_type != "statistics_pooling":
             raise NotImplementedError("predict_ragged supports statistics_pooling; use predict_batch_padded")
-        eng = self.engine
+        eng = set_engine(self.engine)
         feats, _ = self._to_device(flat_features)
         feats = feats.view(1, feats.shape[0], feats.shape[1])
         st = torch.as_tensor(np.asarray(starts), dtype=torch.int32).to(eng.device, non_blocking=True)

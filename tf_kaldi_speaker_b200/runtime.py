@@ -336,6 +336,10 @@ class Engine(object):
         self.capturing = False           # True while a CUDA graph of the step is being captured
         self.epilogue_stats = True       # False: BN batch statistics from the separate xv_col_stats pass (tests)
         self.fuse_bn_bwd = True          # dgrad epilogues accumulate the producer layer's BN dgamma / dbeta
+        import os as _os
+        # shortest dgrad K loop whose epilogue also forms the producer's BN-backward sums (a separate reduce pass over y and
+        # dX costs ~15 us at config 2; the fused column pass +8..9 us on a K >= 1536 dgrad)
+        self.fuse_bn_bwd_min_k = int(_os.environ.get("XV_FUSE_BNBWD_MINK", "1024"))
         self.fold_inference_bn = True    # inference: BN (moving statistics) + relu in the GEMM epilogue, no separate apply pass
         self.side_wgrad = False          # frame-level wgrad GEMMs on a second stream: measured 1.067 vs 1.056 ms (no gain)
         # utterance-level weight-gradient work (tdnn6 / tdnn7 / head dW GEMMs, head_finish_dw) and the head's weight
@@ -696,7 +700,7 @@ class Engine(object):
                     # Sole consumer of x and a K loop long enough to hide it: this dgrad's epilogue also forms the
                     # BN-backward reductions (dgamma, dbeta) of the layer that produced x from the dX tile it holds.
                     fuse_bn = (self.fuse_bn_bwd and x.bn_bwd is not None and x.consumers == 1 and not fan_in
-                               and k * cout_pad >= 1024 and x.ld % 32 == 0)
+                               and k * cout_pad >= self.fuse_bn_bwd_min_k and x.ld % 32 == 0)
                     bnb = x.bn_bwd[:6] if fuse_bn else None
                     self.gemm(L.operand(dy, False, div=(cout_pad if k > 1 else 0), tap_rows=(-1 if k > 1 else 0)),
                               L.operand(W, False, div=(cout_pad if k > 1 else 0), tap_rows=(x.ld if k > 1 else 0)),
