@@ -35,6 +35,10 @@ pytestmark = pytest.mark.gpu
 AAM = "additive_angular_margin_softmax"
 ARC = dict(feature_norm=True, feature_scaling_factor=64)
 C3P = dict(optimizer="momentum", momentum=0.9, asoftmax_lambda_min=10)
+C4P = dict(feature_norm=True, feature_scaling_factor=30, pooling_type="self_attention", att_key_input="tdnn4_relu",
+           att_key_num_nodes=[1500, 1500], att_key_network_type=3, att_value_input="tdnn5_relu", att_value_num_nodes=[],
+           att_value_network_type=0, att_apply_nonlinear=False, att_use_scale=True, att_num_heads=4, att_split_key=True,
+           att_penalty_term=0.01)
 
 CASES = {
     # name: (B, T, D, C, loss, extra params, lr, [global_step per call])
@@ -45,6 +49,9 @@ CASES = {
     "c2_aam_b128_t200": (128, 200, 30, 7200, AAM, ARC, 0.01, [0, 1, 2, 3, 4, 5]),
     "c2_aam_b128_t400": (128, 400, 30, 7200, AAM, ARC, 0.01, [200000, 200001, 200002, 200003, 200004, 200005]),
     "c3_asoftmax_m4_d23": (128, 200, 23, 4300, "asoftmax", C3P, 0.001, [0, 1, 10000, 10001, 100000, 1000000]),
+    # C4: multi-head self-attention pooling (nnet_conf/tdnn_amsoftmax_m0.20_linear_bn_1e-2_tdnn4_att.json with 4 heads,
+    # split key, penalty) + additive margin softmax
+    "c4_attention_h4_am": (64, 200, 30, 1000, "additive_margin_softmax", C4P, 0.01, [50000, 50001, 50002, 50003, 50004, 50005]),
 }
 
 
