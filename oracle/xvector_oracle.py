@@ -20,10 +20,11 @@ the arithmetic of these reference files (paths relative to /root/reference):
 Parity pinning status (see DESIGN.md "Oracle"):
   * margin heads (asoftmax m=1,2,4 / AM / AAM, feature_norm on/off): PINNED against the reference's own
     NumPy known-answer functions model/test_utils.py:157-318 on the reference's adversarial inputs
-    (model/tdnn.py:254-343) -- tests/test_oracle_vs_reference.py imports them from /root/reference and
-    tests/golden/heads_*.npz holds the committed vectors made by tests/golden/make_golden.py.
-  * length-masked statistics pooling: PINNED against model/multitask_v1/pooling.py:68-83 (restated inline
-    NumPy check, golden vectors committed).
+    (model/tdnn.py:254-343) -- tests/golden/make_golden.py imports them from /root/reference (build container only)
+    and commits tests/golden/heads.npz; tests/test_oracle_golden.py checks this module against it.
+  * length-masked statistics pooling: PINNED against model/multitask_v1/pooling.py:68-80 (the reference's inline
+    ``compute_stat_pooling``, exec'd from the reference source text by make_golden.py; golden vectors committed).
+  * ring loss / MHE: PINNED against model/test_utils.py:855-884 (tests/golden/aux.npz).
   * self-attention pooling: weakly pinned against model/test_utils.py:321-376 (py2 integer division fixed).
   * TDNN conv/dense/BN forward, unmasked statistics_pooling, all backward passes, optimizer and BN
     moving-stat updates, plain softmax head, extraction averaging: "parity unpinned" -- the reference

@@ -582,6 +582,75 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
   }
 }
 
+// ReLU specialisation of the fused tdnn5 backward (the pooling gradient evaluated on the fly): the upstream gradient is
+// affine in the activation, da = ca + cb*a per (segment, channel), and with ReLU a = z = scale*y + shift on the positive
+// set, so dy = scale*g + ka*y + kb collapses to ONE fma with per-(segment, channel) constants chosen by the sign of z:
+//   z > 0 :  dy = (scale^2 cb + ka) y + (scale (ca + cb shift) + kb)          z <= 0 :  dy = ka y + kb.
+// Rows stay packed in registers (16 bytes each) until they are consumed:
+// 5 instructions per element instead of 7.
+__global__ void __launch_bounds__(256, 2) bn_act_bwd_apply_pool_relu_kernel(
+    const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dy, const float* __restrict__ scale,
+    const float* __restrict__ shift, const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+    const float* __restrict__ dgamma, const float* __restrict__ dbeta, float inv_count, RowGrid rg, int C, long long ld,
+    int seg_len, int seg_valid, const int* __restrict__ lengths, PoolGradSrc ps) {
+  pdl_entry();
+  constexpr int WROWS = XV_WROWS_FUSED;
+  const WideBlock wb = wide_block(rg, seg_len, seg_valid, lengths);
+  const int c0 = wb.c0;
+  if (c0 >= C) return;
+  const RowChunk rc = wb.rc;
+  float sc[WV], sh[WV], a1[WV], b1[WV], a0[WV], b0[WV];
+  load8f(scale + c0, sc); load8f(shift + c0, sh);
+  {
+    float mu[WV], rs[WV], dg[WV], db[WV];
+    load8f(save_mean + c0, mu); load8f(save_rstd + c0, rs); load8f(dgamma + c0, dg); load8f(dbeta + c0, db);
+    PoolCoef8 pc;
+    pool_coef_load8(pc, ps, rc.b, c0, rc.L);
+#pragma unroll
+    for (int j = 0; j < WV; ++j) {
+      a0[j] = -sc[j] * rs[j] * dg[j] * inv_count;
+      b0[j] = -sc[j] * db[j] * inv_count - a0[j] * mu[j];
+      a1[j] = fmaf(sc[j] * sc[j], pc.cb[j], a0[j]);
+      b1[j] = fmaf(sc[j], fmaf(pc.cb[j], sh[j], pc.ca[j]), b0[j]);
+    }
+  }
+  const long long step = 8 * ld;
+  const long long off = (rc.m_base + rc.t0 + wb.w) * ld + c0;
+  const __nv_bfloat16* yp = y + off;
+  __nv_bfloat16* op = dy + off;
+  for (int t = rc.t0 + wb.w; t < rc.t1; t += 8 * WROWS, yp += WROWS * step, op += WROWS * step) {
+    uint4 raw[WROWS];
+    bool in[WROWS], valid[WROWS];
+#pragma unroll
+    for (int u = 0; u < WROWS; ++u) {
+      const int tt = t + 8 * u;
+      in[u] = tt < rc.t1;
+      valid[u] = tt < rc.t1 && tt < rc.L;
+      if (valid[u]) raw[u] = *reinterpret_cast<const uint4*>(yp + u * step);
+    }
+#pragma unroll
+    for (int u = 0; u < WROWS; ++u) {
+      if (!in[u]) continue;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (valid[u]) {
+        const uint32_t wds[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float y0 = __uint_as_float(wds[q] << 16), y1 = __uint_as_float(wds[q] & 0xffff0000u);
+          const bool p0 = fmaf(y0, sc[2 * q], sh[2 * q]) > 0.f, p1 = fmaf(y1, sc[2 * q + 1], sh[2 * q + 1]) > 0.f;
+          const float r0 = fmaf(p0 ? a1[2 * q] : a0[2 * q], y0, p0 ? b1[2 * q] : b0[2 * q]);
+          const float r1 = fmaf(p1 ? a1[2 * q + 1] : a0[2 * q + 1], y1, p1 ? b1[2 * q + 1] : b0[2 * q + 1]);
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(r0, r1);
+          ow[q] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      *reinterpret_cast<uint4*>(op + u * step) = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Statistics pooling (model/pooling.py:22-32; masked form multitask_v1/pooling.py:22-38).
 // grid = (Cpad/256, B); block = 256 = 8 warps striding over time; shifted one-pass moments
@@ -758,6 +827,123 @@ __global__ void __launch_bounds__(256) stats_pool_fwd_kernel(const __nv_bfloat16
       }
     }
   }
+}
+
+// ReLU specialisation of the training variant (fused tdnn5 BN + ReLU, pooled moments AND the four backward sums).
+// With u = y - y0 (y0 = a reference point near the segment's first frame, pool_ref_point), kappa = scale, z0 = kappa*y0 + shift, the activation on
+// the positive set P = {t : z_t > 0} is a = kappa*u + z0 and zero elsewhere, so THREE accumulators per channel,
+//   B0 = |P|,   B1 = sum_P u,   B2 = sum_P u^2,
+// give everything: sum a = kappa B1 + z0 B0; sum (a - m)^2 = kappa^2 B2 + 2 kappa d B1 + d^2 B0 + (L - B0) m^2 with d = z0 - m
+// (every term is O(L var): u is measured from a typical frame, no cancellation); S1 = B0, S2 = sum a,
+// S3 = rstd (B1 + e B0), S4 = rstd (kappa B2 + (kappa e + z0) B1 + z0 e B0) with e = y0 - mean.
+// 7 instructions per element instead of ~12 and three accumulators instead of six, which lets a thread own 8 channels
+// (16-byte loads, 512 contiguous bytes per warp) under 96 registers.
+// Reference point of the shifted moments: the segment's first frame if it is active, else the point on the ReLU kink
+// (z = 0) -- deviations are then measured from a TYPICAL activation value (the first frame's, or 0), which keeps the
+// variance free of cancellation exactly like the generic kernel's shift by the first frame's activation.
+__device__ __forceinline__ float pool_ref_point(float y_first, float kappa, float shift) {
+  const float z = fmaf(y_first, kappa, shift);
+  return (z > 0.f || kappa == 0.f) ? y_first : y_first - z / kappa;
+}
+
+__global__ void __launch_bounds__(256, 3) stats_pool_fwd_relu_sums_kernel(
+    const __nv_bfloat16* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ out3, int seg_len, int seg_valid,
+    const int* __restrict__ lengths, int c_real, int cpad, long long ld, const float* __restrict__ scale,
+    const float* __restrict__ shift, const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+    float* __restrict__ bwd_sums) {
+  pdl_entry();
+  constexpr int CPT = 8, BC = 32 * CPT, PR = 4;
+  __shared__ float red[8][3][BC];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * BC + lane * CPT;
+  const int L = lengths ? lengths[b] : seg_valid;
+  const __nv_bfloat16* xb = x + static_cast<long long>(b) * seg_len * ld;
+  float b0[CPT], b1[CPT], b2[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) b0[j] = b1[j] = b2[j] = 0.f;
+  if (c0 < cpad && L > 0) {
+    float sc[CPT], sh[CPT], y0[CPT];
+    load8f(scale + c0, sc);
+    load8f(shift + c0, sh);
+    load8(xb + c0, y0);
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) y0[j] = pool_ref_point(y0[j], sc[j], sh[j]);
+    const long long step = 8 * ld;
+    const __nv_bfloat16* xp = xb + static_cast<long long>(w) * ld + c0;
+    for (int t = w; t < L; t += 8 * PR, xp += PR * step) {
+      uint4 raw[PR];               // rows stay packed (4 registers each) until they are consumed
+      bool ok[PR];
+#pragma unroll
+      for (int u = 0; u < PR; ++u) {
+        ok[u] = t + 8 * u < L;
+        if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(xp + u * step);
+      }
+#pragma unroll
+      for (int u = 0; u < PR; ++u) {
+        if (!ok[u]) continue;
+        const uint32_t wds[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const float yv = __uint_as_float((j & 1) ? (wds[j >> 1] & 0xffff0000u) : (wds[j >> 1] << 16));
+          const float d = yv - y0[j];
+          if (fmaf(yv, sc[j], sh[j]) > 0.f) {
+            b0[j] += 1.0f;
+            b1[j] += d;
+            b2[j] = fmaf(d, d, b2[j]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    red[w][0][lane * CPT + j] = b0[j];
+    red[w][1][lane * CPT + j] = b1[j];
+    red[w][2][lane * CPT + j] = b2[j];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * BC + threadIdx.x;
+  if (c >= cpad) return;
+  float n0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { n0 += red[k][0][threadIdx.x]; s1 += red[k][1][threadIdx.x]; s2 += red[k][2][threadIdx.x]; }
+  float mean = 0.f, sd = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f, S4 = 0.f;
+  if (c < c_real && L > 0) {
+    const float kap = scale[c];
+    const float y0c = pool_ref_point(__bfloat162float(xb[c]), kap, shift[c]);
+    const float z0 = fmaf(y0c, kap, shift[c]);
+    const float fl = static_cast<float>(L);
+    const float invl = 1.0f / (fl + 1e-16f);
+    const float sum_a = fmaf(kap, s1, z0 * n0);
+    mean = sum_a * invl;
+    const float d = z0 - mean;
+    const float ssq = kap * kap * s2 + 2.f * kap * d * s1 + d * d * n0 + (fl - n0) * mean * mean;
+    float var = ssq * invl;
+    var = (var <= 1e-12f) ? 1e-12f : var;       // VAR2STD_EPSILON floor (mask blend, pooling.py:28-29)
+    sd = sqrtf(var);
+    const float e = y0c - save_mean[c], rs = save_rstd[c];
+    S1 = n0;
+    S2 = sum_a;
+    S3 = rs * fmaf(e, n0, s1);
+    S4 = rs * (kap * s2 + fmaf(kap, e, z0) * s1 + z0 * e * n0);
+  }
+  float* ob = out + static_cast<long long>(b) * 2 * cpad;
+  ob[c] = mean;
+  ob[cpad + c] = sd;
+  if (out3) {   // [hi | hi | lo] split copy: operand of the tdnn6 GEMM (K = 3 * 2*cpad)
+    __nv_bfloat16* o3 = out3 + static_cast<long long>(b) * 6 * cpad;
+    const __nv_bfloat16 mh = __float2bfloat16(mean), shh = __float2bfloat16(sd);
+    o3[c] = mh; o3[cpad + c] = shh;
+    o3[2 * cpad + c] = mh; o3[3 * cpad + c] = shh;
+    o3[4 * cpad + c] = __float2bfloat16(mean - __bfloat162float(mh));
+    o3[5 * cpad + c] = __float2bfloat16(sd - __bfloat162float(shh));
+  }
+  float* sb = bwd_sums + static_cast<long long>(b) * 4 * cpad;
+  sb[c] = S1;
+  sb[cpad + c] = S2;
+  sb[2 * cpad + c] = S3;
+  sb[3 * cpad + c] = S4;
 }
 
 // BN backward reductions of the layer feeding the statistics pooling, from the per-(segment, channel) sums above:
@@ -1083,6 +1269,16 @@ static int flat_mode(int which) {
   return mode[which];
 }
 
+// XV_POOL_RELU_FAST=0 selects the generic training kernel for the ReLU case too (A/B measurements)
+static bool pool_relu_fast() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("XV_POOL_RELU_FAST");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 }  // namespace xv
 
 using namespace xv;
@@ -1272,7 +1468,11 @@ extern "C" int xv_bn_act_bwd_apply(const void* y, const void* da, void* dy, cons
   }
   const RowGrid rg = make_row_grid(rows, seg_len, C, WCH, pooled ? FUSED_STREAM_ROWS : STREAM_ROWS);
   const unsigned grid = static_cast<unsigned>(ceil_div(C, WCH) * (rows / rg.seg_len) * rg.chunks);   // row chunk major, channel group minor
-  if (pooled) {
+  if (pooled && act == ACT_RELU && pool_relu_fast()) {
+    ::xv::launch_pdl((bn_act_bwd_apply_pool_relu_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream),
+                     static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dy), scale, shift, save_mean, save_rstd,
+                     dgamma, dbeta, 1.0f / count, rg, C, static_cast<long long>(ld), seg_len, seg_valid, lengths, ps);
+  } else if (pooled) {
     XV_ACT_DISPATCH(act, (::xv::launch_pdl((bn_act_bwd_apply_kernel<true, A_>), grid, 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(y), nullptr, static_cast<__nv_bfloat16*>(dy), scale, shift, save_mean,
         save_rstd, dgamma, dbeta, 1.0f / count, alpha, rg, C, ld, seg_len, seg_valid, lengths, ps)));
@@ -1299,7 +1499,11 @@ extern "C" int xv_stats_pool_fwd(const void* x, float* out, void* out_split, int
   const cudaStream_t s_ = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* o3 = static_cast<__nv_bfloat16*>(out_split);
-  if (bwd_sums) {
+  if (bwd_sums && act == ACT_RELU && pool_relu_fast()) {
+    dim3 grid(ceil_div(cpad, 256), B);
+    ::xv::launch_pdl((stats_pool_fwd_relu_sums_kernel), grid, 256, 0, s_, xb, out, o3, seg_len, seg_valid, lengths, c_real, cpad,
+                     static_cast<long long>(ld), scale, shift, save_mean, save_rstd, bwd_sums);
+  } else if (bwd_sums) {
     dim3 grid(ceil_div(cpad, 32 * XV_POOL_CPT), B);
     XV_ACT_DISPATCH(act, (::xv::launch_pdl((stats_pool_fwd_kernel<true, XV_POOL_CPT, A_>), grid, 256, 0, s_, xb, out, o3, seg_len,
                                            seg_valid, lengths, c_real, cpad, ld, scale, shift, alpha, save_mean, save_rstd,

@@ -17,11 +17,18 @@ import os
 import random
 import struct
 import time
-from multiprocessing import Event, Process, Queue
+import multiprocessing
 
 import numpy as np
 
 from .kaldi_io import CompressedFeatureReader
+
+
+# Worker processes are forked, like the reference's (data_loader.py:381-397): the children only read archives and run
+# NumPy, and a fork shares the (large) speaker -> segments tables copy-on-write.  XV_LOADER_START_METHOD=spawn|forkserver
+# trades that for a clean child (the tables are then pickled to every worker).
+_MP = multiprocessing.get_context(os.environ.get("XV_LOADER_START_METHOD", "fork"))
+Event, Process, Queue = _MP.Event, _MP.Process, _MP.Queue
 
 
 class DataOutOfRange(Exception):
