@@ -19,7 +19,9 @@
                                      // configurations (512x4, 512x8, 1024x2) measured 79-80 us (29 us instead of 45 us at 2 MB)
 #endif
 #ifndef XV_AR_CFG_DEFAULT
-#define XV_AR_CFG_DEFAULT 3
+#define XV_AR_CFG_DEFAULT 4          // 256 threads, one 16-byte vector per step, next ld_reduce issued before the current store:
+                                     // 8 x B200, 39 MB: 106-107 us against 131 us for "whole slice in flight at once" (cfg 0-3) --
+                                     // profiles/r02_allreduce_bench_8gpu.json; anything with <= 1.2 MB in flight per GPU lands there
 #endif
 #ifndef XV_DP_BARRIER_TIMEOUT_S
 #define XV_DP_BARRIER_TIMEOUT_S 20ull      // rank skew at the exchange is micro- to milliseconds; first-step JIT / capture < 20 s
@@ -27,10 +29,12 @@
 
 namespace xv {
 
-// Threads per block x 16-byte accesses in flight per thread.  The exchange is latency-bound unless a rank's whole slice is
-// in flight at once (a multimem round trip through the switch is several microseconds): 148 x 512 x 4 x 16 B = 4.8 MB in
-// flight took 8 dependent round trips for a 19.5 MB slice at N = 2 (125 us); XV_AR_CFG = 0..3 selects
-// (512,4) / (1024,4) / (512,8) / (1024,8).
+// XV_AR_CFG = 0..3: (512,4) / (1024,4) / (512,8) / (1024,8) threads x 16-byte accesses per thread, every load of a thread
+// issued before its first store (round 1); 4..12: the software-pipelined kernel below with (256,1) (256,2) (512,1) (512,2)
+// (1024,1) (128,2) (128,1) (64,1) (64,2); 13: the round-1 kernel with (256,1).  Measured on 8 x B200: the fewer bytes a GPU
+// keeps in flight (down to ~0.6 MB) the better -- with the whole slice issued at once every rank first saturates its
+// OUTBOUND link (serving the other ranks' reductions) and then its INBOUND link (receiving the broadcasts); short
+// dependent load -> store chains interleave the two phases across warps and keep both directions busy.
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -107,6 +111,38 @@ __global__ void __launch_bounds__(AR_THREADS) dp_allreduce_multimem_kernel(float
 }
 
 
+// Software-pipelined form: a thread walks its vectors U at a time and issues the NEXT group's ld_reduce before it stores the
+// current group, so that at any moment part of the grid is pulling reductions (outbound-heavy: every rank serves S bytes)
+// while another part is broadcasting results (inbound-heavy) -- both NVLink directions stay busy instead of alternating.
+template <int AR_THREADS, int U>
+__global__ void __launch_bounds__(AR_THREADS) dp_allreduce_multimem_pipe_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ flags,
+                                                                                uint32_t* __restrict__ block_epoch, int rank, int world,
+                                                                                long long n_vec) {
+  const uint32_t epoch0 = block_epoch[blockIdx.x];
+  rank_barrier(flags, rank, world, epoch0 + 1);
+  const long long per = (n_vec + world - 1) / world;
+  const long long lo = per * rank, hi = (lo + per < n_vec) ? lo + per : n_vec;
+  const long long stride = static_cast<long long>(gridDim.x) * AR_THREADS;
+  long long i = lo + static_cast<long long>(blockIdx.x) * AR_THREADS + threadIdx.x;
+  float4 cur[U], nxt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (i + u * stride < hi) cur[u] = multimem_ld_reduce_add(mc + 4 * (i + u * stride));
+  for (; i < hi; i += stride * U) {
+    const long long in = i + stride * U;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (in + u * stride < hi) nxt[u] = multimem_ld_reduce_add(mc + 4 * (in + u * stride));
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i + u * stride < hi) multimem_st(mc + 4 * (i + u * stride), cur[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+  }
+  rank_barrier(flags, rank, world, epoch0 + 2);
+  if (threadIdx.x == 0) block_epoch[blockIdx.x] = epoch0 + 2;
+}
+
 // Peer-memory variant (no multicast): rank r sums slice r over the peers' buffers with direct NVLink loads and stores the
 // result into every peer's buffer.  Per GPU and direction it moves (N-1)/N of the buffer in each phase -- the same as a
 // ring -- so it only wins where the multicast path is wasteful: at N = 2 the in-switch reduction sends a rank's OWN data
@@ -166,11 +202,10 @@ extern "C" int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_p
                                      "world <= 32, grid <= 1024)");
   int sms; int rc = device_sm_count(&sms); if (rc) return rc;
   if (grid > sms) return set_error(XV_ERR_INVALID, "xv_dp_allreduce_multimem: the grid must be co-resident (grid <= SM count)");
-  static int cfg = -1;
-  if (cfg < 0) {
-    const char* e = getenv("XV_AR_CFG");
-    cfg = e ? atoi(e) : XV_AR_CFG_DEFAULT;
-    if (cfg < 0 || cfg > 3) cfg = XV_AR_CFG_DEFAULT;
+  int cfg = XV_AR_CFG_DEFAULT;      // read per call (a launch is captured once per graph): tools/allreduce_bench.py sweeps it
+  if (const char* e = getenv("XV_AR_CFG")) {
+    cfg = atoi(e);
+    if (cfg < 0 || cfg > 13) cfg = XV_AR_CFG_DEFAULT;
   }
   float* mc = static_cast<float*>(multicast_ptr) + offset;
   uint32_t* const* fl = reinterpret_cast<uint32_t* const*>(flag_ptrs_dev);
@@ -181,6 +216,16 @@ extern "C" int xv_dp_allreduce_multimem(void* multicast_ptr, void* const* flag_p
     case 0: dp_allreduce_multimem_kernel<512, 4><<<grid, 512, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
     case 1: dp_allreduce_multimem_kernel<1024, 4><<<grid, 1024, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
     case 2: dp_allreduce_multimem_kernel<512, 8><<<grid, 512, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 4: dp_allreduce_multimem_pipe_kernel<256, 1><<<grid, 256, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 5: dp_allreduce_multimem_pipe_kernel<256, 2><<<grid, 256, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 6: dp_allreduce_multimem_pipe_kernel<512, 1><<<grid, 512, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 7: dp_allreduce_multimem_pipe_kernel<512, 2><<<grid, 512, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 8: dp_allreduce_multimem_pipe_kernel<1024, 1><<<grid, 1024, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 9: dp_allreduce_multimem_pipe_kernel<128, 2><<<grid, 128, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 10: dp_allreduce_multimem_pipe_kernel<128, 1><<<grid, 128, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 11: dp_allreduce_multimem_pipe_kernel<64, 1><<<grid, 64, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 12: dp_allreduce_multimem_pipe_kernel<64, 2><<<grid, 64, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
+    case 13: dp_allreduce_multimem_kernel<256, 1><<<grid, 256, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
     default: dp_allreduce_multimem_kernel<1024, 8><<<grid, 1024, 0, s_>>>(mc, fl, ep, rank, world, nv); break;
   }
   XV_CUDA_CHECK(cudaGetLastError());

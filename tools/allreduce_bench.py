@@ -74,7 +74,27 @@ def main():
                                                               L.ptr(epoch), rank, world, C.c_int64(0), C.c_int64(n), sms, L.stream_ptr())))
         g = plain[:n]
         t_nccl = timed(lambda: dist.all_reduce(g))
-        out[name] = {"multimem_us": t_mm, "p2p_us": t_p2p, "nccl_us": t_nccl, "correct": ok,
+        sweep = {}
+        if os.environ.get("XV_AR_SWEEP"):
+            keep = os.environ.get("XV_AR_CFG")
+            for cfg in os.environ["XV_AR_SWEEP"].split(","):
+                os.environ["XV_AR_CFG"] = cfg
+                buf.fill_(float(rank + 1))
+                torch.cuda.synchronize()
+                dist.barrier()
+                L.check(lib.xv_dp_allreduce_multimem(C.c_void_p(int(hdl.multicast_ptr)), C.c_void_p(int(hf.buffer_ptrs_dev)), L.ptr(epoch),
+                                                     rank, world, C.c_int64(0), C.c_int64(n), sms, L.stream_ptr()))
+                torch.cuda.synchronize()
+                good = bool((buf[:n] == want).all().item()) and bool((buf[n:n + 1024] == float(rank + 1)).all().item())
+                t = timed(lambda: L.check(lib.xv_dp_allreduce_multimem(C.c_void_p(int(hdl.multicast_ptr)), C.c_void_p(int(hf.buffer_ptrs_dev)),
+                                                                       L.ptr(epoch), rank, world, C.c_int64(0), C.c_int64(n), sms,
+                                                                       L.stream_ptr())))
+                sweep["cfg%s" % cfg] = {"us": t, "correct": good}
+            if keep is None:
+                os.environ.pop("XV_AR_CFG", None)
+            else:
+                os.environ["XV_AR_CFG"] = keep
+        out[name] = {"multimem_us": t_mm, "p2p_us": t_p2p, "nccl_us": t_nccl, "correct": ok, "multimem_cfg_sweep": sweep,
                      "multimem_busbw_GBs": 2.0 * (world - 1) / world * n * 4 / t_mm / 1e3,
                      "nccl_busbw_GBs": 2.0 * (world - 1) / world * n * 4 / t_nccl / 1e3}
     if rank == 0:
