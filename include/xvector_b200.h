@@ -266,6 +266,26 @@ XV_API int xv_att_scores_bwd(const void* key, const float* qpad, const float* ds
                              void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * NetVLAD / GhostVLAD pooling (replaces model/pooling.py:195-277 `ghost_vlad`; known answer model/test_utils.py:421-436).
+ * K = vlad_num_centers real clusters, KG = K + vlad_num_ghosts <= 64.  logits bf16 [B*seg_len, ldl] is the output of the
+ * `vlad_weight_affine` frame layer; post f32 [B, seg_len, KG] = softmax over the clusters (0 for frames >= length);
+ * centers f32 [KG, ldc]; res / gres f32 [B, K, cpad]; mass / sumsq / gc f32 [B, K]; out f32 [B, K*cpad] =
+ * l2_normalize(res, per cluster) (then over the whole row when final_norm), out_split (optional) bf16 [B, 3*K*cpad] =
+ * [hi | hi | lo] of out.  xv_vlad_pool_bwd: dout f32 [B, K*cpad] -> dlogits bf16 [B*seg_len, ldl] (softmax Jacobian
+ * applied, padded columns and frames zeroed), dvalue bf16 [B*seg_len, ld] (= or +=), dcenters f32 [KG, ldc] (+=).
+ * ------------------------------------------------------------------------------------------ */
+XV_API int xv_vlad_post_fwd(const void* logits, float* post, int B, int seg_len, int seg_valid, const int32_t* lengths, int KG,
+                            int ldl, void* stream);
+XV_API int xv_vlad_pool_fwd(const void* value, const float* post, const float* centers, float* res, float* mass, float* sumsq,
+                            float* out, void* out_split, int B, int seg_len, int seg_valid, const int32_t* lengths, int K,
+                            int KG, int c_real, int cpad, int64_t ld, int ldc, int final_norm, void* stream);
+XV_API int xv_vlad_pool_bwd(const void* value, const float* post, const float* centers, const float* mass, const float* sumsq,
+                            const float* out, const float* dout, float* gres, float* gc, void* dlogits, void* dvalue,
+                            float* dcenters, int B, int seg_len, int seg_valid, const int32_t* lengths, int K, int KG,
+                            int c_real, int cpad, int64_t ld, int ldl, int ldc, int final_norm, int accumulate_dvalue,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Utterance-level layers (tdnn6/tdnn7 BN + activation on f32 [B, C], model/tdnn.py:147-189).
  * mode: 0 = no BN (last_layer_no_bn), 1 = training (batch statistics), 2 = inference (moving statistics).
  * a_split: optional bf16 copy of the activation, split_terms = 1 (plain) or 3 ([hi | hi | lo]).

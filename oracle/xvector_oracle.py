@@ -92,6 +92,10 @@ def pooling_output_dim(params):
         nodes = list(params.att_value_num_nodes)
         dv = nodes[-1] if len(nodes) > 0 else _endpoint_dim(params.att_value_input, params)
         return 2 * dv
+    if params.pooling_type == "ghost_vlad":
+        nodes = list(params.vlad_value_num_nodes)
+        dv = nodes[-1] if len(nodes) > 0 else _endpoint_dim(params.vlad_value_input, params)
+        return params.vlad_num_centers * dv
     raise NotImplementedError("Not implement %s pooling" % params.pooling_type)
 
 
@@ -154,6 +158,24 @@ def init_params(dim, params, num_speakers=None, loss_type=None, seed=0, dtype=to
             bn("tdnn/attention/att_post_bn", 2 * dv)
             alpha("tdnn/attention/att_post_relu", 2 * dv)
 
+    if params.pooling_type == "ghost_vlad":       # model/pooling.py:225-258
+        def vnet(kind, in_dim, nodes):
+            d = in_dim
+            for i, n in enumerate(nodes):
+                scope = "tdnn/vlad/vlad_%s%d" % (kind, i)
+                P["%s/vlad_%s%d_dense/kernel" % (scope, kind, i)] = _glorot_uniform((d, n), gen)
+                P["%s/vlad_%s%d_dense/bias" % (scope, kind, i)] = torch.zeros(n, dtype=torch.float64)
+                bn("%s/vlad_%s%d_bn" % (scope, kind, i), n)
+                alpha("%s/vlad_%s%d_relu" % (scope, kind, i), n)
+                d = n
+            return d
+        dv = vnet("value", _endpoint_dim(params.vlad_value_input, params), list(params.vlad_value_num_nodes))
+        dk = vnet("key", _endpoint_dim(params.vlad_key_input, params), list(params.vlad_key_num_nodes))
+        kg = params.vlad_num_centers + params.vlad_num_ghosts
+        P["tdnn/vlad/vlad_weight_affine/kernel"] = _glorot_uniform((dk, kg), gen)
+        P["tdnn/vlad/vlad_weight_affine/bias"] = torch.zeros(kg, dtype=torch.float64)
+        P["tdnn/vlad/vlad_centers"] = _glorot_uniform((kg, dv), gen)
+
     pool_dim = pooling_output_dim(params)
     P["tdnn/tdnn6_dense/kernel"] = _glorot_uniform((pool_dim, 512), gen)
     P["tdnn/tdnn6_dense/bias"] = torch.zeros(512, dtype=torch.float64)
@@ -181,8 +203,9 @@ def trainable_names(P):
 
 
 def l2_regularised(name):
-    """L2 applies to kernels only (model/tdnn.py:43, model/common.py:136, model/loss.py:33,102)."""
-    return name.endswith("/kernel")
+    """L2 applies to kernels (model/tdnn.py:43, model/common.py:136, model/loss.py:33,102) and the VLAD centres
+    (model/pooling.py:256-258)."""
+    return name.endswith("/kernel") or name.endswith("/vlad_centers")
 
 
 # --------------------------------------------------------------------------------------
@@ -327,6 +350,52 @@ def self_attention(endpoints, P, params, is_training, updates, lengths=None):
     return att, penalty
 
 
+def _l2_normalize(x, dim, epsilon=1e-12):
+    """tf.nn.l2_normalize: x * rsqrt(max(sum(x^2), epsilon))."""
+    return x * torch.rsqrt(torch.clamp((x * x).sum(dim, keepdim=True), min=epsilon))
+
+
+def ghost_vlad(endpoints, P, params, is_training, updates, lengths=None, store=None):
+    """model/pooling.py:195-277 (NetVLAD / GhostVLAD).  ``lengths``: frames >= length carry no posterior mass (no reference
+    definition; the masked-pooling rule of multitask_v1/pooling.py).  ``store``: storage rounding of the frame tensors
+    (bf16 emulation)."""
+    relu_type = params.dict.get("network_relu_type", "relu")
+    q = store if store is not None else (lambda t: t)
+
+    def stack(x, kind, nodes):
+        for i, _ in enumerate(nodes):             # dense_bn_relu, model/common.py:113-146
+            name = "vlad_%s%d" % (kind, i)
+            scope = "tdnn/vlad/" + name
+            x = x @ q(P["%s/%s_dense/kernel" % (scope, name)]) + P["%s/%s_dense/bias" % (scope, name)]
+            endpoints["%s_dense" % name] = x
+            x = batch_norm(x, P, "%s/%s_bn" % (scope, name), params.batchnorm_momentum, is_training, updates, store=store,
+                           stats_from_stored=store is not None)
+            endpoints["%s_bn" % name] = x
+            x = q(_activation(x, P, "%s/%s_relu" % (scope, name), relu_type))
+            endpoints["%s_relu" % name] = x
+        return x
+
+    value = stack(endpoints[params.vlad_value_input], "value", list(params.vlad_value_num_nodes))
+    key = stack(endpoints[params.vlad_key_input], "key", list(params.vlad_key_num_nodes))
+    key = q(key @ q(P["tdnn/vlad/vlad_weight_affine/kernel"]) + P["tdnn/vlad/vlad_weight_affine/bias"])
+    A = torch.softmax(key, dim=-1)                                    # [B, L, K+G]
+    if lengths is not None:
+        t = torch.arange(A.shape[1]).reshape(1, -1, 1)
+        A = A * (t < lengths.reshape(-1, 1, 1)).to(A.dtype)
+    endpoints["vlad_weights"] = A
+    centers = P["tdnn/vlad/vlad_centers"]
+    res = torch.einsum("blk,bld->bkd", A, value) - A.sum(1).unsqueeze(2) * centers.unsqueeze(0)
+    res = res[:, :params.vlad_num_centers, :]
+    res = _l2_normalize(res, -1)
+    out = res.reshape(res.shape[0], -1)
+    if params.vlad_final_l2_norm:
+        out = _l2_normalize(out, -1)
+    endpoints["vlad_value"] = value
+    endpoints["vlad_key"] = key
+    endpoints["vlad_centers"] = centers
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # Network (model/tdnn.py:8-191) and entire_network (model/trainer.py:168-188)
 # --------------------------------------------------------------------------------------
@@ -362,6 +431,8 @@ def tdnn(features, P, params, is_training=False, updates=None, lengths=None, mir
         x = statistics_pooling(x, plen)
     elif params.pooling_type == "self_attention":
         x, penalty = self_attention(ep, P, params, is_training, updates, plen)
+    elif params.pooling_type == "ghost_vlad":
+        x = ghost_vlad(ep, P, params, is_training, updates, plen, store=bf16_ste if emulate_bf16 else None)
     else:
         raise NotImplementedError("Not implement %s pooling" % params.pooling_type)
     ep["pooling"] = x

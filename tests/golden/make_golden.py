@@ -8,6 +8,7 @@ known-answer functions (run in the build container, where /root/reference exists
   statpool.npz   the inline NumPy check ``compute_stat_pooling`` of model/multitask_v1/pooling.py:68-80, exec'd from the
                  reference source text (it lives under ``__main__``).
   aux.npz        model/test_utils.py:855-884 compute_ring_loss / compute_mhe (auxiliary losses of model/loss.py:985-1037).
+  vlad.npz       model/test_utils.py:421-436 compute_ghost_vlad (NetVLAD / GhostVLAD pooling, model/pooling.py:195-277).
   attention.npz  model/test_utils.py:321-376 compute_self_attention, exec'd from the reference source with
                  the two py2 integer divisions (``value_dim/n_heads``, ``key_dim/n_heads``) turned into ``//``.
 
@@ -159,8 +160,27 @@ def make_attention(tu):
     print("attention.npz")
 
 
+def make_vlad(tu):
+    # model/test_utils.py:421-436 compute_ghost_vlad, the known answer of model/pooling.py:195-277
+    rng = np.random.RandomState(20244)
+    out = {}
+    for tag, (k, g, final, b, l, d) in {"k8_g2": (8, 2, False, 5, 23, 40), "k4_g0_final": (4, 0, True, 4, 17, 24),
+                                        "k5_g1_final": (5, 1, True, 6, 30, 72)}.items():
+        value = (rng.randn(b, l, d) * (0.5 + rng.rand(b, 1, 1) * 2) + rng.randn(b, 1, d)).astype(np.float32)
+        key = (rng.randn(b, l, k + g) * 2).astype(np.float32)
+        centers = xavier(rng, k + g, d)
+        p = ParamsPlain()
+        p.dict.update(vlad_num_centers=k, vlad_num_ghosts=g, vlad_final_l2_norm=final)
+        o = tu.compute_ghost_vlad(value.astype(np.float64), key.astype(np.float64), centers.astype(np.float64), p)
+        out[tag + "/value"], out[tag + "/key"], out[tag + "/centers"], out[tag + "/out"] = value, key, centers, o
+        out[tag + "/cfg"] = np.array([k, g, int(final)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "vlad.npz"), **out)
+    print("vlad.npz")
+
+
 if __name__ == "__main__":
     tu = load_test_utils()
+    make_vlad(tu)
     make_heads(tu)
     make_statpool()
     make_attention(tu)

@@ -78,6 +78,30 @@ def test_self_attention(golden_dir):
         assert np.allclose(pen.item(), float(g[tag + "/penalty"]), rtol=1e-8)
 
 
+def test_ghost_vlad(golden_dir):
+    """GhostVLAD pooling (model/pooling.py:195-277) against model/test_utils.py:421-436 compute_ghost_vlad."""
+    g = np.load(os.path.join(golden_dir, "vlad.npz"))
+    for tag in ("k8_g2", "k4_g0_final", "k5_g1_final"):
+        k, gh, final = [int(v) for v in g[tag + "/cfg"]]
+        value = torch.from_numpy(g[tag + "/value"].astype(np.float64))
+        key = torch.from_numpy(g[tag + "/key"].astype(np.float64))
+        p = O.ParamsPlain(vlad_value_input="v", vlad_key_input="k", vlad_key_num_nodes=[], vlad_value_num_nodes=[],
+                          vlad_num_centers=k, vlad_num_ghosts=gh, vlad_final_l2_norm=bool(final), batchnorm_momentum=0.99)
+        # the cluster logits ARE the key here: identity weight affine
+        P = {"tdnn/vlad/vlad_weight_affine/kernel": torch.eye(k + gh, dtype=torch.float64),
+             "tdnn/vlad/vlad_weight_affine/bias": torch.zeros(k + gh, dtype=torch.float64),
+             "tdnn/vlad/vlad_centers": torch.from_numpy(g[tag + "/centers"].astype(np.float64))}
+        out = O.ghost_vlad({"v": value, "k": key}, P, p, True, None)
+        assert out.shape == (value.shape[0], k * value.shape[2])
+        assert np.allclose(out.numpy(), g[tag + "/out"], rtol=1e-9, atol=1e-12)
+        # full lengths == unmasked; a shorter length == the truncated utterance
+        full = torch.full((value.shape[0],), value.shape[1], dtype=torch.int64)
+        assert np.allclose(O.ghost_vlad({"v": value, "k": key}, P, p, True, None, full).numpy(), out.numpy(), rtol=1e-12)
+        short = O.ghost_vlad({"v": value, "k": key}, P, p, True, None, full - 5)
+        trunc = O.ghost_vlad({"v": value[:, :-5], "k": key[:, :-5]}, P, p, True, None)
+        assert np.allclose(short.numpy(), trunc.numpy(), rtol=1e-12)
+
+
 def test_aux_losses_match_reference_numpy(golden_dir):
     """Ring loss and MHE (model/loss.py:985-1037) against model/test_utils.py:855-884 (compute_ring_loss, compute_mhe)."""
     g = np.load(os.path.join(golden_dir, "aux.npz"))

@@ -109,17 +109,17 @@ def declare_attention_variables(engine, params):
             st.declare(VarSpec("tdnn/attention/att_post_relu/alpha", (2 * dv,), (2 * dvp,), row_map=idx, init=0.01))
 
 
-def _run_stack(eng, x, layers, params, training, endpoints):
+def _run_stack(eng, x, layers, params, training, endpoints, root="tdnn/attention", buf_prefix="att"):
     relu_act = activation_id(params)
     prelu = relu_act == L.ACT_PRELU
     mom = float(params.batchnorm_momentum)
     for name, cin, cout, bn, act in layers:
-        scope = "tdnn/attention/%s/%s" % (name, name)
+        scope = "%s/%s/%s" % (root, name, name)
         act_id = {"none": L.ACT_NONE, "tanh": L.ACT_TANH, "relu": relu_act}[act]
         bn_names = None
         if bn:
             bn_names = tuple(scope + "_bn/" + s for s in ("gamma", "beta", "moving_mean", "moving_variance"))
-        y, a = eng.frame_affine(x, scope + "_dense/kernel", scope + "_dense/bias", 1, cout, "att/" + name, training,
+        y, a = eng.frame_affine(x, scope + "_dense/kernel", scope + "_dense/bias", 1, cout, buf_prefix + "/" + name, training,
                                 bn=bn_names, act=act_id,
                                 alpha=(scope + "_relu/alpha") if (prelu and act == "relu") else None,
                                 unbiased_moving_var=False, momentum=mom)

@@ -1,4 +1,4 @@
-"""Temporal pooling with the reference's operator surface (model/pooling.py:9-34, 37-192).
+"""Temporal pooling with the reference's operator surface (model/pooling.py:9-34, 37-192, 195-277).
 
 statistics_pooling: per (segment, channel) mean and standard deviation over the valid frames in ONE pass over
 the bf16 activations (shifted moments, fp32 accumulation), with the masked variable-length semantics of
@@ -24,6 +24,9 @@ def pooling_output_dim(params):
         dvp = _pad_to(dv, 64)
         rows = np.concatenate([np.arange(dv), dvp + np.arange(dv)])
         return 2 * dv, 2 * dvp, rows
+    if params.pooling_type == "ghost_vlad":
+        from .vlad import vlad_output_dim
+        return vlad_output_dim(params)
     raise NotImplementedError("Not implement %s pooling" % params.pooling_type)
 
 
@@ -47,4 +50,15 @@ def declare_attention_variables(engine, params):
 def self_attention(features, aux_features, endpoints, params, is_training=None):
     """Multi-head attentive statistics pooling (model/pooling.py:37-192); see model/attention.py."""
     from .attention import self_attention as _impl
+    return _impl(features, aux_features, endpoints, params, is_training)
+
+
+def declare_vlad_variables(engine, params):
+    from .vlad import declare_vlad_variables as _decl
+    return _decl(engine, params)
+
+
+def ghost_vlad(features, aux_features, endpoints, params, is_training):
+    """NetVLAD / GhostVLAD pooling (model/pooling.py:195-277); see model/vlad.py."""
+    from .vlad import ghost_vlad as _impl
     return _impl(features, aux_features, endpoints, params, is_training)

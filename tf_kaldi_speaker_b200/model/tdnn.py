@@ -16,7 +16,8 @@ import numpy as np
 from .. import _lib as L
 from ..runtime import VarSpec, get_engine, _pad_to
 from .common import activation_id
-from .pooling import statistics_pooling, self_attention, declare_attention_variables, pooling_output_dim
+from .pooling import (statistics_pooling, self_attention, ghost_vlad, declare_attention_variables, declare_vlad_variables,
+                      pooling_output_dim)
 
 
 def _bn_specs(store, prefix, c_real, c_pad):
@@ -72,6 +73,8 @@ def declare_variables(engine, dim, params):
 
     if params.pooling_type == "self_attention":
         declare_attention_variables(engine, params)
+    elif params.pooling_type == "ghost_vlad":
+        declare_vlad_variables(engine, params)
     pool_real, pool_pad, pool_rows = pooling_output_dim(params)
     st.declare(VarSpec("tdnn/tdnn6_dense/kernel", (pool_real, 512), (pool_pad, 512), row_map=pool_rows, l2=l2,
                        shadow="split", init="glorot", fans=(pool_real, 512)))
@@ -141,6 +144,8 @@ def tdnn(features, params, is_training=None, reuse_variables=None, aux_features=
         u = statistics_pooling(x, aux_features, endpoints, params, is_training)
     elif params.pooling_type == "self_attention":
         u = self_attention(x, aux_features, endpoints, params, is_training)
+    elif params.pooling_type == "ghost_vlad":
+        u = ghost_vlad(x, aux_features, endpoints, params, is_training)
     else:
         raise NotImplementedError("Not implement %s pooling" % params.pooling_type)
     endpoints["pooling"] = u

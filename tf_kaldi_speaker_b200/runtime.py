@@ -825,6 +825,53 @@ class Engine(object):
             u.needs_grad = True
         return u, w[:, :, :valid]
 
+    def vlad_pool(self, logits, value, centers, K, G, final_norm, training):
+        """NetVLAD / GhostVLAD aggregation (model/pooling.py:249-276): posteriors = softmax of the cluster logits over the
+        K real + G ghost clusters, residuals to the centres summed over the valid frames, intra-cluster (and optionally
+        final) L2 normalisation.  logits / value: FrameAct; returns (UttAct [B, K*dv], posteriors f32 [B, T, K+G] view)."""
+        st = self.store
+        assert logits.B == value.B and logits.T == value.T and logits.valid == value.valid, \
+            "key and value must have the same length"
+        B, T, valid = value.B, value.T, value.valid
+        lp = L.ptr(value.lengths)
+        ld_, vd = logits.materialize(), value.materialize()
+        logits.consumers += 1
+        value.consumers += 1
+        KG = K + G
+        ldl, cpad, c_real = logits.ld, value.ld, value.C
+        cen = st.view(centers)                          # f32 [KG, cpad]
+        ldc = cen.shape[1]
+        s = L.stream_ptr
+        post = self.buf("vlad/post", (B, T, KG), torch.float32)
+        self.call(self.lib.xv_vlad_post_fwd, L.ptr(ld_), L.ptr(post), B, T, valid, lp, KG, ldl, s())
+        res = self.buf("vlad/res", (B, K, cpad), torch.float32)
+        mass = self.buf("vlad/mass", (B, K), torch.float32)
+        sumsq = self.buf("vlad/sumsq", (B, K), torch.float32)
+        out = self.buf("pool/out", (B, K * cpad), torch.float32)
+        out3 = self.buf("pool/out3", (B, 3 * K * cpad), torch.bfloat16)
+        self.call(self.lib.xv_vlad_pool_fwd, L.ptr(vd), L.ptr(post), L.ptr(cen), L.ptr(res), L.ptr(mass), L.ptr(sumsq),
+                  L.ptr(out), L.ptr(out3), B, T, valid, lp, K, KG, c_real, cpad, C.c_int64(cpad), ldc, int(final_norm), s())
+        u = UttAct(out, out3, "pool", None)
+        u.dense = lambda: out.view(B, K, cpad)[:, :, :c_real].reshape(B, K * c_real)
+        if training:
+            def bwd():
+                if u.grad is None:
+                    return
+                gres = self.buf("vlad/gres", (B, K, cpad), torch.float32)
+                gc = self.buf("vlad/gc", (B, K), torch.float32)
+                dl = self.buf(logits.name + "/grad", (B * T, ldl), torch.bfloat16)
+                acc_v = value.grad is not None
+                dv = value.grad if acc_v else self.buf(value.name + "/grad", (B * T, cpad), torch.bfloat16)
+                self.call(self.lib.xv_vlad_pool_bwd, L.ptr(vd), L.ptr(post), L.ptr(cen), L.ptr(mass), L.ptr(sumsq), L.ptr(out),
+                          L.ptr(u.grad), L.ptr(gres), L.ptr(gc), L.ptr(dl), L.ptr(dv), L.ptr(st.grad(centers)), B, T, valid, lp,
+                          K, KG, c_real, cpad, C.c_int64(cpad), ldl, ldc, int(final_norm), int(acc_v), s())
+                assert logits.grad is None, "the cluster logits have one consumer"
+                logits.grad = dl
+                value.grad = dv
+            self.tape.append(bwd)
+            u.needs_grad = True
+        return u, post[:, :valid, :]
+
     def utt_bn_act(self, u, bn, name, training, act=L.ACT_RELU, alpha=None, momentum=0.99):
         """BN over the batch + activation on an utterance-level tensor without a preceding dense layer
         (att_post_bn / att_post_relu, model/pooling.py:175-182).  Returns (BN output UttAct, activation UttAct)."""
