@@ -286,6 +286,31 @@ XV_API int xv_vlad_pool_bwd(const void* value, const float* post, const float* c
                             void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Metric-learning losses on the [B, E] embeddings (replace model/loss.py:358-498 semihard_triplet_loss, :501-634
+ * angular_triplet_loss, :637-705 e2e_valid_loss and model/common.py:61-110 pairwise_euc_distances / pairwise_cos_similarity;
+ * known answers model/test_utils.py:21-154, 439-650).  B <= 2048 rows.  All of them are functions of the fp32 Gram matrix:
+ *   xv_gram_f32          gram f32 [B, B] = x x^T
+ *   xv_semihard_triplet  loss[0] += scale * mean over the positive pairs of max(margin + D_ap - D_an(semi-hard), 0);
+ *   xv_angular_triplet   kind 0 = asoftmax (margin 1 / 2 / 4), 1 = additive margin, 2 = additive angular margin; hard = 0:
+ *                        mean over the violating triplets, hard = 1: hardest positive / negative per anchor;
+ *                        both also write coef f32 [B, B] (symmetric) and diag f32 [B] with
+ *   xv_pairwise_bwd      dx f32 [B, ldx] = coef x + diag o x = dLoss/dx.
+ *   work: f32 scratch of 2*B*B + 8 floats.  scale folds the replica weight of data-parallel runs.
+ *   xv_e2e_valid_loss    forward only; rows are speaker-ordered (num_speakers x num_segments, >= 2 segments), logits =
+ *                        20 * cosine to the speaker centres, the own speaker scored against the centre of its OTHER
+ *                        segments; loss[0] += scale * mean cross entropy.  work: (B + num_speakers) * E + num_speakers floats.
+ * ------------------------------------------------------------------------------------------ */
+XV_API int xv_gram_f32(const float* x, float* gram, int B, int E, int64_t ldx, void* stream);
+XV_API int xv_semihard_triplet(const float* gram, const int32_t* labels, int B, float margin, int squared, float scale,
+                               float* loss, float* coef, float* diag, float* work, void* stream);
+XV_API int xv_angular_triplet(const float* gram, const int32_t* labels, int B, int kind, float margin, int hard, float scale,
+                              float* loss, float* coef, float* diag, float* work, void* stream);
+XV_API int xv_pairwise_bwd(const float* coef, const float* diag, const float* x, float* dx, int B, int E, int64_t ldx,
+                           void* stream);
+XV_API int xv_e2e_valid_loss(const float* x, int num_speakers, int num_segments, int E, int64_t ldx, float scale, float* loss,
+                             float* work, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Utterance-level layers (tdnn6/tdnn7 BN + activation on f32 [B, C], model/tdnn.py:147-189).
  * mode: 0 = no BN (last_layer_no_bn), 1 = training (batch statistics), 2 = inference (moving statistics).
  * a_split: optional bf16 copy of the activation, split_terms = 1 (plain) or 3 ([hi | hi | lo]).

@@ -583,7 +583,138 @@ def aux_loss(x, labels, P, params):
     return total
 
 
+# --------------------------------------------------------------------------------------
+# Metric-learning losses on the embeddings (model/loss.py:358-705, model/common.py:61-110)
+# --------------------------------------------------------------------------------------
+def pairwise_euc_distances(x, squared=False):
+    """model/common.py:61-93: ||a||^2 - 2<a,b> + ||b||^2 from the Gram matrix (its diagonal gives the norms), clamped at 0;
+    the non-squared form masks exact zeros around the sqrt."""
+    dot = x @ x.t()
+    sq = torch.diagonal(dot)
+    d = torch.clamp(sq.unsqueeze(1) - 2.0 * dot + sq.unsqueeze(0), min=0.0)
+    if not squared:
+        mask = (d == 0.0).to(d.dtype)
+        d = torch.sqrt(d + mask * 1e-16) * (1.0 - mask)
+    return d
+
+
+def pairwise_cos_similarity(x, epsilon=1e-12):
+    """model/common.py:96-110."""
+    dot = x @ x.t()
+    inv = torch.rsqrt(torch.clamp((x * x).sum(-1, keepdim=True), min=epsilon))
+    return torch.clamp(dot * (inv @ inv.t()), -1.0, 1.0)
+
+
+def _masked_maximum(data, mask, dim=1):
+    m = data.amin(dim, keepdim=True)
+    return ((data - m) * mask).amax(dim, keepdim=True) + m
+
+
+def _masked_minimum(data, mask, dim=1):
+    m = data.amax(dim, keepdim=True)
+    return ((data - m) * mask).amin(dim, keepdim=True) + m
+
+
+def semihard_triplet_loss(x, labels, params):
+    """model/loss.py:358-498 (TF metric_learning triplet_semihard_loss on pairwise_euc_distances).  [x, i] indexes the
+    (anchor, positive) pair; amin / amax split the gradient evenly among ties like tf.reduce_min / reduce_max."""
+    b = x.shape[0]
+    lab = labels.reshape(-1, 1)
+    margin = float(params.margin)
+    d = pairwise_euc_distances(x, bool(params.triplet_loss_squared))
+    adjacency = lab == lab.t()
+    adj_not = ~adjacency
+    d_tile = d.repeat(b, 1)                                            # row i*b + x = d[x, :]
+    mask = adj_not.repeat(b, 1) & (d_tile > d.t().reshape(-1, 1))     # d[x, y] > d[x, i] for a negative y
+    mask_final = (mask.to(d.dtype).sum(1, keepdim=True) > 0.0).reshape(b, b).t()
+    maskf = mask.to(d.dtype)
+    negatives_outside = _masked_minimum(d_tile, maskf).reshape(b, b).t()
+    negatives_inside = _masked_maximum(d, adj_not.to(d.dtype)).repeat(1, b)
+    semi_hard = torch.where(mask_final, negatives_outside, negatives_inside)
+    loss_mat = margin + d - semi_hard
+    mask_pos = adjacency.to(d.dtype) - torch.eye(b, dtype=d.dtype)
+    num_pos = torch.clamp(mask_pos.sum(), min=1e-16)
+    return torch.clamp(loss_mat * mask_pos, min=0.0).sum() / num_pos
+
+
+def _angular_positive(c, loss_type, margin):
+    """d_p of model/loss.py:535-560.  The sqrt of the arc form is floored at 1e-12 so that masked-out entries with
+    |cos| = 1 (the diagonal) give a finite derivative; the reference graph yields 0 * inf there."""
+    if loss_type == "asoftmax":
+        m = int(margin)
+        if m == 1:
+            return c
+        if m == 2:
+            return 2.0 * torch.sign(c) * c * c - 1.0
+        if m == 4:
+            c2, c4 = c * c, c ** 4
+            s0 = torch.sign(c)
+            s3 = torch.sign(2.0 * c2 - 1.0) * s0
+            s4 = 2.0 * s0 + s3 - 3.0
+            return s3 * (8.0 * c4 - 8.0 * c2 + 1.0) + s4
+        raise NotImplementedError("[ERROR] m=%d is not unsupported if asoftmax is selected." % m)
+    if loss_type == "additive_margin_softmax":
+        return c - margin
+    new = c * math.cos(margin) - torch.sqrt(torch.clamp(1.0 - c * c, min=1e-12)) * math.sin(margin)
+    return torch.where(c <= math.cos(math.pi - margin), -new - 2.0, new)
+
+
+def angular_triplet_loss(x, labels, params):
+    """model/loss.py:501-634: online-mined triplet loss on pairwise cosines, d_p margin-transformed like the softmax
+    heads; triplet_type "all" (mean over the violating triplets) or "hard" (hardest positive / negative per anchor)."""
+    assert params.triplet_type in ("all", "hard")
+    assert params.loss_type in ("asoftmax", "additive_margin_softmax", "additive_angular_margin_softmax")
+    margin = float(params.margin)
+    eps = 1e-12
+    b = x.shape[0]
+    c = pairwise_cos_similarity(x)
+    pos = _angular_positive(c, params.loss_type, margin)
+    neg = c
+    eye = torch.eye(b, dtype=torch.bool)
+    lab_eq = labels.reshape(1, -1) == labels.reshape(-1, 1)
+    if params.triplet_type == "all":
+        ne = ~eye
+        distinct = ne.unsqueeze(2) & ne.unsqueeze(1) & ne.unsqueeze(0)
+        valid = lab_eq.unsqueeze(2) & (~lab_eq).unsqueeze(1)
+        mask = (distinct & valid).to(c.dtype)
+        tl = torch.clamp(mask * (neg.unsqueeze(1) - pos.unsqueeze(2)), min=0.0)
+        num_pos = (tl > eps).to(c.dtype).sum()
+        return tl.sum() / (num_pos + 1e-16)
+    map_ = (lab_eq & ~eye).to(c.dtype)
+    ap = pos * map_ + pos.amax(1, keepdim=True) * (1.0 - map_)
+    hardest_pos = ap.amin(1, keepdim=True)
+    man = (~lab_eq).to(c.dtype)
+    an = neg * man + pos.amin(1, keepdim=True) * (1.0 - man)          # (sic) the fill is the row minimum of d_p
+    hardest_neg = an.amax(1, keepdim=True)
+    return torch.clamp(hardest_neg - hardest_pos, min=0.0).mean()
+
+
+def e2e_valid_loss(x, labels, params):
+    """model/loss.py:637-705: softmax GE2E loss (scale 20, no bias) on speaker-ordered batches; a sample's own speaker is
+    scored against the centre of the OTHER segments of that speaker."""
+    n, m = int(params.num_valid_speakers_per_batch), int(params.num_valid_segments_per_speaker)
+    f = l2_scaling(x, 1.0)
+    dim = f.shape[1]
+    fr = f.reshape(n, m, dim)
+    center = l2_scaling(fr.mean(1), 1.0)
+    center_ex = l2_scaling((fr.sum(1, keepdim=True) - fr).reshape(n * m, dim), 1.0)
+    sim = f @ center.t()
+    sim_ex = (f * center_ex).sum(1)
+    own = torch.arange(n).repeat_interleave(m)
+    mask = torch.zeros(n * m, n, dtype=f.dtype)
+    mask[torch.arange(n * m), own] = 1.0
+    sim = 20.0 * (sim * (1.0 - mask) + sim_ex.unsqueeze(1) * mask)
+    return _xent(sim, own)
+
+
+METRIC_LOSSES = {"semihard_triplet_loss": semihard_triplet_loss, "angular_triplet_loss": angular_triplet_loss}
+
+
 def loss_network(loss_type, x, labels, P, params, global_step=None):
+    if loss_type in METRIC_LOSSES:
+        return METRIC_LOSSES[loss_type](x, labels, params), None
+    if loss_type == "e2e_valid_loss":
+        return e2e_valid_loss(x, labels, params), None
     if loss_type not in HEADS:
         raise NotImplementedError("Not implement %s loss" % loss_type)
     if loss_type == "softmax":

@@ -8,6 +8,8 @@ known-answer functions (run in the build container, where /root/reference exists
   statpool.npz   the inline NumPy check ``compute_stat_pooling`` of model/multitask_v1/pooling.py:68-80, exec'd from the
                  reference source text (it lives under ``__main__``).
   aux.npz        model/test_utils.py:855-884 compute_ring_loss / compute_mhe (auxiliary losses of model/loss.py:985-1037).
+  triplet.npz    model/test_utils.py:118-154 compute_triplet_loss, :488-650 *_angular_triplet_loss, :21-86 compute_ge2e_loss
+                 (semi-hard / angular triplet losses and the softmax GE2E validation loss of model/loss.py:358-705).
   vlad.npz       model/test_utils.py:421-436 compute_ghost_vlad (NetVLAD / GhostVLAD pooling, model/pooling.py:195-277).
   attention.npz  model/test_utils.py:321-376 compute_self_attention, exec'd from the reference source with
                  the two py2 integer divisions (``value_dim/n_heads``, ``key_dim/n_heads``) turned into ``//``.
@@ -178,8 +180,45 @@ def make_vlad(tu):
     print("vlad.npz")
 
 
+def make_triplet(tu):
+    # model/test_utils.py:118-154 compute_triplet_loss, :488-650 {asoftmax,amsoftmax,arcsoftmax}_angular_triplet_loss,
+    # :21-86 compute_ge2e_loss -- the known answers of model/loss.py:358-705, on the data of model/tdnn.py:355-445
+    # (speaker-ordered labels, one duplicated and one negated embedding)
+    rng = np.random.RandomState(20245)
+    n_spk, n_seg, dim = 6, 4, 16
+    n = n_spk * n_seg
+    labels = np.repeat(np.arange(n_spk), n_seg).astype(np.int32)
+    out = {"labels": labels, "num_speakers": np.int64(n_spk), "num_segments": np.int64(n_seg)}
+    emb = rng.rand(n, dim).astype(np.float32)
+    emb[-1, :] = emb[-2, :]                                   # tdnn.py:359
+    out["semihard/emb"] = emb
+    semi = []
+    for squared in (True, False):
+        for margin in (0.2, 0.5):
+            semi.append((float(squared), margin, float(tu.compute_triplet_loss(emb.astype(np.float64).copy(), labels, margin, squared))))
+    out["semihard/cases"] = np.array(semi, dtype=np.float64)
+    emb2 = rng.rand(n, dim).astype(np.float32) - 0.3
+    emb2[1, :] = emb2[0, :]                                   # tdnn.py:377-378
+    emb2[2, :] = -emb2[0, :]
+    out["angular/emb"] = emb2
+    ang = []
+    kinds = {"asoftmax": (0, tu.asoftmax_angular_triplet_loss), "additive_margin_softmax": (1, tu.amsoftmax_angular_triplet_loss),
+             "additive_angular_margin_softmax": (2, tu.arcsoftmax_angular_triplet_loss)}
+    for ti, ttype in enumerate(("all", "hard")):
+        for name, margins in (("asoftmax", (1, 2, 4)), ("additive_margin_softmax", (0.1, 0.35)),
+                              ("additive_angular_margin_softmax", (0.3,))):
+            code, fn = kinds[name]
+            for m in margins:
+                ang.append((code, ti, float(m), float(fn(emb2.astype(np.float64).copy(), labels, m, ttype))))
+    out["angular/cases"] = np.array(ang, dtype=np.float64)
+    out["e2e/loss"] = np.float64(tu.compute_ge2e_loss(emb2.astype(np.float64).copy(), labels, 20, 0, "softmax"))
+    np.savez_compressed(os.path.join(HERE, "triplet.npz"), **out)
+    print("triplet.npz: %d semihard + %d angular cases + e2e" % (len(semi), len(ang)))
+
+
 if __name__ == "__main__":
     tu = load_test_utils()
+    make_triplet(tu)
     make_vlad(tu)
     make_heads(tu)
     make_statpool()

@@ -102,6 +102,25 @@ def test_ghost_vlad(golden_dir):
         assert np.allclose(short.numpy(), trunc.numpy(), rtol=1e-12)
 
 
+def test_metric_losses_match_reference_numpy(golden_dir):
+    """Semi-hard / angular triplet losses and the GE2E validation loss (model/loss.py:358-705) against the reference's
+    NumPy known answers (model/test_utils.py:118-154, 488-650, 21-86) on the data of model/tdnn.py:355-445."""
+    g = np.load(os.path.join(golden_dir, "triplet.npz"))
+    lab = torch.from_numpy(g["labels"].astype(np.int64))
+    x = O.l2_scaling(torch.from_numpy(g["semihard/emb"].astype(np.float64)), 1.0)   # "L2 normalization should be applied before"
+    for sq, m, want in g["semihard/cases"]:
+        p = O.ParamsPlain(margin=float(m), triplet_loss_squared=bool(sq))
+        assert np.allclose(float(O.semihard_triplet_loss(x, lab, p)), want, rtol=1e-9)
+    x = torch.from_numpy(g["angular/emb"].astype(np.float64))
+    names = ["asoftmax", "additive_margin_softmax", "additive_angular_margin_softmax"]
+    for code, ti, m, want in g["angular/cases"]:
+        p = O.ParamsPlain(margin=float(m), triplet_type=("all", "hard")[int(ti)], loss_type=names[int(code)])
+        # arc form: the sqrt floor (1e-12, finite gradients at |cos| = 1) moves the duplicated pair by 1e-6 * sin(m)
+        assert np.allclose(float(O.angular_triplet_loss(x, lab, p)), want, rtol=1e-7 if int(code) == 2 else 1e-9)
+    p = O.ParamsPlain(num_valid_speakers_per_batch=int(g["num_speakers"]), num_valid_segments_per_speaker=int(g["num_segments"]))
+    assert np.allclose(float(O.e2e_valid_loss(x, lab, p)), float(g["e2e/loss"]), rtol=1e-9)
+
+
 def test_aux_losses_match_reference_numpy(golden_dir):
     """Ring loss and MHE (model/loss.py:985-1037) against model/test_utils.py:855-884 (compute_ring_loss, compute_mhe)."""
     g = np.load(os.path.join(golden_dir, "aux.npz"))

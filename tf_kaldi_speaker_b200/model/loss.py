@@ -1,4 +1,5 @@
-"""Classification heads with the reference's operator surface (model/loss.py:9-355).
+"""Classification heads (model/loss.py:9-355) and metric-learning losses (model/loss.py:358-705) with the reference's
+operator surface.
 
 softmax / asoftmax / additive_margin_softmax / additive_angular_margin_softmax keep the reference signatures
 ``f(features, labels, num_outputs, params, is_training=None, reuse_variables=None, name="softmax")
@@ -154,3 +155,75 @@ def additive_angular_margin_softmax(features, labels, num_outputs, params, is_tr
                               params.arcsoftmax_lambda_gamma, params.arcsoftmax_lambda_power, params.dict["global_step"])
     return _run_head(features, labels, num_outputs, params, is_training, name, L.HEAD_AAM, margin=params.arcsoftmax_m,
                      fa=fa, fs=fs)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Metric-learning losses on the embeddings (model/loss.py:358-705).  No speaker matrix: the batches come from the
+# speakers x segments sampler (KaldiDataRandomQueue, params.num_speakers_per_batch / num_segments_per_speaker).
+# ---------------------------------------------------------------------------------------------------------------------
+METRIC_LOSSES = ("semihard_triplet_loss", "angular_triplet_loss", "e2e_valid_loss")
+_ANGULAR_KINDS = {"asoftmax": 0, "additive_margin_softmax": 1, "additive_angular_margin_softmax": 2}
+
+
+def _metric_endpoints(loss, labels):
+    endpoints = OrderedDict()
+    endpoints["loss"] = loss
+    endpoints["labels"] = labels
+    return endpoints
+
+
+def semihard_triplet_loss(features, labels, num_outputs, params, is_training=None, reuse_variables=None, name="triplet_loss"):
+    """Triplet loss with semi-hard negative mining (model/loss.py:358-498; TF metric_learning.triplet_semihard_loss).
+
+    Args:
+        features: [batch, dim] handle; the L2 normalisation is expected to have been applied (feature_norm).
+        labels: int tensor [batch].
+        num_outputs, reuse_variables, name: unused, kept for signature compatibility.
+        params: params.margin, params.triplet_loss_squared.
+        is_training: record the backward closure.
+    :return: (loss, endpoints)
+    """
+    eng = get_engine()
+    assert features.data.dim() == labels.dim() + 1
+    loss, _ = eng.metric_loss(features, labels, "semihard", bool(is_training),
+                              scaling=float(getattr(features, "scaling", 0.0) or 0.0), margin=float(params.margin),
+                              squared=bool(params.triplet_loss_squared))
+    return loss, _metric_endpoints(loss, labels)
+
+
+def angular_triplet_loss(features, labels, num_outputs, params, is_training=None, reuse_variables=None,
+                         name="angular_triplet_loss"):
+    """Online-mined triplet loss on pairwise cosines (model/loss.py:501-634).
+
+    Args:
+        features: [batch, dim] handle.
+        labels: int tensor [batch].
+        params: params.margin; params.triplet_type "all" | "hard"; params.loss_type "asoftmax" |
+                "additive_margin_softmax" | "additive_angular_margin_softmax" (the transform of the positive similarity).
+        is_training: record the backward closure.
+    :return: (loss, endpoints)
+    """
+    eng = get_engine()
+    assert features.data.dim() == labels.dim() + 1
+    assert params.triplet_type == "all" or params.triplet_type == "hard"
+    assert params.loss_type in ["asoftmax", "additive_margin_softmax", "additive_angular_margin_softmax"]
+    params.margin = float(params.margin)
+    loss, _ = eng.metric_loss(features, labels, "angular", bool(is_training),
+                              scaling=float(getattr(features, "scaling", 0.0) or 0.0), margin=params.margin,
+                              angular_kind=_ANGULAR_KINDS[params.loss_type], hard=(params.triplet_type == "hard"))
+    return loss, _metric_endpoints(loss, labels)
+
+
+def e2e_valid_loss(features, labels, num_outputs, params, is_training=None, reuse_variables=None, name="valid_e2e_loss"):
+    """Softmax generalized end-to-end loss for the validation set (model/loss.py:637-705); forward only.  The rows must be
+    speaker-ordered: [s1, s1, ..., s2, s2, ...] with params.num_valid_speakers_per_batch x
+    params.num_valid_segments_per_speaker rows."""
+    assert "num_valid_speakers_per_batch" in params.dict and "num_valid_segments_per_speaker" in params.dict, \
+        "Valid parameters should be set if E2E loss is selected"
+    if is_training:
+        raise NotImplementedError("e2e_valid_loss is the validation loss of angular_triplet_loss (trainer.py:272-275)")
+    eng = get_engine()
+    loss, _ = eng.metric_loss(features, labels, "e2e_valid", False, scaling=float(getattr(features, "scaling", 0.0) or 0.0),
+                              speakers=int(params.num_valid_speakers_per_batch),
+                              segments=int(params.num_valid_segments_per_speaker))
+    return loss, _metric_endpoints(loss, labels)

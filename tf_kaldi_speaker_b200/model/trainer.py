@@ -21,6 +21,7 @@ from ..runtime import Engine, ScaledUtt, set_engine
 from . import tdnn as tdnn_mod
 from .tdnn import tdnn
 from .loss import (softmax, asoftmax, additive_margin_softmax, additive_angular_margin_softmax,
+                   semihard_triplet_loss, angular_triplet_loss, e2e_valid_loss, METRIC_LOSSES,
                    declare_head_variables, margin_schedule)
 
 
@@ -84,7 +85,12 @@ class Trainer(object):
                 self.loss_network = additive_margin_softmax
             elif loss_type == "additive_angular_margin_softmax":
                 self.loss_network = additive_angular_margin_softmax
+            elif loss_type == "semihard_triplet_loss":
+                self.loss_network = semihard_triplet_loss
+            elif loss_type == "angular_triplet_loss":
+                self.loss_network = angular_triplet_loss
             else:
+                # generalized_angular_triplet_loss (loss.py:708-901, moving-average class centres) is not built
                 raise NotImplementedError("Not implement %s loss" % self.loss_type)
             self.num_speakers = num_speakers
             if self.global_step is None:
@@ -116,10 +122,11 @@ class Trainer(object):
             tdnn_mod.declare_variables(eng, dim, self.params)
             if mode != "predict":
                 e = int(self.params.dict.get("num_nodes_last_layer", 512))
-                declare_head_variables(eng, e, num_speakers, self.params, loss_type)
+                if loss_type not in METRIC_LOSSES:         # the metric-learning losses have no speaker matrix
+                    declare_head_variables(eng, e, num_speakers, self.params, loss_type)
             eng.store.finalize()
             eng.store.init(int(self.params.dict.get("seed", 0)))
-        elif mode != "predict" and "softmax/output/kernel" not in eng.store:
+        elif mode != "predict" and loss_type not in METRIC_LOSSES and "softmax/output/kernel" not in eng.store:
             raise L.XvError("build('predict') was called first: the head variables cannot be added afterwards; "
                             "build train/valid before predict")
         self.modes.add(mode)
@@ -144,7 +151,8 @@ class Trainer(object):
         ``l2_loss=False``: the regularisation loss is left to the optimizer kernel (same pass over the parameters)."""
         eng = set_engine(self.engine)      # the operator functions (model/tdnn.py, loss.py) act on the current engine
         eng.begin_step(True)
-        eng.prefetch_head_weights("softmax/output/kernel", normalize=(self.loss_type != "softmax"))
+        if self.loss_type not in METRIC_LOSSES:
+            eng.prefetch_head_weights("softmax/output/kernel", normalize=(self.loss_type != "softmax"))
         if self._h2d_event is not None:
             self._h2d_event.wait(torch.cuda.current_stream())     # this step's batch has arrived (see _static_batch)
         out, endpoints = self.entire_network(features, self.params, True, True)
@@ -432,7 +440,9 @@ class Trainer(object):
         vp.dict["global_step"] = self.global_step or 0
         eng.begin_step(False)
         out, endpoints = self.entire_network(features, vp, False, True)
-        loss, _ = self.loss_network(out, labels, self.num_speakers, vp, False, True)
+        # angular triplet training validates with the softmax GE2E loss (model/trainer.py:272-275, 300-301)
+        loss_network = e2e_valid_loss if self.loss_type == "angular_triplet_loss" else self.loss_network
+        loss, _ = loss_network(out, labels, self.num_speakers, vp, False, True)
         self.endpoints = endpoints
         return float(loss.item()), endpoints["output"].dense()
 

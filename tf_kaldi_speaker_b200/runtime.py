@@ -1095,6 +1095,56 @@ class Engine(object):
             self.tape.append(bwd)
         return self.scalars[0], logits, x
 
+    def metric_loss(self, u, labels, kind, training, scaling=0.0, margin=0.0, squared=False, angular_kind=0, hard=False,
+                    speakers=0, segments=0):
+        """Pairwise metric-learning losses on the embeddings (model/loss.py:358-705): kind = "semihard" | "angular" | "e2e_valid".
+        One fp32 Gram matrix of the (optionally l2-scaled) embeddings, a mining kernel per anchor row, and -- in training --
+        dLoss/dx = coef x + diag o x through a second fp32 GEMM (csrc/xv_metric.cu).  Data parallel: the mining is per
+        replica (triplets never cross ranks, like per-replica batch-norm); the summed scalars / gradients are replica means."""
+        B, E = u.data.shape
+        s = L.stream_ptr
+        x = self.buf("metric/x", (B, E), torch.float32)
+        x3 = self.buf("metric/x3", (B, 3 * E), torch.bfloat16)
+        xnorm = self.buf("metric/xnorm", (B,), torch.float32)
+        urinv = self.buf("metric/urinv", (B,), torch.float32)
+        self.call(self.lib.xv_head_prep_features, L.ptr(u.data), C.c_float(scaling), L.ptr(x), L.ptr(x3), L.ptr(xnorm),
+                  L.ptr(urinv), B, E, s())
+        rep = 1.0 if self.inv_global_batch is None else 1.0 / max(1, int(round(1.0 / (self.inv_global_batch * B))))
+        loss = self.scalars[0:1]
+        if kind == "e2e_valid":
+            assert speakers * segments == B, "e2e_valid_loss: the batch must hold num_valid_speakers_per_batch x " \
+                                             "num_valid_segments_per_speaker speaker-ordered rows"
+            work = self.buf("metric/e2e_work", ((B + speakers) * E + speakers,), torch.float32)
+            self.call(self.lib.xv_e2e_valid_loss, L.ptr(x), speakers, segments, E, C.c_int64(E), C.c_float(rep), L.ptr(loss),
+                      L.ptr(work), s())
+            return self.scalars[0], x
+        labels = labels.to(device=self.device, dtype=torch.int32).contiguous()
+        gram = self.buf("metric/gram", (B, B), torch.float32)
+        coef = self.buf("metric/coef", (B, B), torch.float32)
+        diag = self.buf("metric/diag", (B,), torch.float32)
+        work = self.buf("metric/work", (2 * B * B + 8,), torch.float32)
+        self.call(self.lib.xv_gram_f32, L.ptr(x), L.ptr(gram), B, E, C.c_int64(E), s())
+        if kind == "semihard":
+            self.call(self.lib.xv_semihard_triplet, L.ptr(gram), L.ptr(labels), B, C.c_float(margin), int(squared),
+                      C.c_float(rep), L.ptr(loss), L.ptr(coef), L.ptr(diag), L.ptr(work), s())
+            self.launches += 3
+        elif kind == "angular":
+            self.call(self.lib.xv_angular_triplet, L.ptr(gram), L.ptr(labels), B, int(angular_kind), C.c_float(margin),
+                      int(hard), C.c_float(rep), L.ptr(loss), L.ptr(coef), L.ptr(diag), L.ptr(work), s())
+            self.launches += 1 if hard else 2
+        else:
+            raise NotImplementedError("metric loss %s" % kind)
+        if training:
+            def bwd():
+                dxg = self.buf("metric/dx", (B, E), torch.float32)
+                self.call(self.lib.xv_pairwise_bwd, L.ptr(coef), L.ptr(diag), L.ptr(x), L.ptr(dxg), B, E, C.c_int64(E), s())
+                du = self.buf(u.name + "/grad", (B, E), torch.float32)
+                self.call(self.lib.xv_head_finish_dx, L.ptr(dxg), L.ptr(None), L.ptr(x), L.ptr(xnorm), L.ptr(u.data),
+                          L.ptr(urinv), C.c_float(scaling), L.ptr(du), B, E, s())
+                u.grad = du
+            self.tape.append(bwd)
+        return self.scalars[0], x
+
     def margin_head_sharded(self, u, labels, kernel, bias, head_type, num_outputs, training, margin=0.0, asoftmax_m=1,
                             scaling=0.0):
         """Class-sharded variant of margin_head (north_star "Data parallelism"; SURVEY 8e 2'): this rank holds columns
