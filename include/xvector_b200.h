@@ -307,6 +307,23 @@ XV_API int xv_angular_triplet(const float* gram, const int32_t* labels, int B, i
                               float* loss, float* coef, float* diag, float* work, void* stream);
 XV_API int xv_pairwise_bwd(const float* coef, const float* diag, const float* x, float* dx, int B, int E, int64_t ldx,
                            void* stream);
+/* Generalized angular triplet loss against class centres (replaces model/loss.py:708-901, loss_compute "raw"; known answer
+ * model/test_utils.py:653-852).  cos f32 [B, ldc] = cosine of every sample to every centre (XV_EPI_F32 GEMM of the
+ * l2-normalised features with the xv_head_prep_weights operand).  xv_center_triplet: loss[0] += scale * (w_triplet *
+ * triplet + w_center * centre); d (optional) bf16 [B, ldc] = dLoss/dcos, the operand of the head's dW / dx GEMMs; topn 1 / k:
+ * hardest k non-target centres, 0: all; counters: 4 floats of scratch.  xv_center_between: t f32 [E] = sum of the normalised
+ * centres, loss[0] += coef * between-class term; xv_center_between_bwd: dwn += coef * d between / d(normalised centres)
+ * (before xv_head_finish_dw).  xv_center_update (triplet_center "average", training): w[:, y_i] -= decay * (w_old[:, y_i] -
+ * feats[i, :]) summed over the samples of a class (loss.py:766-783); delta: B*E floats of scratch. */
+XV_API int xv_center_triplet(const float* cosm, const int32_t* labels, int B, int C, int64_t ldc, float margin,
+                             float target_margin, int topn, float w_triplet, float w_center, float scale, float* loss, void* d,
+                             float* counters, void* stream);
+XV_API int xv_center_between(const float* w, const float* inv_norm, int E, int C, int64_t ldw, float coef, float* t, float* loss,
+                             void* stream);
+XV_API int xv_center_between_bwd(float* dwn, const float* w, const float* inv_norm, const float* t, int E, int C, int64_t ldw,
+                                 float coef, void* stream);
+XV_API int xv_center_update(float* w, const float* feats, const int32_t* labels, float* delta, int B, int E, int64_t ldw,
+                            float decay, void* stream);
 XV_API int xv_e2e_valid_loss(const float* x, int num_speakers, int num_segments, int E, int64_t ldx, float scale, float* loss,
                              float* work, void* stream);
 

@@ -198,8 +198,17 @@ def init_params(dim, params, num_speakers=None, loss_type=None, seed=0, dtype=to
     return OrderedDict((k, v.to(dtype)) for k, v in P.items())
 
 
-def trainable_names(P):
-    return [k for k in P if not (k.endswith("moving_mean") or k.endswith("moving_variance"))]
+def _average_centres(params, loss_type):
+    """generalized_angular_triplet_loss with triplet_center = "average": the class centres are a non-trainable variable
+    updated like batch-norm statistics, without a regulariser (model/loss.py:755-760)."""
+    return (loss_type == "generalized_angular_triplet_loss" and params is not None
+            and params.dict.get("triplet_center") == "average")
+
+
+def trainable_names(P, params=None, loss_type=None):
+    skip_w = _average_centres(params, loss_type)
+    return [k for k in P if not (k.endswith("moving_mean") or k.endswith("moving_variance")
+                                 or (skip_w and k == "softmax/output/kernel"))]
 
 
 def l2_regularised(name):
@@ -707,10 +716,57 @@ def e2e_valid_loss(x, labels, params):
     return _xent(sim, own)
 
 
+def generalized_angular_triplet_loss(x, labels, P, params, is_training=True, updates=None):
+    """model/loss.py:708-901 (loss_compute = "raw"): triplet loss against class centres ``softmax/output/kernel`` [E, C] --
+    trainable ("learnable") or a moving average of the class members updated before the distances are taken ("average",
+    tf.assign: no gradient through the update).  Returns (loss, parts)."""
+    assert params.triplet_center in ("learnable", "average")
+    if params.loss_compute != "raw":
+        raise NotImplementedError("Not implemented.")           # loss.py:826
+    assert float(params.l2_loss_weight) == 0.0, "The weight decay is applied by regularization term, not the loss!"
+    margin, target_margin = float(params.margin), float(params.target_margin)
+    topn = int(params.triplet_topn)
+    w = P["softmax/output/kernel"]
+    lab = labels.long()
+    fn = _l2_normalize(x, 1)
+    w_upd = w
+    if params.triplet_center == "average" and is_training:
+        decay = 1.0 - float(params.triplet_center_momentum)
+        wf = w.detach().t()
+        delta = (wf[lab] - x.detach()) * decay
+        w_upd = (wf - torch.zeros_like(wf).index_add_(0, lab, delta)).t()      # scatter_nd sums repeated labels
+        if updates is not None:
+            updates["softmax/output/kernel"] = w_upd
+    wn = _l2_normalize(w_upd, 0)
+    eps = 1e-12
+    dist = (fn * fn).sum(1, keepdim=True) + (wn * wn).sum(0, keepdim=True) - 2.0 * (fn @ wn)     # sum((f - w)^2)
+    b, c = dist.shape
+    mask = torch.zeros_like(dist)
+    mask[torch.arange(b), lab] = 1.0
+    target = dist[torch.arange(b), lab]
+    new_dist = dist * (1.0 - mask) + (dist.amax(1, keepdim=True) + dist) * mask
+    tmask = (target > target_margin).to(dist.dtype)
+    if topn == 1:
+        tl = tmask * torch.clamp(margin + target - new_dist.amin(1), min=1e-16)
+    elif topn == 0:
+        tl = tmask.unsqueeze(1) * (torch.clamp(margin + target.unsqueeze(1) - new_dist, min=1e-16) * (1.0 - mask))
+    else:
+        nt = -torch.topk(-new_dist, topn, dim=1, sorted=False)[0]
+        tl = tmask.unsqueeze(1) * torch.clamp(margin + target.unsqueeze(1) - nt, min=1e-16)
+    triplet = tl.sum() / ((tl > eps).to(dist.dtype).sum() + eps)
+    center = (tmask * target).sum() / (tmask.sum() + eps)
+    between = -((1.0 - torch.eye(c, dtype=dist.dtype)) * (2.0 - 2.0 * (wn.t() @ wn))).sum() / (c * (c - 1))
+    loss = (float(params.triplet_loss_weight) * triplet + float(params.center_loss_weight) * center
+            + float(params.between_loss_weight) * between)
+    return loss, {"triplet_loss": triplet, "center_loss": center, "between_loss": between, "average_centers": w_upd}
+
+
 METRIC_LOSSES = {"semihard_triplet_loss": semihard_triplet_loss, "angular_triplet_loss": angular_triplet_loss}
 
 
-def loss_network(loss_type, x, labels, P, params, global_step=None):
+def loss_network(loss_type, x, labels, P, params, global_step=None, is_training=True, updates=None):
+    if loss_type == "generalized_angular_triplet_loss":
+        return generalized_angular_triplet_loss(x, labels, P, params, is_training, updates)[0], None
     if loss_type in METRIC_LOSSES:
         return METRIC_LOSSES[loss_type](x, labels, params), None
     if loss_type == "e2e_valid_loss":
@@ -737,7 +793,8 @@ def regularization_loss(P, params):
     s_out = float(params.dict.get("output_weight_l2_regularizer", s))
     total = 0.0
     for k, v in P.items():
-        if l2_regularised(k):
+        if l2_regularised(k) and not (k == "softmax/output/kernel" and params.dict.get("triplet_center") == "average"
+                                      and "triplet_topn" in params.dict):
             total = total + (s_out if k.startswith("softmax/") else s) * (v ** 2).sum() / 2
     return total
 
@@ -746,7 +803,7 @@ def forward_loss(P, features, labels, params, loss_type, global_step, is_trainin
                  emulate_bf16=False):
     x, ep, penalty = entire_network(features, P, params, is_training=is_training, updates=updates,
                                     emulate_bf16=emulate_bf16)
-    loss, logits = loss_network(loss_type, x, labels, P, params, global_step)
+    loss, logits = loss_network(loss_type, x, labels, P, params, global_step, is_training, updates)
     total = loss + regularization_loss(P, params)
     if penalty is not None:
         total = total + penalty
@@ -757,10 +814,10 @@ def forward_loss(P, features, labels, params, loss_type, global_step, is_trainin
 def train_step(P, opt_state, features, labels, params, loss_type, learning_rate, global_step, emulate_bf16=False):
     """One sess.run(train_op).  Returns (raw_loss, total_loss, grads, new_P, new_opt_state, endpoints);
     endpoints["__raw_grads"] holds the gradients before clip_by_global_norm."""
-    Pg = OrderedDict((k, v.detach().clone().requires_grad_(k in trainable_names(P))) for k, v in P.items())
+    names = trainable_names(P, params, loss_type)
+    Pg = OrderedDict((k, v.detach().clone().requires_grad_(k in names)) for k, v in P.items())
     updates = OrderedDict()
     loss, total, ep = forward_loss(Pg, features, labels, params, loss_type, global_step, True, updates, emulate_bf16)
-    names = trainable_names(P)
     gl = torch.autograd.grad(total, [Pg[n] for n in names], allow_unused=True)
     grads = OrderedDict((n, (g if g is not None else torch.zeros_like(P[n]))) for n, g in zip(names, gl))
     ep["__raw_grads"] = grads

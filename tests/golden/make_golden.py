@@ -10,6 +10,8 @@ known-answer functions (run in the build container, where /root/reference exists
   aux.npz        model/test_utils.py:855-884 compute_ring_loss / compute_mhe (auxiliary losses of model/loss.py:985-1037).
   triplet.npz    model/test_utils.py:118-154 compute_triplet_loss, :488-650 *_angular_triplet_loss, :21-86 compute_ge2e_loss
                  (semi-hard / angular triplet losses and the softmax GE2E validation loss of model/loss.py:358-705).
+  gtriplet.npz   model/test_utils.py:653-852 compute_generalized_triplet_loss (triplet / centre / between-class parts of
+                 model/loss.py:708-901 for learnable and moving-average class centres, top-n = 1, 0, k).
   vlad.npz       model/test_utils.py:421-436 compute_ghost_vlad (NetVLAD / GhostVLAD pooling, model/pooling.py:195-277).
   attention.npz  model/test_utils.py:321-376 compute_self_attention, exec'd from the reference source with
                  the two py2 integer divisions (``value_dim/n_heads``, ``key_dim/n_heads``) turned into ``//``.
@@ -216,8 +218,37 @@ def make_triplet(tu):
     print("triplet.npz: %d semihard + %d angular cases + e2e" % (len(semi), len(ang)))
 
 
+def make_gtriplet(tu):
+    # model/test_utils.py:653-852 compute_generalized_triplet_loss, the known answer of model/loss.py:708-901
+    rng = np.random.RandomState(20246)
+    n, dim, c = 24, 16, 11
+    emb = (rng.randn(n, dim) * (0.5 + rng.rand(n, 1))).astype(np.float32)
+    w = xavier(rng, dim, c)
+    out = {"emb": emb, "w": w}
+    cases = []
+    for ci, (center, topn, margin, tmargin, repeat) in enumerate([("learnable", 1, 0.3, 0.2, True), ("learnable", 0, 0.1, 0.5, True),
+                                                                  ("learnable", 3, 0.3, 0.0, True), ("average", 1, 0.3, 0.2, False),
+                                                                  ("average", 4, 0.2, 0.1, False)]):
+        # the NumPy code updates the averaged centres one sample at a time, the graph all at once (scatter_nd): they agree
+        # only when no label repeats, so the "average" cases use distinct labels
+        labels = (rng.randint(0, c, size=(n,)) if repeat else rng.permutation(c)[:min(n, c)]).astype(np.int32)
+        e = emb[:len(labels)]
+        p = ParamsPlain()
+        p.dict.update(triplet_center=center, triplet_center_momentum=0.9, loss_compute="raw", triplet_topn=topn, margin=margin,
+                      target_margin=tmargin, center_loss_weight=0.5, between_loss_weight=0.25, l2_loss_weight=0.0)
+        loss, w_upd = tu.compute_generalized_triplet_loss(e.astype(np.float64).copy(), w.astype(np.float64).copy(), labels, p, c)
+        out["case%d/labels" % ci] = labels
+        out["case%d/w_update" % ci] = np.asarray(w_upd)
+        out["case%d/parts" % ci] = np.array([float(loss["triplet_loss"]), float(loss["center_loss"]), float(loss["between_loss"])])
+        cases.append((float(center == "average"), topn, margin, tmargin))
+    out["cases"] = np.array(cases, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "gtriplet.npz"), **out)
+    print("gtriplet.npz: %d cases" % len(cases))
+
+
 if __name__ == "__main__":
     tu = load_test_utils()
+    make_gtriplet(tu)
     make_triplet(tu)
     make_vlad(tu)
     make_heads(tu)

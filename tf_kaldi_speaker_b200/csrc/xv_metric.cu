@@ -8,6 +8,7 @@
 //        dLoss/dX = M X + d o X,
 // and a second fp32 GEMM evaluates it.  fp32 throughout: the mining decisions (hardest / semi-hard negative, violated
 // triplets) are comparisons between pairwise entries, so the products are not rounded to bf16.
+#include <cuda_bf16.h>
 #include <math.h>
 
 #include "xv_internal.h"
@@ -511,6 +512,170 @@ __global__ void __launch_bounds__(256) e2e_loss_kernel(const float* __restrict__
   if (threadIdx.x == 0) atomicAdd(loss, scale * (mx + logf(se) - sim[own]));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Generalized angular triplet loss against class centres (model/loss.py:708-901, loss_compute = "raw").  cos [B, ldc] =
+// <f_i / |f_i|, w_j / |w_j|> comes from the tcgen05 GEMM; dist = 2 - 2 cos (unit vectors).  One block per sample:
+//   target_i = dist[i, y_i], active_i = target_i > target_margin,
+//   top-n = 1 / k: the n smallest non-target distances, n = 0: every non-target class;
+//   triplet  = sum active_i max(margin + target_i - dist_ij, 1e-16) / (#(that > 1e-12) + 1e-12)
+//   centre   = sum active_i target_i / (sum active_i + 1e-12)
+// GRAD = false accumulates the four sums (counters[0..3]); GRAD = true reads them, adds the loss and writes d = dLoss/dcos.
+struct GtCfg {
+  float margin, target_margin, w_triplet, w_center;
+  int topn;
+};
+
+template <bool GRAD>
+__global__ void __launch_bounds__(256) gtriplet_rows_kernel(const float* __restrict__ cosm, const int* __restrict__ labels, int Cn,
+                                                            long long ldc, GtCfg g, float scale, float* __restrict__ counters,
+                                                            float* __restrict__ loss, __nv_bfloat16* __restrict__ d) {
+  pdl_entry();
+  extern __shared__ float sd[];          // [Cn] distances; selected entries are overwritten with +inf during the top-n search
+  __shared__ float red[8];
+  __shared__ float rv[8];
+  __shared__ int ri[8];
+  __shared__ float selv;
+  __shared__ int seli;
+  const int i = blockIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int y = labels[i];
+  const float* cr = cosm + static_cast<long long>(i) * ldc;
+  for (int j = threadIdx.x; j < Cn; j += 256) sd[j] = 2.0f - 2.0f * cr[j];
+  __syncthreads();
+  const float td = sd[y];
+  const float tm = (td > g.target_margin) ? 1.f : 0.f;
+  const float eps = 1e-12f;
+  float a = 0.f, cg = 0.f;
+  __nv_bfloat16* dr = nullptr;
+  if (GRAD) {
+    a = scale * g.w_triplet / (counters[1] + eps);
+    cg = scale * g.w_center / (counters[3] + eps);
+    if (i == 0 && threadIdx.x == 0)
+      atomicAdd(loss, scale * (g.w_triplet * counters[0] / (counters[1] + eps) + g.w_center * counters[2] / (counters[3] + eps)));
+    if (d) {
+      dr = d + static_cast<long long>(i) * ldc;
+      for (int j = threadIdx.x; j < ldc; j += 256) dr[j] = __float2bfloat16(0.f);
+    }
+    __syncthreads();
+  }
+  float sum = 0.f, cnt = 0.f, nsel = 0.f;
+  if (g.topn == 0) {
+    for (int j = threadIdx.x; j < Cn; j += 256) {
+      if (j == y) continue;
+      const float t = g.margin + td - sd[j];
+      const float tl = fmaxf(t, 1e-16f) * tm;
+      sum += tl;
+      cnt += (tl > eps) ? 1.f : 0.f;
+      if (GRAD && tm > 0.f && t >= 1e-16f) {
+        nsel += 1.f;
+        if (dr) dr[j] = __float2bfloat16(2.0f * a);       // dLoss/ddist = -a, dist = 2 - 2 cos
+      }
+    }
+  } else {
+    if (threadIdx.x == 0) sd[y] = INFINITY;               // the target is pushed above the row maximum (loss.py:790)
+    __syncthreads();
+    for (int k = 0; k < g.topn; ++k) {
+      float bv = INFINITY;
+      int bi = 0x7fffffff;
+      for (int j = threadIdx.x; j < Cn; j += 256)
+        if (sd[j] < bv) { bv = sd[j]; bi = j; }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { rv[wp] = bv; ri[wp] = bi; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+          if (rv[w] < bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; }
+        selv = bv;
+        seli = bi;
+        if (bi < Cn) sd[bi] = INFINITY;
+      }
+      __syncthreads();
+      if (seli >= Cn) break;                               // fewer than top-n non-target classes
+      if (threadIdx.x == 0) {
+        const float t = g.margin + td - selv;
+        const float tl = fmaxf(t, 1e-16f) * tm;
+        sum += tl;
+        cnt += (tl > eps) ? 1.f : 0.f;
+        if (GRAD && tm > 0.f && t >= 1e-16f) {
+          nsel += 1.f;
+          if (dr) dr[seli] = __float2bfloat16(2.0f * a);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!GRAD) {
+    sum = m_block_sum(sum, red);
+    cnt = m_block_sum(cnt, red);
+    if (threadIdx.x == 0) {
+      if (sum != 0.f) atomicAdd(counters, sum);
+      if (cnt != 0.f) atomicAdd(counters + 1, cnt);
+      if (tm > 0.f) {
+        atomicAdd(counters + 2, td);
+        atomicAdd(counters + 3, 1.f);
+      }
+    }
+  } else {
+    nsel = m_block_sum(nsel, red);
+    // dLoss/dtarget = a * (#selected negatives) + centre term; d cos = -2 d dist
+    if (threadIdx.x == 0 && dr) dr[y] = __float2bfloat16(-2.0f * (a * nsel + cg * tm));
+  }
+}
+
+// t[e] = sum_j w[e, j] inv_norm[j]  (sum of the normalised centres), one block per row e
+__global__ void __launch_bounds__(256) centre_colsum_kernel(const float* __restrict__ w, const float* __restrict__ inv_norm,
+                                                            float* __restrict__ t, int Cn, long long ldw) {
+  pdl_entry();
+  __shared__ float red[8];
+  const int e = blockIdx.x;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < Cn; j += 256) s = fmaf(w[static_cast<long long>(e) * ldw + j], inv_norm[j], s);
+  s = m_block_sum(s, red);
+  if (threadIdx.x == 0) t[e] = s;
+}
+// between = -mean_{i != j} |w_i - w_j|^2 = -2 + 2 (|t|^2 - C) / (C (C - 1))  for unit centres (loss.py:821-822)
+__global__ void __launch_bounds__(256) centre_between_loss_kernel(const float* __restrict__ t, int E, int Cn, float coef,
+                                                                  float* __restrict__ loss) {
+  pdl_entry();
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int e = threadIdx.x; e < E; e += 256) s = fmaf(t[e], t[e], s);
+  s = m_block_sum(s, red);
+  const float cc = static_cast<float>(Cn) * static_cast<float>(Cn - 1);
+  if (threadIdx.x == 0) atomicAdd(loss, coef * (-2.0f + 2.0f * (s - static_cast<float>(Cn)) / cc));
+}
+// dLoss/dwn[e, j] += coef * 4 / (C (C - 1)) * (t[e] - wn[e, j])
+__global__ void __launch_bounds__(256) centre_between_bwd_kernel(float* __restrict__ dwn, const float* __restrict__ w,
+                                                                 const float* __restrict__ inv_norm, const float* __restrict__ t,
+                                                                 int E, int Cn, long long ldw, float coef4) {
+  pdl_entry();
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(E) * Cn) return;
+  const int e = static_cast<int>(idx / Cn), j = static_cast<int>(idx % Cn);
+  const long long o = static_cast<long long>(e) * ldw + j;
+  dwn[o] += coef4 * (t[e] - w[o] * inv_norm[j]);
+}
+// Moving-average centres (loss.py:766-783): delta_i = (w[:, y_i] - f_i) * decay from the OLD centres, then
+// w[:, y_i] -= delta_i summed over the samples of a class (tf.scatter_nd adds repeated indices).
+__global__ void __launch_bounds__(128) centre_delta_kernel(const float* __restrict__ w, const float* __restrict__ f,
+                                                           const int* __restrict__ labels, float* __restrict__ delta, int E,
+                                                           long long ldw, float decay) {
+  pdl_entry();
+  const int i = blockIdx.x, y = labels[i];
+  for (int e = threadIdx.x; e < E; e += 128)
+    delta[static_cast<long long>(i) * E + e] = (w[static_cast<long long>(e) * ldw + y] - f[static_cast<long long>(i) * E + e]) * decay;
+}
+__global__ void __launch_bounds__(128) centre_scatter_kernel(float* __restrict__ w, const float* __restrict__ delta,
+                                                             const int* __restrict__ labels, int E, long long ldw) {
+  pdl_entry();
+  const int i = blockIdx.x, y = labels[i];
+  for (int e = threadIdx.x; e < E; e += 128) atomicAdd(&w[static_cast<long long>(e) * ldw + y], -delta[static_cast<long long>(i) * E + e]);
+}
+
 }  // namespace xv
 
 using namespace xv;
@@ -626,6 +791,63 @@ extern "C" int xv_e2e_valid_loss(const float* x, int num_speakers, int num_segme
   ::xv::launch_pdl((e2e_loss_kernel), static_cast<int>(Bn), 256, static_cast<size_t>(num_speakers) * sizeof(float), s_,
                    static_cast<const float*>(f), static_cast<const float*>(S), static_cast<const float*>(Sn), num_speakers,
                    num_segments, E, scale / static_cast<float>(Bn), loss);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_center_triplet(const float* cosm, const int32_t* labels, int B, int C, int64_t ldc, float margin, float target_margin,
+                                 int topn, float w_triplet, float w_center, float scale, float* loss, void* d, float* counters,
+                                 void* stream) {
+  if (!cosm || !labels || !loss || !counters || B < 1 || C < 2 || ldc < C || topn < 0 || topn >= C)
+    return set_error(XV_ERR_INVALID, "xv_center_triplet: bad arguments (0 <= triplet_topn < classes)");
+  const size_t smem = static_cast<size_t>(C) * sizeof(float);
+  if (smem > 200 * 1024) return set_error(XV_ERR_UNSUPPORTED, "xv_center_triplet: at most 51200 classes");
+  if (smem > 48 * 1024) {
+    XV_CUDA_CHECK(cudaFuncSetAttribute(gtriplet_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    XV_CUDA_CHECK(cudaFuncSetAttribute(gtriplet_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+  GtCfg g;
+  g.margin = margin; g.target_margin = target_margin; g.w_triplet = w_triplet; g.w_center = w_center; g.topn = topn;
+  XV_CUDA_CHECK(cudaMemsetAsync(counters, 0, 4 * sizeof(float), s_));
+  ::xv::launch_pdl((gtriplet_rows_kernel<false>), B, 256, smem, s_, cosm, labels, C, static_cast<long long>(ldc), g, scale, counters,
+                   loss, static_cast<__nv_bfloat16*>(nullptr));
+  XV_CUDA_CHECK(cudaGetLastError());
+  ::xv::launch_pdl((gtriplet_rows_kernel<true>), B, 256, smem, s_, cosm, labels, C, static_cast<long long>(ldc), g, scale, counters,
+                   loss, static_cast<__nv_bfloat16*>(d));
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_center_between(const float* w, const float* inv_norm, int E, int C, int64_t ldw, float coef, float* t, float* loss,
+                                 void* stream) {
+  if (!w || !inv_norm || !t || !loss || E < 1 || C < 2 || ldw < C) return set_error(XV_ERR_INVALID, "xv_center_between: bad arguments");
+  cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+  ::xv::launch_pdl((centre_colsum_kernel), E, 256, 0, s_, w, inv_norm, t, C, static_cast<long long>(ldw));
+  XV_CUDA_CHECK(cudaGetLastError());
+  ::xv::launch_pdl((centre_between_loss_kernel), 1, 256, 0, s_, static_cast<const float*>(t), E, C, coef, loss);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_center_between_bwd(float* dwn, const float* w, const float* inv_norm, const float* t, int E, int C, int64_t ldw,
+                                     float coef, void* stream) {
+  if (!dwn || !w || !inv_norm || !t || E < 1 || C < 2 || ldw < C) return set_error(XV_ERR_INVALID, "xv_center_between_bwd: bad arguments");
+  const float coef4 = coef * 4.0f / (static_cast<float>(C) * static_cast<float>(C - 1));
+  ::xv::launch_pdl((centre_between_bwd_kernel), ceil_div(static_cast<long long>(E) * C, 256), 256, 0, static_cast<cudaStream_t>(stream),
+                   dwn, w, inv_norm, t, E, C, static_cast<long long>(ldw), coef4);
+  XV_CUDA_CHECK(cudaGetLastError());
+  return XV_OK;
+}
+
+extern "C" int xv_center_update(float* w, const float* feats, const int32_t* labels, float* delta, int B, int E, int64_t ldw,
+                                float decay, void* stream) {
+  if (!w || !feats || !labels || !delta || B < 1 || E < 1 || ldw < 1) return set_error(XV_ERR_INVALID, "xv_center_update: bad arguments");
+  cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+  ::xv::launch_pdl((centre_delta_kernel), B, 128, 0, s_, static_cast<const float*>(w), feats, labels, delta, E,
+                   static_cast<long long>(ldw), decay);
+  XV_CUDA_CHECK(cudaGetLastError());
+  ::xv::launch_pdl((centre_scatter_kernel), B, 128, 0, s_, w, static_cast<const float*>(delta), labels, E, static_cast<long long>(ldw));
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
