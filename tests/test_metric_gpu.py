@@ -209,3 +209,200 @@ def test_metric_train_step(name, loss_type, extra):
         lo, _ = O.loss_network(vt, xo, y, Pn, po, gstep)
     print("  valid loss %.6f oracle %.6f" % (lv, lo.item()))
     assert abs(lv - lo.item()) <= 1e-2 * abs(lo.item())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# generalized_angular_triplet_loss (model/loss.py:708-901): class centres, learnable or moving averages
+# ---------------------------------------------------------------------------------------------------------------------
+def _centre_kernels(cosm, labels, margin, tmargin, topn, w_t, w_c, scale=1.0, want_d=True):
+    from tf_kaldi_speaker_b200 import _lib as L
+    lib = L.load()
+    B, Cn = cosm.shape
+    ldc = (Cn + 7) // 8 * 8
+    cd = torch.zeros(B, ldc, device="cuda")
+    cd[:, :Cn] = cosm.cuda().float()
+    cd[:, Cn:] = 0.9            # padded columns must be ignored
+    lab = labels.cuda().to(torch.int32).contiguous()
+    loss = torch.zeros(1, device="cuda")
+    d = torch.full((B, ldc), float("nan"), dtype=torch.bfloat16, device="cuda") if want_d else None
+    counters = torch.full((8,), float("nan"), device="cuda")
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(lib.xv_center_triplet(L.ptr(cd), L.ptr(lab), B, Cn, C.c_int64(ldc), C.c_float(margin), C.c_float(tmargin), int(topn),
+                                  C.c_float(w_t), C.c_float(w_c), C.c_float(scale), L.ptr(loss), L.ptr(d), L.ptr(counters), s))
+    torch.cuda.synchronize()
+    return float(loss.item()), (None if d is None else d.float().cpu())
+
+
+def _gt_from_cos(cosm, labels, margin, tmargin, topn, w_t, w_c):
+    """The triplet + centre parts of the oracle's generalized_angular_triplet_loss as a function of the cosine matrix."""
+    dist = 2.0 - 2.0 * cosm
+    b = dist.shape[0]
+    lab = labels.long()
+    mask = torch.zeros_like(dist)
+    mask[torch.arange(b), lab] = 1.0
+    target = dist[torch.arange(b), lab]
+    new_dist = dist * (1.0 - mask) + (dist.amax(1, keepdim=True) + dist) * mask
+    tmask = (target > tmargin).to(dist.dtype)
+    if topn == 1:
+        tl = tmask * torch.clamp(margin + target - new_dist.amin(1), min=1e-16)
+    elif topn == 0:
+        tl = tmask.unsqueeze(1) * (torch.clamp(margin + target.unsqueeze(1) - new_dist, min=1e-16) * (1.0 - mask))
+    else:
+        nt = -torch.topk(-new_dist, topn, dim=1, sorted=False)[0]
+        tl = tmask.unsqueeze(1) * torch.clamp(margin + target.unsqueeze(1) - nt, min=1e-16)
+    triplet = tl.sum() / ((tl > 1e-12).to(dist.dtype).sum() + 1e-12)
+    center = (tmask * target).sum() / (tmask.sum() + 1e-12)
+    return w_t * triplet + w_c * center
+
+
+def test_centre_triplet_known_answers(golden_dir):
+    from tf_kaldi_speaker_b200 import _lib as L
+    lib = L.load()
+    g = np.load(os.path.join(golden_dir, "gtriplet.npz"))
+    for ci, (avg, topn, m, tm) in enumerate(g["cases"]):
+        lab = torch.from_numpy(g["case%d/labels" % ci].astype(np.int64))
+        x = torch.from_numpy(g["emb"][:len(lab)].astype(np.float64))
+        w = torch.from_numpy(g["case%d/w_update" % ci])            # the centres the reference took the distances to
+        fn = x / x.norm(dim=1, keepdim=True)
+        wn = w / w.norm(dim=0, keepdim=True)
+        cosm = fn @ wn
+        want_t, want_c, want_b = [float(v) for v in g["case%d/parts" % ci]]
+        got_t, _ = _centre_kernels(cosm, lab, float(m), float(tm), int(topn), 1.0, 0.0, want_d=False)
+        got_c, _ = _centre_kernels(cosm, lab, float(m), float(tm), int(topn), 0.0, 1.0, want_d=False)
+        assert abs(got_t - want_t) <= 2e-5 * abs(want_t), (ci, got_t, want_t)
+        assert abs(got_c - want_c) <= 2e-5 * abs(want_c), (ci, got_c, want_c)
+        E, Cn = w.shape
+        ldw = (Cn + 7) // 8 * 8
+        wd = torch.zeros(E, ldw, device="cuda")
+        wd[:, :Cn] = w.float().cuda()
+        inv = torch.zeros(ldw, device="cuda")
+        inv[:Cn] = (1.0 / w.norm(dim=0)).float().cuda()
+        t = torch.empty(E, device="cuda")
+        loss = torch.zeros(1, device="cuda")
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(lib.xv_center_between(L.ptr(wd), L.ptr(inv), E, Cn, C.c_int64(ldw), C.c_float(1.0), L.ptr(t), L.ptr(loss), s))
+        torch.cuda.synchronize()
+        assert abs(loss.item() - want_b) <= 2e-5 * abs(want_b), (ci, loss.item(), want_b)
+        if avg:      # the moving-average update itself: w_update from the initial centres and the raw features
+            w0 = torch.zeros(E, ldw, device="cuda")
+            w0[:, :Cn] = torch.from_numpy(g["w"]).cuda()
+            f = x.float().cuda().contiguous()
+            delta = torch.empty(len(lab), E, device="cuda")
+            L.check(lib.xv_center_update(L.ptr(w0), L.ptr(f), L.ptr(lab.cuda().to(torch.int32)), L.ptr(delta), len(lab), E,
+                                         C.c_int64(ldw), C.c_float(1.0 - 0.9), s))
+            torch.cuda.synchronize()
+            assert torch.allclose(w0[:, :Cn].cpu().double(), w, rtol=1e-5, atol=1e-6), ci
+
+
+GT = [(64, 1000, 1, 0.3, 0.2), (64, 1000, 0, 0.1, 0.5), (32, 7200, 5, 0.3, 0.0), (17, 50, 49, 0.2, 0.1), (40, 13000, 1, 0.3, 0.0)]
+
+
+@pytest.mark.parametrize("B,Cn,topn,margin,tmargin", GT)
+def test_centre_triplet_gradient(B, Cn, topn, margin, tmargin):
+    g = torch.Generator().manual_seed(B + Cn + topn)
+    cosm = torch.tanh(0.8 * torch.randn(B, Cn, generator=g)).float()      # fp32-representable: both sides see the same numbers
+    labels = torch.randint(0, Cn, (B,), generator=g)
+    got, d = _centre_kernels(cosm, labels, margin, tmargin, topn, 0.7, 0.4, scale=0.5)
+    c64 = cosm.double().requires_grad_(True)
+    want = 0.5 * _gt_from_cos(c64, labels, margin, tmargin, topn, 0.7, 0.4)
+    gc, = torch.autograd.grad(want, c64)
+    assert abs(got - want.item()) <= 2e-5 * abs(want.item()), (got, want.item())
+    assert rel_fro(d[:, :Cn], gc) <= 4e-3, rel_fro(d[:, :Cn], gc)         # d is emitted as bf16
+    assert float(d[:, Cn:].abs().max()) == 0.0 if d.shape[1] > Cn else True
+
+
+GT_STEP = [
+    ("learnable_top1_between", dict(triplet_center="learnable", triplet_topn=1, margin=0.3, target_margin=0.1,
+                                    triplet_loss_weight=1.0, center_loss_weight=0.5, between_loss_weight=0.25)),
+    ("average_top5", dict(triplet_center="average", triplet_center_momentum=0.9, triplet_topn=5, margin=0.3, target_margin=0.0,
+                          triplet_loss_weight=1.0, center_loss_weight=0.1, between_loss_weight=0.0)),
+    ("learnable_all_featnorm", dict(triplet_center="learnable", triplet_topn=0, margin=0.05, target_margin=0.5,
+                                    triplet_loss_weight=2.0, center_loss_weight=0.0, between_loss_weight=1.0, feature_norm=True,
+                                    feature_scaling_factor=20.0)),
+]
+
+
+@pytest.mark.parametrize("name,extra", GT_STEP, ids=[c[0] for c in GT_STEP])
+def test_centre_triplet_train_step(name, extra):
+    from tf_kaldi_speaker_b200.misc.utils import ParamsPlain
+    from tf_kaldi_speaker_b200.model.trainer import Trainer
+    from tests.xv_testlib import make_batch
+    loss_type = "generalized_angular_triplet_loss"
+    B, T, D, Cn = 64, 60, 30, 300
+    pd = base_params()
+    pd.update(loss_compute="raw", l2_loss_weight=0.0, feature_norm=False)
+    pd.update(extra)
+    x, y = make_batch(B, T, D, Cn, seed=5)
+    po = O.ParamsPlain(**dict(pd))
+    P = O.init_params(D, po, Cn, loss_type, seed=4)
+    gen = torch.Generator().manual_seed(6)
+    for k in P:
+        if k.endswith("/gamma"):
+            P[k] = P[k] + 0.2 * torch.randn(P[k].shape, generator=gen, dtype=torch.float64)
+        elif k.endswith("/beta") or k.endswith("/bias"):
+            P[k] = P[k] + 0.1 * torch.randn(P[k].shape, generator=gen, dtype=torch.float64)
+    lr, gstep = 0.01, 100
+    loss_o, total_o, _, newP_o, _, ep_o = O.train_step(P, {}, x.double(), y, po, loss_type, lr, gstep)
+    grads_o = ep_o["__raw_grads"]
+
+    tr = Trainer(ParamsPlain(**dict(pd)), "/tmp/xv_test_model_gt_" + name)
+    tr.build("train", D, loss_type, Cn)
+    st = tr.engine.store
+    assert set(st.specs.keys()) == set(P.keys()), set(st.specs.keys()) ^ set(P.keys())
+    st.load_tf({k: v.numpy() for k, v in P.items()})
+    res = tr.train_step(x, y, lr, gstep, fetch_loss=True)
+    torch.cuda.synchronize()
+    loss_rel = abs(res["raw_loss"] - loss_o.item()) / abs(loss_o.item())
+    total_rel = abs(res["loss"] - total_o.item()) / abs(total_o.item())
+    emb = tr.endpoints["tdnn6_dense"].dense().cpu().numpy()
+    cos = min_cosine(emb, ep_o["tdnn6_dense"].detach().numpy())
+    print(name, "loss %.6f oracle %.6f loss_rel %.2e total_rel %.2e emb_cos %.6f" % (res["raw_loss"], loss_o.item(), loss_rel,
+                                                                                      total_rel, cos))
+    # End to end the loss is a count-normalised sum over a handful of (sample, centre) pairs selected on bf16-activation
+    # embeddings: one pair entering or leaving the set moves it by several per cent (average_top5: 4.3e-2, 1 of ~25 pairs).
+    assert loss_rel <= 8e-2 and total_rel <= 1e-2
+    assert cos >= 0.999
+    # What IS tight: the loss and the centre gradient as functions of the embeddings the CUDA step itself produced.
+    xc = tr.endpoints["output"].dense().double().cpu().requires_grad_(True)
+    wc = P["softmax/output/kernel"].clone().requires_grad_(True)
+    loss_tf, parts = O.generalized_angular_triplet_loss(xc, y, {"softmax/output/kernel": wc}, po, True, {})
+    tf_rel = abs(res["raw_loss"] - loss_tf.item()) / abs(loss_tf.item())
+    print("  teacher-forced loss rel %.2e" % tf_rel)
+    assert tf_rel <= 1e-3, (res["raw_loss"], loss_tf.item())
+    newv = st.export_tf()
+    average = extra["triplet_center"] == "average"
+    if not average:
+        gw_tf, = torch.autograd.grad(loss_tf, wc)
+        gw = st.export_tf(grads=True)["softmax/output/kernel"].astype(np.float64)
+        print("  teacher-forced centre gradient rel %.2e" % rel_fro(gw, gw_tf.numpy()))
+        assert rel_fro(gw, gw_tf.numpy()) <= 1e-2            # dLoss/dcos is emitted as bf16
+    if average:
+        # the centres moved by the moving-average rule, not by the optimizer, and carry no gradient / regulariser
+        assert "softmax/output/kernel" not in grads_o
+        w0 = P["softmax/output/kernel"].numpy()
+        assert rel_fro(newv["softmax/output/kernel"] - w0, newP_o["softmax/output/kernel"].numpy() - w0) <= 3e-2
+        # ... and exactly by that rule on the features the step itself produced
+        assert rel_fro(newv["softmax/output/kernel"] - w0, parts["average_centers"].detach().numpy() - w0) <= 1e-5
+    ge = st.export_tf(grads=True)
+    s = float(pd["weight_l2_regularizer"])
+    worst = {}
+    for n, go in grads_o.items():
+        gv = ge[n].astype(np.float64)
+        if O.l2_regularised(n):
+            gv = gv + s * P[n].numpy()
+        if np.linalg.norm(go.numpy()) < 1e-9:
+            continue
+        worst[n] = rel_fro(gv, go.numpy())
+        c = float(np.dot(gv.ravel(), go.numpy().ravel()) / (np.linalg.norm(gv) * np.linalg.norm(go.numpy()) + 1e-300))
+        assert worst[n] <= 0.35 and c >= 0.93, (n, worst[n], c)
+    print("  worst grads vs fp64:", sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+    for i in range(2):
+        r2 = tr.train_step(x, y, lr, gstep + 1 + i, fetch_loss=True)
+        assert np.isfinite(r2["loss"])
+    lv, _ = tr.valid_step(x, y)
+    Pn = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in st.export_tf().items()}
+    with torch.no_grad():
+        xo, _, _ = O.entire_network(x.double(), Pn, po, is_training=False)
+        lo, _ = O.loss_network(loss_type, xo, y, Pn, po, gstep, False, None)
+    print("  valid loss %.6f oracle %.6f" % (lv, lo.item()))
+    assert abs(lv - lo.item()) <= 1e-2 * abs(lo.item())

@@ -37,6 +37,11 @@ def declare_head_variables(engine, embedding_dim, num_outputs, params, loss_type
                                col_range=(sh.lo, sh.hi)))
         return
     cpad = _pad_to(num_outputs, 8)
+    if loss_type == "generalized_angular_triplet_loss" and params.triplet_center == "average":
+        # class centres updated on the fly like batch-norm statistics: not trainable, no regulariser (loss.py:755-760)
+        st.declare(VarSpec(name + "/output/kernel", (embedding_dim, num_outputs), (embedding_dim, cpad), l2=0.0,
+                           init="glorot", fans=(embedding_dim, num_outputs), trainable=False))
+        return
     st.declare(VarSpec(name + "/output/kernel", (embedding_dim, num_outputs), (embedding_dim, cpad), l2=l2,
                        init="glorot", fans=(embedding_dim, num_outputs)))
     if loss_type == "softmax":
@@ -227,3 +232,46 @@ def e2e_valid_loss(features, labels, num_outputs, params, is_training=None, reus
                               speakers=int(params.num_valid_speakers_per_batch),
                               segments=int(params.num_valid_segments_per_speaker))
     return loss, _metric_endpoints(loss, labels)
+
+
+def generalized_angular_triplet_loss(features, labels, num_outputs, params, is_training=None, reuse_variables=None,
+                                     name="softmax"):
+    """Angular triplet loss against the centres of the classes (model/loss.py:708-901, ``loss_compute = "raw"``).
+
+    Args:
+        features: [batch, dim] handle WITHOUT L2 normalisation.
+        labels: int tensor [batch].
+        num_outputs: #classes.
+        params: triplet_center "learnable" | "average" (+ triplet_center_momentum), loss_compute "raw", margin,
+                target_margin, triplet_topn (0: every class violating the margin, 1: hardest, k: top-k hardest),
+                triplet_loss_weight, center_loss_weight, between_loss_weight, l2_loss_weight (must be 0).
+        is_training: update the averaged centres / record the backward closure.
+    :return: (loss, endpoints)
+    """
+    assert features.data.dim() == labels.dim() + 1
+    assert params.triplet_center == "learnable" or params.triplet_center == "average"
+    assert params.loss_compute == "raw" or params.loss_compute == "softplus"
+    if params.loss_compute != "raw":
+        raise NotImplementedError("Not implemented.")                # loss.py:826
+    params.margin = float(params.margin)
+    params.target_margin = float(params.target_margin)
+    params.triplet_topn = int(params.triplet_topn)
+    params.triplet_loss_weight = float(params.triplet_loss_weight)
+    params.center_loss_weight = float(params.center_loss_weight)
+    params.between_loss_weight = float(params.between_loss_weight)
+    assert params.l2_loss_weight == 0.0, "The weight decay is applied by regularization term, not the loss!"
+    eng = get_engine()
+    if eng.head_shard is not None:
+        raise NotImplementedError("generalized_angular_triplet_loss is not available with the class-sharded head")
+    average = params.triplet_center == "average"
+    loss, cosm, _ = eng.centre_triplet_head(
+        features, labels, name + "/output/kernel", num_outputs, bool(is_training),
+        scaling=float(getattr(features, "scaling", 0.0) or 0.0), average=average,
+        momentum=float(params.triplet_center_momentum) if average else 0.0, margin=params.margin,
+        target_margin=params.target_margin, topn=params.triplet_topn, w_triplet=params.triplet_loss_weight,
+        w_center=params.center_loss_weight, w_between=params.between_loss_weight)
+    endpoints = OrderedDict()
+    endpoints["average_centers"] = eng.store.view(name + "/output/kernel")
+    endpoints["cos"] = cosm[:, :num_outputs]
+    endpoints["labels"] = labels
+    return loss, endpoints

@@ -21,7 +21,8 @@ from ..runtime import Engine, ScaledUtt, set_engine
 from . import tdnn as tdnn_mod
 from .tdnn import tdnn
 from .loss import (softmax, asoftmax, additive_margin_softmax, additive_angular_margin_softmax,
-                   semihard_triplet_loss, angular_triplet_loss, e2e_valid_loss, METRIC_LOSSES,
+                   semihard_triplet_loss, angular_triplet_loss, e2e_valid_loss, generalized_angular_triplet_loss,
+                   METRIC_LOSSES,
                    declare_head_variables, margin_schedule)
 
 
@@ -89,8 +90,9 @@ class Trainer(object):
                 self.loss_network = semihard_triplet_loss
             elif loss_type == "angular_triplet_loss":
                 self.loss_network = angular_triplet_loss
+            elif loss_type == "generalized_angular_triplet_loss":
+                self.loss_network = generalized_angular_triplet_loss
             else:
-                # generalized_angular_triplet_loss (loss.py:708-901, moving-average class centres) is not built
                 raise NotImplementedError("Not implement %s loss" % self.loss_type)
             self.num_speakers = num_speakers
             if self.global_step is None:

@@ -1145,6 +1145,84 @@ class Engine(object):
             self.tape.append(bwd)
         return self.scalars[0], x
 
+    def centre_triplet_head(self, u, labels, kernel, num_outputs, training, scaling=0.0, average=False, momentum=0.0,
+                            margin=0.0, target_margin=0.0, topn=1, w_triplet=1.0, w_center=0.0, w_between=0.0):
+        """Generalized angular triplet loss against class centres (model/loss.py:708-901, loss_compute "raw").  The cosine of
+        every sample to every (normalised) centre is the head's tcgen05 GEMM on the [hi|hi|lo] split operands; a row kernel
+        mines the hardest top-n centres and writes dLoss/dcos, which feeds the head's own dW / dx GEMMs and normalisation
+        Jacobians.  ``average``: the centres are a moving average of the class members, updated before the cosines are
+        taken (no gradient), instead of trainable parameters."""
+        st = self.store
+        Wm = st.view(kernel)                           # fp32 [E, cpad]
+        E, cpad = Wm.shape
+        Cn = num_outputs
+        B = u.data.shape[0]
+        s = L.stream_ptr
+        labels = labels.to(device=self.device, dtype=torch.int32).contiguous()
+        rep = 1.0 if self.inv_global_batch is None else 1.0 / max(1, int(round(1.0 / (self.inv_global_batch * B))))
+        if average and rep != 1.0:
+            raise NotImplementedError("triplet_center = average under data parallelism (every replica would keep its own centres)")
+        x3 = self.buf("head/x3", (B, 3 * E), torch.bfloat16)
+        xnorm = self.buf("head/xnorm", (B,), torch.float32)
+        urinv = self.buf("head/urinv", (B,), torch.float32)
+        if average and training:
+            # the centres move towards the features the loss function was GIVEN (l2-scaled when feature_norm is on)
+            feats = u.data
+            if scaling > 0.0:
+                feats = self.buf("head/xs", (B, E), torch.float32)
+                self.call(self.lib.xv_head_prep_features, L.ptr(u.data), C.c_float(scaling), L.ptr(feats), L.ptr(x3), L.ptr(xnorm),
+                          L.ptr(urinv), B, E, s())
+            delta = self.buf("head/centre_delta", (B, E), torch.float32)
+            if self._head_prefetch is not None:        # normalised from the OLD centres: discard
+                self.join_side_stream()
+                self._head_prefetch = None
+            self.call(self.lib.xv_center_update, L.ptr(Wm), L.ptr(feats), L.ptr(labels), L.ptr(delta), B, E, C.c_int64(cpad),
+                      C.c_float(1.0 - momentum), s())
+            self.launches += 1
+        wn3 = self.buf("head/wn3", (3 * E, cpad), torch.bfloat16)
+        inv_norm = self.buf("head/inv_norm", (cpad,), torch.float32)
+        if self._head_prefetch == (kernel, 1):
+            self.join_side_stream()
+            self._head_prefetch = None
+        else:
+            self.call(self.lib.xv_head_prep_weights, L.ptr(Wm), L.ptr(wn3), L.ptr(inv_norm), E, cpad, C.c_int64(cpad), 1, s())
+        x = self.buf("head/x", (B, E), torch.float32)          # l2_normalize(features): scaling 1 on the raw output
+        self.call(self.lib.xv_head_prep_features, L.ptr(u.data), C.c_float(1.0), L.ptr(x), L.ptr(x3), L.ptr(xnorm), L.ptr(urinv),
+                  B, E, s())
+        cosm = self.buf("head/cos", (B, cpad), torch.float32)
+        self.gemm(L.operand(x3, False), L.operand(wn3, True, cols=Cn), B, Cn, 3 * E, cosm, epilogue=L.EPI_F32)
+        trainable_w = training and not average
+        d = self.buf("head/d", (B, cpad), torch.bfloat16) if training else None
+        counters = self.buf("head/gt_counters", (8,), torch.float32)
+        loss = self.scalars[0:1]
+        self.call(self.lib.xv_center_triplet, L.ptr(cosm), L.ptr(labels), B, Cn, C.c_int64(cpad), C.c_float(margin),
+                  C.c_float(target_margin), int(topn), C.c_float(w_triplet), C.c_float(w_center), C.c_float(rep), L.ptr(loss),
+                  L.ptr(d), L.ptr(counters), s())
+        tsum = self.buf("head/centre_sum", (E,), torch.float32)
+        self.call(self.lib.xv_center_between, L.ptr(Wm), L.ptr(inv_norm), E, Cn, C.c_int64(cpad), C.c_float(w_between * rep),
+                  L.ptr(tsum), L.ptr(loss), s())
+        self.launches += 2
+        if training:
+            def bwd():
+                if trainable_w:
+                    gw = st.grad(kernel)
+                    with self.on_side_stream(self.side_utt):
+                        self.gemm(L.operand(x3, True, cols=E), L.operand(d, True, cols=Cn), E, Cn, B, gw, epilogue=L.EPI_F32)
+                        if w_between != 0.0:
+                            self.call(self.lib.xv_center_between_bwd, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), L.ptr(tsum), E, Cn,
+                                      C.c_int64(cpad), C.c_float(w_between * rep), s())
+                        self.call(self.lib.xv_head_finish_dw, L.ptr(gw), L.ptr(Wm), L.ptr(inv_norm), E, cpad, s())
+                dxg = self.buf("head/dxg", (B, E), torch.float32, zero=True)
+                sp = self.splits_for(B, E, Cn)
+                self.gemm(L.operand(d, False, cols=Cn), L.operand(wn3, False, rows=E, cols=Cn), B, E, Cn, dxg,
+                          epilogue=L.EPI_F32, splits=sp)
+                du = self.buf(u.name + "/grad", (B, E), torch.float32)
+                self.call(self.lib.xv_head_finish_dx, L.ptr(dxg), L.ptr(None), L.ptr(x), L.ptr(xnorm), L.ptr(u.data), L.ptr(urinv),
+                          C.c_float(1.0), L.ptr(du), B, E, s())
+                u.grad = du
+            self.tape.append(bwd)
+        return self.scalars[0], cosm, x
+
     def margin_head_sharded(self, u, labels, kernel, bias, head_type, num_outputs, training, margin=0.0, asoftmax_m=1,
                             scaling=0.0):
         """Class-sharded variant of margin_head (north_star "Data parallelism"; SURVEY 8e 2'): this rank holds columns
