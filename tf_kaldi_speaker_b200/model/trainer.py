@@ -26,6 +26,25 @@ from .loss import (softmax, asoftmax, additive_margin_softmax, additive_angular_
                    declare_head_variables, margin_schedule)
 
 
+class LossHandle(object):
+    """Result of ``train_step(..., fetch_loss="async")``: the step's {"raw_loss", "loss"} once its 20-byte device-to-host
+    copy has landed.  The pinned slot is reused after four further asynchronous fetches; an unread handle is latched first."""
+
+    def __init__(self, trainer, host, event, seq):
+        self._trainer, self._host, self._event, self._value, self._seq = trainer, host, event, None, seq
+
+    def result(self):
+        if self._value is None:
+            self._event.synchronize()
+            vals = self._host[:5].tolist()
+            self._value = {"raw_loss": vals[0], "loss": vals[0] + vals[1] + vals[3]}
+            if self._seq > self._trainer._loss_seq_read:       # train_ops mirrors the NEWEST step that has been read
+                self._trainer._loss_seq_read = self._seq
+                self._trainer.train_ops = dict(self._value)
+            self._host = self._event = None
+        return dict(self._value)
+
+
 class Trainer(object):
     def __init__(self, params, model_dir, single_cpu=False, engine=None):
         """Args mirror model/trainer.py:24.  ``single_cpu`` is accepted and ignored (the CUDA path has no CPU mode)."""
@@ -55,6 +74,9 @@ class Trainer(object):
         self._static = {}
         self._copy_stream = None
         self._h2d_event = None
+        self._loss_ring = None
+        self._loss_seq = 0
+        self._loss_seq_read = 0
         self.use_cuda_graph = bool(params.dict.get("cuda_graph", True))
         self._captured = 0           # batch shapes whose step has been captured
         self._in_memory = False      # True once this object holds parameters newer than (or loaded from) the checkpoint
@@ -192,28 +214,53 @@ class Trainer(object):
         if self._h2d_event is None:
             self._copy_stream = torch.cuda.Stream(device=self.engine.device)
             self._h2d_event = torch.cuda.Event(enable_timing=False, external=True)
-        # Host batches are uploaded on a copy stream: the step waits for them only in front of the first kernel that reads
-        # the features (an external event-wait node inside the captured graph, see _fwd_bwd), so the gradient-buffer fill,
-        # the scalar feed and the head weight preparation at the start of the step overlap the PCIe transfer.
-        cs = self._copy_stream if from_host else main
-        if from_host:
-            cs.wait_stream(main)            # the previous step has finished reading the static buffers
+        if not from_host:
+            st["x"].copy_(features, non_blocking=True)
+            st["y"].copy_(labels.to(torch.int32), non_blocking=True)
+            self._h2d_event.record(main)
+            return st
+        # Host batches go through two device staging buffers on a copy stream: the upload of step n+1 runs while step n is
+        # still computing (it only has to wait until step n-1's staging buffer has been consumed), and the step itself
+        # starts with a 3 MB device-to-device copy into the static buffers the captured graph reads.  Without the staging
+        # pair the upload could not start before the previous step had finished with the static buffers (round 1 / early
+        # round 2: 60 us of PCIe time exposed per step).
+        if "stage" not in st:
+            dev = self.engine.device
+            st["stage"] = [(torch.empty(key, dtype=torch.float32, device=dev), torch.empty((key[0],), dtype=torch.int32, device=dev))
+                           for _ in range(2)]
+            st["staged"] = [torch.cuda.Event() for _ in range(2)]
+            st["consumed"] = [None, None]
+            st["k"] = 0
+        k = st["k"] = 1 - st["k"]
+        sx, sy = st["stage"][k]
+        cs = self._copy_stream
+        if st["consumed"][k] is not None:
+            cs.wait_event(st["consumed"][k])
         with torch.cuda.stream(cs):
             if hasattr(features, "decode_into"):
                 # dataset.feeder.CompressedSegmentBatch: H2D of the raw uint8 crops + on-device dequantise / transpose
-                features.decode_into(st["x"])
+                features.decode_into(sx)
                 self.engine.launches += 1
             else:
-                st["x"].copy_(features, non_blocking=True)       # H2D (or D2D) of this step's batch
-            st["y"].copy_(labels.to(torch.int32), non_blocking=True)
-            self._h2d_event.record(cs)
+                sx.copy_(features, non_blocking=True)            # H2D of this step's batch
+            sy.copy_(labels.to(torch.int32), non_blocking=True)
+            st["staged"][k].record(cs)
+        st["host_ref"] = (features, labels)        # keep the (pinned) source alive until the next call
+        main.wait_event(st["staged"][k])
+        st["x"].copy_(sx, non_blocking=True)
+        st["y"].copy_(sy, non_blocking=True)
+        if st["consumed"][k] is None:
+            st["consumed"][k] = torch.cuda.Event()
+        st["consumed"][k].record(main)
+        self._h2d_event.record(main)
         return st
 
     def train_step(self, features, labels, learning_rate, global_step=None, fetch_loss=False):
         """The hot-loop body = sess.run(train_op) (trainer.py:491-508): forward, backward, [all-reduce], optimizer,
         BN moving statistics.  After two eager warm-up calls per batch shape the whole step is captured into a CUDA
         graph and replayed; learning rate / margin schedule live in device scalars set before each replay.
-        Returns {"loss": total, "raw_loss": loss} when fetch_loss (one 16-byte D2H read), else None."""
+        Returns {"loss": total, "raw_loss": loss} when fetch_loss (one 20-byte D2H read, synchronous), a LossHandle when
+        fetch_loss == "async" (the same read queued behind the step; ``.result()`` waits for it), else None."""
         eng = self.engine
         if global_step is None:
             global_step = self.global_step or 0
@@ -329,6 +376,22 @@ class Trainer(object):
     def _finish_step(self, global_step, fetch_loss):
         eng = self.engine
         self.global_step = int(global_step) + 1
+        if fetch_loss == "async" and (self.dp is None or (self.dp.scalars_reduced and eng.head_shard is None)):
+            # the step's loss record is copied to pinned host memory behind the step; the caller reads it when it needs it
+            # (LossHandle.result()), typically one step later, so the host never waits for the step it has just queued
+            if self._loss_ring is None:
+                self._loss_ring = [[torch.empty(8, dtype=torch.float32).pin_memory(), torch.cuda.Event(), None] for _ in range(4)]
+                self._loss_slot = 0
+            self._loss_slot = (self._loss_slot + 1) % len(self._loss_ring)
+            slot = self._loss_ring[self._loss_slot]
+            if slot[2] is not None:
+                slot[2].result()          # a handle nobody has read yet owns this slot: latch its value (copied 4 steps ago)
+            host, ev = slot[0], slot[1]
+            host[:5].copy_(eng.scalars[:5], non_blocking=True)
+            ev.record()
+            self._loss_seq += 1
+            slot[2] = LossHandle(self, host, ev, self._loss_seq)
+            return slot[2]
         if fetch_loss:
             vals = eng.scalars[:5].tolist()          # one D2H read
             raw, l2, pen = vals[0], vals[1], vals[3]
@@ -395,6 +458,7 @@ class Trainer(object):
             data_loader.start()
         steps = int(self.params.num_steps_per_epoch)
         epoch = int(curr_step / steps)
+        pending = None
         try:
             for step in range(curr_step % steps, steps):
                 try:
@@ -402,10 +466,12 @@ class Trainer(object):
                             step % int(self.params.show_training_progress) == 0)
                     t0 = time.time()
                     features, labels = data_loader.fetch()
-                    res = self.train_step(features, labels, learning_rate, curr_step, fetch_loss=show)
+                    res = self.train_step(features, labels, learning_rate, curr_step, fetch_loss="async" if show else False)
+                    if pending is not None:      # the progress line of the previous logged step: its loss has landed by now
+                        self._print_progress(*pending)
+                        pending = None
                     if show:
-                        print("Epoch: [%2d] step: [%2d/%2d] time: %.4f s/step, raw loss: %f, total loss: %f"
-                              % (epoch, step, steps, time.time() - t0, res["raw_loss"], res["loss"]), flush=True)
+                        pending = (epoch, step, steps, t0, res)
                     self._in_memory = True
                     if step % int(self.params.save_checkpoints_steps) == 0 and curr_step != 0:
                         self.save(curr_step)
@@ -414,11 +480,19 @@ class Trainer(object):
                     print("Finished reading features.")
                     break
         finally:
+            if pending is not None:
+                self._print_progress(*pending)
             if hasattr(data_loader, "stop"):
                 data_loader.stop()
         self.global_step = curr_step
         self.save(curr_step)
         return
+
+    @staticmethod
+    def _print_progress(epoch, step, steps, t0, res):
+        r = res.result() if hasattr(res, "result") else res
+        print("Epoch: [%2d] step: [%2d/%2d] time: %.4f s/step, raw loss: %f, total loss: %f"
+              % (epoch, step, steps, time.time() - t0, r["raw_loss"], r["loss"]), flush=True)
 
     # ------------------------------------------------------------------ validation (trainer.py:261-303, 592-706)
     def _valid_params(self):
