@@ -74,6 +74,7 @@ class Trainer(object):
         self._static = {}
         self._copy_stream = None
         self._h2d_event = None
+        self._step_done = None
         self._loss_ring = None
         self._loss_seq = 0
         self._loss_seq_read = 0
@@ -220,22 +221,17 @@ class Trainer(object):
             self._h2d_event.record(main)
             return st
         # Host batches go through two device staging buffers on a copy stream: the upload of step n+1 runs while step n is
-        # still computing (it only has to wait until step n-1's staging buffer has been consumed), and the step itself
-        # starts with a 3 MB device-to-device copy into the static buffers the captured graph reads.  Without the staging
-        # pair the upload could not start before the previous step had finished with the static buffers (round 1 / early
-        # round 2: 60 us of PCIe time exposed per step).
+        # still computing (it only has to wait until step n-1's staging buffer has been handed over); a 3 MB device-to-device
+        # copy then moves it into the static buffers the captured graph reads.  Without the staging pair the upload could not
+        # start before the previous step had finished with the static buffers (60 us of PCIe time exposed per step).
         if "stage" not in st:
             dev = self.engine.device
             st["stage"] = [(torch.empty(key, dtype=torch.float32, device=dev), torch.empty((key[0],), dtype=torch.int32, device=dev))
                            for _ in range(2)]
-            st["staged"] = [torch.cuda.Event() for _ in range(2)]
-            st["consumed"] = [None, None]
             st["k"] = 0
         k = st["k"] = 1 - st["k"]
         sx, sy = st["stage"][k]
-        cs = self._copy_stream
-        if st["consumed"][k] is not None:
-            cs.wait_event(st["consumed"][k])
+        cs = self._copy_stream          # in-order: the upload into stage k follows the hand-over that last read stage k
         with torch.cuda.stream(cs):
             if hasattr(features, "decode_into"):
                 # dataset.feeder.CompressedSegmentBatch: H2D of the raw uint8 crops + on-device dequantise / transpose
@@ -244,15 +240,15 @@ class Trainer(object):
             else:
                 sx.copy_(features, non_blocking=True)            # H2D of this step's batch
             sy.copy_(labels.to(torch.int32), non_blocking=True)
-            st["staged"][k].record(cs)
+            # ... and, once the previous step has finished with the static buffers, the device-to-device hand-over -- still on
+            # the copy stream, so that the step's first kernels (gradient fill, scalar feed, head weight preparation) run
+            # beside it; the captured graph waits for _h2d_event only in front of the first kernel that reads the features
+            if self._step_done is not None:
+                cs.wait_event(self._step_done)
+            st["x"].copy_(sx, non_blocking=True)
+            st["y"].copy_(sy, non_blocking=True)
+            self._h2d_event.record(cs)
         st["host_ref"] = (features, labels)        # keep the (pinned) source alive until the next call
-        main.wait_event(st["staged"][k])
-        st["x"].copy_(sx, non_blocking=True)
-        st["y"].copy_(sy, non_blocking=True)
-        if st["consumed"][k] is None:
-            st["consumed"][k] = torch.cuda.Event()
-        st["consumed"][k].record(main)
-        self._h2d_event.record(main)
         return st
 
     def train_step(self, features, labels, learning_rate, global_step=None, fetch_loss=False):
@@ -371,6 +367,9 @@ class Trainer(object):
                 run(ga, gb)
             else:
                 run(None, None)
+        if self._step_done is None:
+            self._step_done = torch.cuda.Event()
+        self._step_done.record()          # the static input buffers may be overwritten from here on (see _static_batch)
         return self._finish_step(global_step, fetch_loss)
 
     def _finish_step(self, global_step, fetch_loss):

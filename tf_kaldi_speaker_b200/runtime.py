@@ -338,9 +338,10 @@ class Engine(object):
         self.fuse_bn_bwd = True          # dgrad epilogues accumulate the producer layer's BN dgamma / dbeta
         import os as _os
         # shortest dgrad K loop whose epilogue also forms the producer's BN-backward sums (a separate reduce pass over y and
-        # dX costs ~15 us at config 2; the packed-f32x2 column pass +4..8 us per launch, +7.7 us on the K = 512 dgrad of tdnn4:
-        # 0.9326 -> 0.9276 ms per step with the K = 512 launch included)
-        self.fuse_bn_bwd_min_k = int(_os.environ.get("XV_FUSE_BNBWD_MINK", "512"))
+        # dX costs ~15 us at config 2; the packed-f32x2 column pass +4..8 us per launch).  XV_FUSE_BNBWD_MINK=512 also fuses the
+        # K = 512 dgrad of tdnn4 (+7.7 us on an 18 us launch against a 14.7 us reduce kernel): 0.9326 -> 0.9276 ms per step in
+        # one A/B pair, inside the run-to-run spread -- left off so that the GEMM launch does GEMM work only
+        self.fuse_bn_bwd_min_k = int(_os.environ.get("XV_FUSE_BNBWD_MINK", "1024"))
         self.fold_inference_bn = True    # inference: BN (moving statistics) + relu in the GEMM epilogue, no separate apply pass
         self.side_wgrad = False          # frame-level wgrad GEMMs on a second stream: measured 1.067 vs 1.056 ms (no gain)
         # utterance-level weight-gradient work (tdnn6 / tdnn7 / head dW GEMMs, head_finish_dw) and the head's weight
