@@ -52,7 +52,7 @@ def _bucket(t, q=256):
     return max(q, (t + q - 1) // q * q)
 
 
-_COPY_THREADS = 6
+_COPY_THREADS = int(os.environ.get("XV_EXTRACT_COPY_THREADS", "6"))      # packer sub-copies (NumPy releases the GIL)
 _copy_executor = None
 
 

@@ -75,6 +75,7 @@ class Trainer(object):
         self._copy_stream = None
         self._h2d_event = None
         self._step_done = None
+        self._up = None
         self._loss_ring = None
         self._loss_seq = 0
         self._loss_seq_read = 0
@@ -592,16 +593,51 @@ class Trainer(object):
         emb = self.predict_batch_padded(features, None)
         return emb[0] if rank == 2 else emb
 
+    def _upload(self, features):
+        """Pinned host batch -> one of two persistent device buffers, on the copy stream: the upload of batch n+1 runs beside
+        the kernels of batch n (a buffer is overwritten only after the batch that read it has finished).  Anything else
+        (numpy, pageable, device tensors) takes the plain path.  Returns (device tensor, release callback)."""
+        if not (torch.is_tensor(features) and not features.is_cuda and features.is_pinned() and features.dtype == torch.float32):
+            return self._to_device(features)[0], (lambda: None)
+        dev = self.engine.device
+        if self._up is None:
+            self._up = [{"buf": None, "free": None, "ready": torch.cuda.Event()} for _ in range(2)]
+            self._up_k = 0
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+        self._up_k = 1 - self._up_k
+        slot = self._up[self._up_k]
+        n = features.numel()
+        cs, main = self._copy_stream, torch.cuda.current_stream()
+        if slot["buf"] is None or slot["buf"].numel() < n:
+            if slot["free"] is not None:
+                slot["free"].synchronize()
+            slot["buf"] = torch.empty(int(n * 1.25), dtype=torch.float32, device=dev)
+        if slot["free"] is not None:
+            cs.wait_event(slot["free"])
+        with torch.cuda.stream(cs):
+            d = slot["buf"][:n].view(features.shape)
+            d.copy_(features, non_blocking=True)
+            slot["ready"].record(cs)
+        main.wait_event(slot["ready"])
+
+        def release():
+            if slot["free"] is None:
+                slot["free"] = torch.cuda.Event()
+            slot["free"].record(main)
+        return d, release
+
     def predict_batch_padded(self, features, lengths, as_device=False):
         """[N, Tmax, D] (+ optional lengths [N]) -> np [N, E]; rows are independent (BN in inference mode, masked
         pooling), so a ragged batch gives the same result as one call per utterance (extract.py:90).
         ``as_device``: return a device tensor (a copy: the workspace is reused by the next call) without synchronising,
         so the caller can overlap the next batch's upload with this one's compute."""
         eng = set_engine(self.engine)
-        feats, _ = self._to_device(features)
+        feats, release = self._upload(features)
         ln = None if lengths is None else torch.as_tensor(np.asarray(lengths), dtype=torch.int32).to(eng.device, non_blocking=True)
         eng.begin_step(False)
         _, endpoints = self.entire_network(feats, self.params, False, True, lengths=ln)
+        release()
         self.endpoints = endpoints
         node = endpoints[self.params.embedding_node]
         if as_device:
@@ -616,12 +652,13 @@ class Trainer(object):
         if self.params.pooling_type != "statistics_pooling":
             raise NotImplementedError("predict_ragged supports statistics_pooling; use predict_batch_padded")
         eng = set_engine(self.engine)
-        feats, _ = self._to_device(flat_features)
+        feats, release = self._upload(flat_features)
         feats = feats.view(1, feats.shape[0], feats.shape[1])
         st = torch.as_tensor(np.asarray(starts), dtype=torch.int32).to(eng.device, non_blocking=True)
         ln = torch.as_tensor(np.asarray(lengths), dtype=torch.int32).to(eng.device, non_blocking=True)
         eng.begin_step(False)
         _, endpoints = self.entire_network(feats, self.params, False, True, ragged=(st, ln))
+        release()
         self.endpoints = endpoints
         node = endpoints[self.params.embedding_node]
         if not hasattr(node, "col_map"):
