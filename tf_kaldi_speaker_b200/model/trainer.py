@@ -217,8 +217,11 @@ class Trainer(object):
             self._copy_stream = torch.cuda.Stream(device=self.engine.device)
             self._h2d_event = torch.cuda.Event(enable_timing=False, external=True)
         if not from_host:
-            st["x"].copy_(features, non_blocking=True)
-            st["y"].copy_(labels.to(torch.int32), non_blocking=True)
+            # a batch written straight into the static buffers (Trainer.input_buffers) needs no copy at all
+            if features.data_ptr() != st["x"].data_ptr():
+                st["x"].copy_(features, non_blocking=True)
+            if not (labels.is_cuda and labels.data_ptr() == st["y"].data_ptr()):
+                st["y"].copy_(labels.to(torch.int32), non_blocking=True)
             self._h2d_event.record(main)
             return st
         # Host batches go through two device staging buffers on a copy stream: the upload of step n+1 runs while step n is
@@ -251,6 +254,19 @@ class Trainer(object):
             self._h2d_event.record(cs)
         st["host_ref"] = (features, labels)        # keep the (pinned) source alive until the next call
         return st
+
+    def input_buffers(self, batch, frames, dim=None):
+        """The static device tensors (features float32 [batch, frames, dim], labels int32 [batch]) the captured step of this
+        batch shape reads.  A producer that already works on the device (an on-device augmentation or decode kernel) can
+        write the next batch straight into them and pass them to train_step, which then skips its device-to-device copy."""
+        key = (int(batch), int(frames), int(dim if dim is not None else self.dim))
+        st = self._static.get(key)
+        if st is None:
+            dev = self.engine.device
+            st = {"x": torch.empty(key, dtype=torch.float32, device=dev),
+                  "y": torch.empty((key[0],), dtype=torch.int32, device=dev), "calls": 0, "graphs": None, "launches": 0}
+            self._static[key] = st
+        return st["x"], st["y"]
 
     def train_step(self, features, labels, learning_rate, global_step=None, fetch_loss=False):
         """The hot-loop body = sess.run(train_op) (trainer.py:491-508): forward, backward, [all-reduce], optimizer,
