@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(256) gtriplet_rows_kernel(const float* __restr
       }
     }
   } else {
+    __syncthreads();                                      // every thread has read its copy of the target distance
     if (threadIdx.x == 0) sd[y] = INFINITY;               // the target is pushed above the row maximum (loss.py:790)
     __syncthreads();
     for (int k = 0; k < g.topn; ++k) {
