@@ -181,9 +181,16 @@ def test_metric_train_step(name, loss_type, extra):
     print(name, "loss %.6f oracle %.6f loss_rel %.2e total_rel %.2e emb_cos %.6f" % (res["raw_loss"], loss_o.item(), loss_rel,
                                                                                       total_rel, cos))
     # the mining decisions sit on bf16-activation embeddings: a flipped hardest / semi-hard choice moves the loss by the
-    # difference of two neighbouring pairwise entries
-    assert loss_rel <= 1e-2 and total_rel <= 1e-2
+    # difference of two neighbouring pairwise entries (measured 5e-5 .. 7.4e-3 run to run)
+    assert loss_rel <= 3e-2 and total_rel <= 1e-2
     assert cos >= 0.999
+    # what IS tight: the loss as a function of the embeddings the CUDA step itself produced
+    with torch.no_grad():
+        xc = tr.endpoints["output"].dense().double().cpu()
+        loss_tf, _ = O.loss_network(loss_type, xc, y, P, po, gstep)
+    tf_rel = abs(res["raw_loss"] - loss_tf.item()) / abs(loss_tf.item())
+    print("  teacher-forced loss rel %.2e" % tf_rel)
+    assert tf_rel <= 2e-4, (res["raw_loss"], loss_tf.item())
     ge = st.export_tf(grads=True)
     s = float(pd["weight_l2_regularizer"])
     worst = {}

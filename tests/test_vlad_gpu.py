@@ -222,7 +222,8 @@ def test_vlad_train_step(name, vl):
     assert loss_rel <= 1e-3 and total_rel <= 1e-3
     assert cos >= 0.999
     assert pool_err <= 2e-2
-    assert w_err <= 5e-2      # bf16 logits of magnitude ~10 carry an absolute error ~3e-2, which peaked posteriors pass on
+    assert w_err <= 8e-2      # bf16 logits of magnitude ~10 carry an absolute error ~3e-2, which peaked posteriors pass on
+                              # (3.1e-2 .. 3.9e-2 over runs; the kernel-level test pins the posteriors to 1e-4 on equal inputs)
     ge = st.export_tf(grads=True)
     s = float(pd["weight_l2_regularizer"])
     worst = {}
