@@ -27,6 +27,14 @@ __device__ __forceinline__ void a_load8(const __nv_bfloat16* p, float (&f)[8]) {
     f[2 * i + 1] = t.y;
   }
 }
+__device__ __forceinline__ void a_unpack8(const ABf16x8& r, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(r.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
 __device__ __forceinline__ void a_store8(__nv_bfloat16* p, const float (&f)[8]) {
   ABf16x8 r;
 #pragma unroll
@@ -242,7 +250,8 @@ __global__ void __launch_bounds__(256) att_pool_fwd_kernel(const __nv_bfloat16* 
 //   dv[t,c]  = w[h(c),t] * (gm_c + 2 gv_c (v - mean_c))          (+= when accumulate)
 //   dw[h,t]  = sum_{c in h} gm_c v + gv_c (v - mean_c)^2
 // with gm = dL/dmean, gv = dL/dstd / (2 std) where the variance is above the floor, else 0.
-__global__ void __launch_bounds__(256) att_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+template <bool ONE_HEAD, bool ACC>
+__global__ void __launch_bounds__(256, ONE_HEAD ? 4 : 1) att_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ pooled,
                                                            const float* __restrict__ dpooled,
                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int H,
@@ -257,6 +266,7 @@ __global__ void __launch_bounds__(256) att_pool_bwd_kernel(const __nv_bfloat16* 
   const int L = lengths ? lengths[b] : seg_valid;
   const float* pb = pooled + static_cast<long long>(b) * 2 * cpad;
   const float* gb = dpooled + static_cast<long long>(b) * 2 * cpad;
+  float csum = 0.f;
   for (int c = threadIdx.x; c < cpad; c += 256) {
     float mu = 0.f, gm = 0.f, gv = 0.f;
     if (c < c_real) {
@@ -265,13 +275,80 @@ __global__ void __launch_bounds__(256) att_pool_bwd_kernel(const __nv_bfloat16* 
       const float sd = pb[cpad + c];
       if (sd * sd > 1.0000001e-12f) gv = gb[cpad + c] / (2.0f * sd);
     }
-    s_mu[c] = mu; s_gm[c] = gm; s_gv[c] = gv;
+    if (ONE_HEAD) {
+      // dv = w (A v + Bc), dw = sum_c v (A/2 v + Bc) + sum_c Cc   with A = 2 gv, Bc = gm - 2 gv mu, Cc = gv mu^2:
+      // two per-channel vectors instead of three, 5 flops per element instead of 8
+      s_mu[c] = 2.0f * gv;
+      s_gm[c] = gm - 2.0f * gv * mu;
+      csum += gv * mu * mu;
+    } else {
+      s_mu[c] = mu; s_gm[c] = gm; s_gv[c] = gv;
+    }
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  __shared__ float s_red[8];
+  if (ONE_HEAD) {
+    csum = warp_sum(csum);
+    if (lane == 0) s_red[wp] = csum;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (ONE_HEAD) {
+    csum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) csum += s_red[k];
+  }
   const int dvh = c_real / H;
   const int t0 = blockIdx.x * 64;
   const int t1 = min(t0 + 64, seg_len);
+  if (ONE_HEAD) {
+    // one head (the shipped configuration), cpad <= 2048: a single weight per frame, no head bookkeeping, and ALL of a frame's
+    // 16-byte loads issued before the first use (up to 8 per lane) -- the generic loop below keeps one load in flight per
+    // lane and is latency-bound (95 us for 157 MB at config 4)
+    for (int t = t0 + wp; t < t1; t += 8) {
+      const long long m = static_cast<long long>(b) * seg_len + t;
+      const bool valid = t < L;
+      __nv_bfloat16* drow = dx + m * ld;
+      if (!valid) {
+        if (!ACC) {
+          const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int c0 = lane * 8; c0 < cpad; c0 += 256) a_store8(drow + c0, z);
+        }
+        if (lane == 0) dw[static_cast<long long>(b) * seg_len + t] = 0.f;
+        continue;
+      }
+      const float wa = w[static_cast<long long>(b) * seg_len + t];
+      const __nv_bfloat16* xrow = x + m * ld;
+      ABf16x8 raw[8], praw[8];          // rows stay packed (4 registers per 8 channels) until they are used
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c0 = lane * 8 + 256 * i;
+        if (c0 < cpad) {
+          raw[i] = *reinterpret_cast<const ABf16x8*>(xrow + c0);
+          if (ACC) praw[i] = *reinterpret_cast<const ABf16x8*>(drow + c0);
+        }
+      }
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c0 = lane * 8 + 256 * i;
+        if (c0 < cpad) {
+          float v[8], prev[8], ca[8], cb[8], o[8];
+          a_unpack8(raw[i], v);
+          if (ACC) a_unpack8(praw[i], prev);
+          a_load8f(s_mu + c0, ca); a_load8f(s_gm + c0, cb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a = fmaf(v[j], fmaf(0.5f * ca[j], v[j], cb[j]), a);
+            o[j] = wa * fmaf(ca[j], v[j], cb[j]) + (ACC ? prev[j] : 0.f);
+          }
+          a_store8(drow + c0, o);
+        }
+      }
+      a = warp_sum(a);
+      if (lane == 0) dw[static_cast<long long>(b) * seg_len + t] = a + csum;
+    }
+    return;
+  }
   for (int t = t0 + wp; t < t1; t += 8) {
     const long long m = static_cast<long long>(b) * seg_len + t;
     const bool valid = t < L;
@@ -389,81 +466,103 @@ __global__ void __launch_bounds__(256) att_softmax_bwd_kernel(const float* __res
 
 // ------------------------------------------------------------------------------------------------
 // scores backward: dkey[m, d] = sum_h de[b,h,t] qpad[h,d] (bf16, zero on invalid frames) and
-// dqpad[h, d] += sum_m de[b,h,t] key[m,d].  Row-streaming grid (ldk/128, rows/64); 4 channels per thread.
+// dqpad[h, d] += sum_m de[b,h,t] key[m,d].  Grid (ldk/256, rows/256): a lane owns 8 channels (16-byte accesses), a warp
+// walks 32 rows two at a time, the block's [H, 256] slice of qpad sits in shared memory, the per-head partial sums of dqpad
+// stay in registers (HT = H rounded up to 1 / 2 / 4 / 8 / 16) and leave through one cross-warp reduction and H * 256 global
+// atomics per 256 rows.  (Round 1 used 64-row blocks of 128 channels with 8-byte accesses: 4800 blocks, 614 k atomics on
+// 1536 addresses -- 264 us at config 4, the largest single kernel of the attention step.)
+constexpr int ASB_ROWS = 256;
+
+template <int HT>
 __global__ void __launch_bounds__(256) att_scores_bwd_kernel(const __nv_bfloat16* __restrict__ key,
                                                              const float* __restrict__ qpad, const float* __restrict__ de,
                                                              __nv_bfloat16* __restrict__ dkey, float* __restrict__ dqpad,
                                                              int rows, int seg_len, int seg_valid,
                                                              const int* __restrict__ lengths, int H, int ldk, int accumulate) {
   pdl_entry();
-  extern __shared__ float sred[];     // [8][H][128]
+  extern __shared__ float sred[];     // [HT][256] qpad slice, then reused as [8][HT][256] reduction scratch
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 128 + lane * 4;
+  const int cb = blockIdx.x * 256;
+  const int c0 = cb + lane * 8;
   const bool c_ok = c0 < ldk;
-  float qv[ATT_MAX_HEADS][4], acc[ATT_MAX_HEADS][4];
-#pragma unroll
-  for (int h = 0; h < ATT_MAX_HEADS; ++h) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      acc[h][j] = 0.f;
-      qv[h][j] = (h < H && c_ok) ? qpad[static_cast<long long>(h) * ldk + c0 + j] : 0.f;
-    }
-  }
-  if (c_ok) {
-    const int r0 = blockIdx.y * 64;
-    const int r1 = min(r0 + 64, rows);
-    for (int m = r0 + wp; m < r1; m += 8) {
-      const int b = m / seg_len, t = m - b * seg_len;
-      const int L = lengths ? lengths[b] : seg_valid;
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
-      __nv_bfloat16* dst = dkey + static_cast<long long>(m) * ldk + c0;
-      if (t < L) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(key + static_cast<long long>(m) * ldk + c0);
-        const float2 k01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-        const float2 k23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-        const float kv[4] = {k01.x, k01.y, k23.x, k23.y};
-#pragma unroll
-        for (int h = 0; h < ATT_MAX_HEADS; ++h) {
-          if (h < H) {
-            const float d = de[(static_cast<long long>(b) * H + h) * seg_len + t];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              o[j] = fmaf(d, qv[h][j], o[j]);
-              acc[h][j] = fmaf(d, kv[j], acc[h][j]);
-            }
-          }
-        }
-        if (accumulate) {
-          const uint2 pr = *reinterpret_cast<const uint2*>(dst);
-          const float2 p01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr.x));
-          const float2 p23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr.y));
-          o[0] += p01.x; o[1] += p01.y; o[2] += p23.x; o[3] += p23.y;
-        }
-      } else if (accumulate) {
-        continue;
-      }
-      __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), c = __floats2bfloat162_rn(o[2], o[3]);
-      uint2 r;
-      r.x = *reinterpret_cast<uint32_t*>(&a);
-      r.y = *reinterpret_cast<uint32_t*>(&c);
-      *reinterpret_cast<uint2*>(dst) = r;
-    }
-  }
-#pragma unroll
-  for (int h = 0; h < ATT_MAX_HEADS; ++h) {
-    if (h < H) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) sred[(wp * H + h) * 128 + lane * 4 + j] = acc[h][j];
-    }
+  for (int i = threadIdx.x; i < HT * 256; i += 256) {
+    const int h = i >> 8, c = cb + (i & 255);
+    sred[i] = (h < H && c < ldk) ? qpad[static_cast<long long>(h) * ldk + c] : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < H * 128; i += 256) {
-    const int h = i / 128, cc = i % 128;
-    const int c = blockIdx.x * 128 + cc;
+  float qv[HT][8], acc[HT][8];
+#pragma unroll
+  for (int h = 0; h < HT; ++h) {
+    a_load8f(sred + h * 256 + lane * 8, qv[h]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[h][j] = 0.f;
+  }
+  __syncthreads();                     // the slice is in registers: the scratch may be overwritten below
+  if (c_ok) {
+    const int r0 = blockIdx.y * ASB_ROWS;
+    const int r1 = min(r0 + ASB_ROWS, rows);
+    for (int mb = r0 + wp; mb < r1; mb += 16) {
+      float kv[2][8], dh[2][HT];
+      bool live[2], inb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {           // two independent rows in flight per warp
+        const int m = mb + 8 * u;
+        inb[u] = m < r1;
+        live[u] = false;
+        if (inb[u]) {
+          const int b = m / seg_len, t = m - b * seg_len;
+          const int L = lengths ? lengths[b] : seg_valid;
+          live[u] = t < L;
+          if (live[u]) {
+            a_load8(key + static_cast<long long>(m) * ldk + c0, kv[u]);
+#pragma unroll
+            for (int h = 0; h < HT; ++h) dh[u][h] = (h < H) ? de[(static_cast<long long>(b) * H + h) * seg_len + t] : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!inb[u]) continue;
+        const int m = mb + 8 * u;
+        __nv_bfloat16* dst = dkey + static_cast<long long>(m) * ldk + c0;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        if (live[u]) {
+#pragma unroll
+          for (int h = 0; h < HT; ++h) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[j] = fmaf(dh[u][h], qv[h][j], o[j]);
+              acc[h][j] = fmaf(dh[u][h], kv[u][j], acc[h][j]);
+            }
+          }
+          if (accumulate) {
+            float prev[8];
+            a_load8(dst, prev);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += prev[j];
+          }
+        } else if (accumulate) {
+          continue;
+        }
+        a_store8(dst, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < HT; ++h) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sred[(wp * HT + h) * 256 + lane * 8 + j] = acc[h][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * 256; i += 256) {
+    const int h = i >> 8, cc = i & 255;
+    const int c = cb + cc;
     if (c < ldk) {
       float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s += sred[(k * H + h) * 128 + cc];
+      for (int k = 0; k < 8; ++k) s += sred[(k * HT + h) * 256 + cc];
       atomicAdd(dqpad + static_cast<long long>(h) * ldk + c, s);
     }
   }
@@ -547,15 +646,24 @@ extern "C" int xv_att_pool_bwd(const void* value, const float* weights, const fl
   if (smem > 48 * 1024) {
     static bool configured = false;
     if (!configured) {
-      XV_CUDA_CHECK(cudaFuncSetAttribute(att_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      XV_CUDA_CHECK(cudaFuncSetAttribute(att_pool_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      XV_CUDA_CHECK(cudaFuncSetAttribute(att_pool_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      XV_CUDA_CHECK(cudaFuncSetAttribute(att_pool_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
     if (smem > 200 * 1024) return set_error(XV_ERR_UNSUPPORTED, "xv_att_pool_bwd: value dim too large");
   }
   dim3 grid(ceil_div(seg_len, 64), B);
-  ::xv::launch_pdl((att_pool_bwd_kernel), grid, 256, smem, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(value), weights, pooled, dpooled, static_cast<__nv_bfloat16*>(dvalue), dweights, H,
-      seg_len, seg_valid, lengths, c_real, cpad, ld, accumulate);
+#define XV_APB_ARGS static_cast<const __nv_bfloat16*>(value), weights, pooled, dpooled, static_cast<__nv_bfloat16*>(dvalue), \
+                    dweights, H, seg_len, seg_valid, lengths, c_real, cpad, ld, accumulate
+  cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+  if (H == 1 && cpad <= 2048) {
+    if (accumulate) ::xv::launch_pdl((att_pool_bwd_kernel<true, true>), grid, 256, smem, s_, XV_APB_ARGS);
+    else ::xv::launch_pdl((att_pool_bwd_kernel<true, false>), grid, 256, smem, s_, XV_APB_ARGS);
+  } else {
+    ::xv::launch_pdl((att_pool_bwd_kernel<false, false>), grid, 256, smem, s_, XV_APB_ARGS);
+  }
+#undef XV_APB_ARGS
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
@@ -588,18 +696,32 @@ extern "C" int xv_att_scores_bwd(const void* key, const float* qpad, const float
   int rc = att_check_heads("xv_att_scores_bwd", H); if (rc) return rc;
   const long long rows = static_cast<long long>(B) * seg_len;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_att_scores_bwd: rows must fit in int32");
-  const size_t smem = static_cast<size_t>(8) * H * 128 * sizeof(float);
-  if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      XV_CUDA_CHECK(cudaFuncSetAttribute(att_scores_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      configured = true;
-    }
+  const int ht = H <= 1 ? 1 : (H <= 2 ? 2 : (H <= 4 ? 4 : (H <= 8 ? 8 : 16)));
+  const size_t smem = static_cast<size_t>(8) * ht * 256 * sizeof(float);
+  dim3 grid(ceil_div(ldk, 256), ceil_div(rows, ASB_ROWS));
+  cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+#define XV_ASB_LAUNCH(HT_)                                                                                                   \
+  do {                                                                                                                       \
+    if (smem > 48 * 1024) {                                                                                                  \
+      static bool configured = false;                                                                                       \
+      if (!configured) {                                                                                                     \
+        XV_CUDA_CHECK(cudaFuncSetAttribute(att_scores_bwd_kernel<HT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                           static_cast<int>(smem)));                                                         \
+        configured = true;                                                                                                   \
+      }                                                                                                                      \
+    }                                                                                                                        \
+    ::xv::launch_pdl((att_scores_bwd_kernel<HT_>), grid, 256, smem, s_, static_cast<const __nv_bfloat16*>(key), qpad, dscores,  \
+                     static_cast<__nv_bfloat16*>(dkey), dqpad, static_cast<int>(rows), seg_len, seg_valid, lengths, H, ldk,  \
+                     accumulate);                                                                                            \
+  } while (0)
+  switch (ht) {
+    case 1: XV_ASB_LAUNCH(1); break;
+    case 2: XV_ASB_LAUNCH(2); break;
+    case 4: XV_ASB_LAUNCH(4); break;
+    case 8: XV_ASB_LAUNCH(8); break;
+    default: XV_ASB_LAUNCH(16); break;
   }
-  dim3 grid(ceil_div(ldk, 128), ceil_div(rows, 64));
-  ::xv::launch_pdl((att_scores_bwd_kernel), grid, 256, smem, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(key), qpad, dscores, static_cast<__nv_bfloat16*>(dkey), dqpad,
-      static_cast<int>(rows), seg_len, seg_valid, lengths, H, ldk, accumulate);
+#undef XV_ASB_LAUNCH
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
