@@ -1,7 +1,8 @@
-"""The reference's callers, unmodified apart from the imports: the epoch loop of
-egs/voxceleb/v1/nnet/lib/train.py:83-136 -- Trainer.train(data_dir, spklist, lr) / Trainer.valid(data_dir, spklist, ...)
-on a synthetic Kaldi directory of compressed archives, variable segment lengths, checkpoints, learning-rate / valid-loss
-bookkeeping -- and the command line of nnet/lib/extract.py:11-96 that wrap/extract_wrapper.sh invokes."""
+"""The reference's entry points on a synthetic Kaldi directory of compressed archives: the
+training driver with the command line of egs/voxceleb/v1/nnet/lib/train.py:13-23 -- epochs of Trainer.train(data_dir,
+spklist, lr) / Trainer.valid(data_dir, spklist, ...), variable segment lengths, checkpoints, the learning_rate / valid_loss
+/ feature_dim files, ``-c`` continuation -- and the command line of nnet/lib/extract.py:11-96 that wrap/extract_wrapper.sh
+invokes."""
 import json
 import os
 
