@@ -116,6 +116,62 @@ __global__ void __launch_bounds__(256) att_scores_fwd_kernel(const __nv_bfloat16
   }
 }
 
+// Same scores, ldk <= 2048 and H * ldk floats of shared memory: the query sits in shared memory, a warp takes four frames of a
+// 32-frame block and issues all of a frame's 16-byte loads (kept packed) before the first use.  The kernel above keeps one
+// load in flight per lane and leaves after one frame (46 us for 78 MB at config 4).
+template <int HT>
+__global__ void __launch_bounds__(256) att_scores_fwd_fast_kernel(const __nv_bfloat16* __restrict__ key,
+                                                                  const float* __restrict__ qpad, float* __restrict__ scores,
+                                                                  int rows, int seg_len, int seg_valid,
+                                                                  const int* __restrict__ lengths, int H, int ldk, float scale) {
+  pdl_entry();
+  extern __shared__ float sq[];       // [H][ldk]
+  for (int i = threadIdx.x; i < H * ldk; i += 256) sq[i] = qpad[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int f = 0; f < 4; ++f) {
+    const int m = blockIdx.x * 32 + f * 8 + wp;
+    if (m >= rows) break;
+    const int b = m / seg_len, t = m - b * seg_len;
+    const int L = lengths ? lengths[b] : seg_valid;
+    if (t >= L) continue;
+    const __nv_bfloat16* kr = key + static_cast<long long>(m) * ldk;
+    ABf16x8 raw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c0 = lane * 8 + 256 * i;
+      if (c0 < ldk) raw[i] = *reinterpret_cast<const ABf16x8*>(kr + c0);
+    }
+    float acc[HT];
+#pragma unroll
+    for (int h = 0; h < HT; ++h) acc[h] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c0 = lane * 8 + 256 * i;
+      if (c0 < ldk) {
+        float kv[8];
+        a_unpack8(raw[i], kv);
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          if (h < H) {
+            float qv[8];
+            a_load8f(sq + h * ldk + c0, qv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[h] = fmaf(kv[j], qv[j], acc[h]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < HT; ++h) {
+      if (h < H) {
+        const float s = warp_sum(acc[h]);
+        if (lane == 0) scores[(static_cast<long long>(b) * H + h) * seg_len + t] = s * scale;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // softmax over the valid frames of one (segment, head); frames >= L get weight 0.  In place allowed.
 __global__ void __launch_bounds__(256) att_softmax_fwd_kernel(const float* __restrict__ scores, float* __restrict__ w,
@@ -604,8 +660,36 @@ extern "C" int xv_att_scores_fwd(const void* key, const float* qpad, float* scor
   int rc = att_check_heads("xv_att_scores_fwd", H); if (rc) return rc;
   const long long rows = static_cast<long long>(B) * seg_len;
   if (rows > 0x7fffffffLL) return set_error(XV_ERR_INVALID, "xv_att_scores_fwd: rows must fit in int32");
-  ::xv::launch_pdl((att_scores_fwd_kernel), ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(key), qpad, scores, static_cast<int>(rows), seg_len, seg_valid, lengths, H, ldk, scale);
+  cudaStream_t s_ = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(H) * ldk * sizeof(float);
+  if (ldk <= 2048 && smem <= 96 * 1024) {
+    const int ht = H <= 1 ? 1 : (H <= 2 ? 2 : (H <= 4 ? 4 : (H <= 8 ? 8 : 16)));
+#define XV_ASF_LAUNCH(HT_)                                                                                                    \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) {                                                                                                   \
+      static bool configured = false;                                                                                        \
+      if (!configured) {                                                                                                      \
+        XV_CUDA_CHECK(cudaFuncSetAttribute(att_scores_fwd_fast_kernel<HT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                           96 * 1024));                                                                       \
+        configured = true;                                                                                                    \
+      }                                                                                                                       \
+    }                                                                                                                         \
+    ::xv::launch_pdl((att_scores_fwd_fast_kernel<HT_>), ceil_div(rows, 32), 256, smem, s_,                                     \
+                     static_cast<const __nv_bfloat16*>(key), qpad, scores, static_cast<int>(rows), seg_len, seg_valid, lengths, \
+                     H, ldk, scale);                                                                                          \
+  } while (0)
+    switch (ht) {
+      case 1: XV_ASF_LAUNCH(1); break;
+      case 2: XV_ASF_LAUNCH(2); break;
+      case 4: XV_ASF_LAUNCH(4); break;
+      case 8: XV_ASF_LAUNCH(8); break;
+      default: XV_ASF_LAUNCH(16); break;
+    }
+#undef XV_ASF_LAUNCH
+  } else {
+    ::xv::launch_pdl((att_scores_fwd_kernel), ceil_div(rows, 8), 256, 0, s_, static_cast<const __nv_bfloat16*>(key), qpad, scores,
+                     static_cast<int>(rows), seg_len, seg_valid, lengths, H, ldk, scale);
+  }
   XV_CUDA_CHECK(cudaGetLastError());
   return XV_OK;
 }
