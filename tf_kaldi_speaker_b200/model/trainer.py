@@ -8,6 +8,7 @@ feature pipeline (dataset/data_loader.py) stays on the host: ``train``/``valid``
 """
 import ctypes as C
 import glob
+import gc
 import os
 import re
 import sys
@@ -361,10 +362,16 @@ class Trainer(object):
             if self.use_cuda_graph and st["calls"] > warm:
                 l0 = eng.launches
                 eng.capturing = True
+                # Capture in "thread_local" error mode with the garbage collector paused: in the default "global" mode ANY
+                # thread's unsafe CUDA call invalidates the capture -- the loader's feeder thread (pinned allocations, event
+                # synchronisation) runs beside the step, and a collection pass that finalises a stale event or pinned buffer
+                # in the middle of the capture does the same (seen once in ~3 full test runs).
+                gc_was_on = gc.isenabled()
+                gc.disable()
                 try:
                     ga = torch.cuda.CUDAGraph()
                     gb = None
-                    with torch.cuda.graph(ga):
+                    with torch.cuda.graph(ga, capture_error_mode="thread_local"):
                         part_a()
                         if self.dp is None:
                             part_b()
@@ -373,10 +380,12 @@ class Trainer(object):
                             part_b()
                     if self.dp is not None and not in_graph_exchange:
                         gb = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(gb):
+                        with torch.cuda.graph(gb, capture_error_mode="thread_local"):
                             part_b()
                 finally:
                     eng.capturing = False
+                    if gc_was_on:
+                        gc.enable()
                 st["launches"] = eng.launches - l0
                 st["graphs"] = (ga, gb)
                 st["gen"] = eng.ws_generation

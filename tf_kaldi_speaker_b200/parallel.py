@@ -164,7 +164,7 @@ class SegmentedGraph(object):
 
     def _open(self):
         self._g = torch.cuda.CUDAGraph()
-        self._ctx = torch.cuda.graph(self._g, pool=self.pool, stream=self.stream)
+        self._ctx = torch.cuda.graph(self._g, pool=self.pool, stream=self.stream, capture_error_mode="thread_local")
         self._ctx.__enter__()
 
     def _close(self):
