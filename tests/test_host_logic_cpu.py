@@ -99,3 +99,31 @@ def test_extraction_chunking_rule():
     ln = torch.tensor(lens, dtype=torch.float64).unsqueeze(1)
     assert torch.allclose(e, (embs * ln).sum(0) / ln.sum(), rtol=1e-10)
     assert O.extract_embedding(x[:20], P, po, chunk_size=50, min_chunk_size=25) is None
+
+
+def test_extraction_packers_lay_out_batches_exactly():
+    """extract._pack_ragged (padding-free layout: chunks back to back + (starts, lengths)) and extract._pack (zero-padded
+    [N, tmax, D] + lengths), including the multi-threaded copy path and slot reuse with a smaller batch."""
+    from tf_kaldi_speaker_b200 import extract as X
+    rng = np.random.RandomState(3)
+    lens = [25, 300, 7000, 26, 513, 9000, 100, 4000, 64, 2500, 1200, 33, 800, 5000]
+    jobs = [(i, 0, rng.randn(n, 30).astype(np.float32)) for i, n in enumerate(lens)]
+    slot = {"buf": None, "event": None}
+    old_threads = X._COPY_THREADS
+    try:
+        for threads, group in ((1, list(range(len(jobs)))), (4, list(range(len(jobs)))), (4, [5, 2, 9])):
+            X._COPY_THREADS, X._copy_executor = threads, None
+            flat, (starts, lengths) = X._pack_ragged(slot, group, jobs, 30)
+            assert flat.shape == (sum(lens[j] for j in group), 30)
+            assert list(lengths) == [lens[j] for j in group]
+            assert list(starts) == list(np.concatenate([[0], np.cumsum([lens[j] for j in group])[:-1]]))
+            for k, j in enumerate(group):
+                assert np.array_equal(flat.numpy()[starts[k]:starts[k] + lengths[k]], jobs[j][2])
+    finally:
+        X._COPY_THREADS, X._copy_executor = old_threads, None
+    group = [0, 3, 11, 8]
+    batch, lengths = X._pack({"buf": None, "event": None}, group, jobs, 256, 30)
+    assert batch.shape == (4, 256, 30) and list(lengths) == [25, 26, 33, 64]
+    for r, j in enumerate(group):
+        assert np.array_equal(batch.numpy()[r, :lens[j]], jobs[j][2])
+        assert not batch.numpy()[r, lens[j]:].any()
