@@ -4,6 +4,7 @@ tests/golden/make_golden.py produced from the REFERENCE's NumPy known-answer fun
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import xvector_oracle as O
@@ -119,6 +120,35 @@ def test_metric_losses_match_reference_numpy(golden_dir):
         assert np.allclose(float(O.angular_triplet_loss(x, lab, p)), want, rtol=1e-7 if int(code) == 2 else 1e-9)
     p = O.ParamsPlain(num_valid_speakers_per_batch=int(g["num_speakers"]), num_valid_segments_per_speaker=int(g["num_segments"]))
     assert np.allclose(float(O.e2e_valid_loss(x, lab, p)), float(g["e2e/loss"]), rtol=1e-9)
+
+
+def test_generalized_triplet_matches_reference_numpy(golden_dir):
+    """generalized_angular_triplet_loss (model/loss.py:708-901) against model/test_utils.py:653-852
+    compute_generalized_triplet_loss: triplet / centre / between-class parts for learnable and moving-average centres,
+    top-n = 1, 0, k, and the updated centres themselves."""
+    g = np.load(os.path.join(golden_dir, "gtriplet.npz"))
+    w = torch.from_numpy(g["w"].astype(np.float64))
+    for ci, (avg, topn, m, tm) in enumerate(g["cases"]):
+        lab = torch.from_numpy(g["case%d/labels" % ci].astype(np.int64))
+        x = torch.from_numpy(g["emb"][:len(lab)].astype(np.float64))
+        p = O.ParamsPlain(triplet_center="average" if avg else "learnable", triplet_center_momentum=0.9, loss_compute="raw",
+                          triplet_topn=int(topn), margin=float(m), target_margin=float(tm), triplet_loss_weight=1.0,
+                          center_loss_weight=0.5, between_loss_weight=0.25, l2_loss_weight=0.0)
+        updates = {}
+        loss, parts = O.generalized_angular_triplet_loss(x, lab, {"softmax/output/kernel": w.clone()}, p, True, updates)
+        want = g["case%d/parts" % ci]
+        got = [float(parts[k]) for k in ("triplet_loss", "center_loss", "between_loss")]
+        assert np.allclose(got, want, rtol=1e-9), (ci, got, want)
+        assert np.allclose(float(loss), want[0] + 0.5 * want[1] + 0.25 * want[2], rtol=1e-9)
+        assert np.allclose(parts["average_centers"].numpy(), g["case%d/w_update" % ci], rtol=1e-12, atol=1e-14)
+        assert ("softmax/output/kernel" in updates) == bool(avg)
+        # validation graph: averaged centres are NOT updated when is_training is False
+        _, pv = O.generalized_angular_triplet_loss(x, lab, {"softmax/output/kernel": w.clone()}, p, False, {})
+        assert torch.equal(pv["average_centers"], w)
+    p = O.ParamsPlain(triplet_center="learnable", loss_compute="softplus", triplet_topn=1, margin=0.1, target_margin=0.0,
+                      triplet_loss_weight=1.0, center_loss_weight=0.0, between_loss_weight=0.0, l2_loss_weight=0.0)
+    with pytest.raises(NotImplementedError):          # loss.py:826
+        O.generalized_angular_triplet_loss(x, lab, {"softmax/output/kernel": w}, p, True, {})
 
 
 def test_aux_losses_match_reference_numpy(golden_dir):
